@@ -1,0 +1,108 @@
+"""ctypes binding of libbde2vid_sm100.so (the C ABI declared in include/bde2vid.h).
+
+There is no CPU fallback anywhere in this package: if the shared library is missing or the
+device is not a Blackwell-class GPU the ops raise.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbde2vid_sm100.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_RELU6, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
+EPI_STORE, EPI_LSTM, EPI_SCATTER = 0, 1, 2
+ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
+
+TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16}
+BDE_DTYPE = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+class GemmDesc(C.Structure):
+    """Mirror of ``struct bde_gemm_desc``."""
+    _fields_ = [
+        ("engine", C.c_int), ("dtype", C.c_int),
+        ("a0", C.c_void_p), ("a1", C.c_void_p),
+        ("c0", C.c_int), ("c1", C.c_int),
+        ("n_img", C.c_int), ("h_in", C.c_int), ("w_in", C.c_int), ("h_out", C.c_int), ("w_out", C.c_int),
+        ("ksize", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
+        ("w", C.c_void_p), ("bias", C.c_void_p),
+        ("n", C.c_int), ("w_ld", C.c_int),
+        ("epi", C.c_int), ("act", C.c_int), ("out_f32", C.c_int),
+        ("out", C.c_void_p), ("residual", C.c_void_p), ("c_prev", C.c_void_p), ("c_out", C.c_void_p),
+        ("row_map", C.c_void_p), ("out2", C.c_void_p),
+    ]
+
+
+EXPORTS = {
+    "bde_last_error": (C.c_char_p, []),
+    "bde_abi_version": (C.c_int, []),
+    "bde_device_ok": (C.c_int, []),
+    "bde_voxelize_seq": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "bde_pack_voxel_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_void_p]),
+    "bde_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "bde_add": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                          C.c_void_p]),
+    "bde_upsample2x_sum": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float] + [C.c_int] * 4
+                           + [C.c_void_p, C.c_int, C.c_void_p]),
+    "bde_pred_sigmoid": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]),
+    "bde_ln_gather": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "bde_layernorm": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                C.c_void_p]),
+    "bde_window_attention": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_void_p]),
+    "bde_cast": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "libbde2vid_sm100.so is not built (%s). Run `python -m bde2vid_b200.build`; "
+            "there is no CPU or PyTorch fallback for this path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.bde_abi_version() != 1:
+        raise RuntimeError("libbde2vid_sm100.so ABI mismatch")
+    _lib = lib
+    return lib
+
+
+def require_device():
+    """Raise unless CUDA is available and the current device is compute capability 10.x."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("bde2vid_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
+    lib = load()
+    ok = lib.bde_device_ok()
+    if ok != 1:
+        raise RuntimeError("bde2vid_b200 kernels are built for sm_100a only (device check returned %d: %s)"
+                           % (ok, lib.bde_last_error().decode()))
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what or "bde call", rc, load().bde_last_error().decode()))
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "bde2vid_b200 ops need contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())

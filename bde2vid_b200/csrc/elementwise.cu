@@ -1,0 +1,274 @@
+// Bandwidth-bound kernels around the GEMMs: bidirectional merge, bilinear x2 + skip sum,
+// prediction head, window-token gather + LayerNorm, row LayerNorm, casts.
+#include "common.cuh"
+
+namespace bde {
+
+// ---------------------------------------------------------------------------------------------
+// out = a + b   (ff + fb, bde2vid_cross_scale_propogation_V5.py:144)
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename TA, typename TB>
+__global__ void add_kernel(const TA* a, const TB* b, float* out_f32, T* out_t, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 x = load4<TA>(a + i * 4), y = load4<TB>(b + i * 4);
+  float4 s = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+  if (out_f32 != nullptr) store4<float>(out_f32 + i * 4, s);
+  if (out_t != nullptr) store4<T>(out_t + i * 4, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dst = bilinear_x2(skip + x_scale * x), align_corners=False (submodules.py:138):
+//   out[2i]   = .25*in[max(i-1,0)] + .75*in[i]
+//   out[2i+1] = .75*in[i]          + .25*in[min(i+1,n-1)]
+// F.interpolate computes source index (dst+0.5)/2-0.5 clamped at 0, lambda from it; the weights
+// above are the exact values of that formula for scale 2.
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename TS, typename TX>
+__global__ void upsample2x_sum_kernel(const TS* __restrict__ skip, const TX* __restrict__ x, float x_scale,
+                                      int h, int w, int c4, T* __restrict__ dst, size_t total) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over n_img * 2h * 2w * c4
+  if (i >= total) return;
+  int cq = (int)(i % c4);
+  size_t pix = i / c4;
+  int ox = (int)(pix % (2 * w));
+  size_t r = pix / (2 * w);
+  int oy = (int)(r % (2 * h));
+  size_t img = r / (2 * h);
+  // source taps
+  int y0, y1, x0, x1;
+  float wy0, wy1, wx0, wx1;
+  if (oy & 1) { y0 = oy >> 1; y1 = min(y0 + 1, h - 1); wy0 = 0.75f; wy1 = 0.25f; }
+  else        { y1 = oy >> 1; y0 = max(y1 - 1, 0);     wy0 = 0.25f; wy1 = 0.75f; }
+  if (ox & 1) { x0 = ox >> 1; x1 = min(x0 + 1, w - 1); wx0 = 0.75f; wx1 = 0.25f; }
+  else        { x1 = ox >> 1; x0 = max(x1 - 1, 0);     wx0 = 0.25f; wx1 = 0.75f; }
+  auto fetch = [&](int yy, int xx) {
+    size_t o = (((size_t)img * h + yy) * w + xx) * (size_t)(c4 * 4) + cq * 4;
+    float4 v = load4<TX>(x + o);
+    v.x *= x_scale; v.y *= x_scale; v.z *= x_scale; v.w *= x_scale;
+    if (skip != nullptr) {
+      float4 s = load4<TS>(skip + o);
+      v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+    }
+    return v;
+  };
+  float4 a = fetch(y0, x0), b = fetch(y0, x1), cc = fetch(y1, x0), d = fetch(y1, x1);
+  // torch: horizontal lerp inside vertical lerp: w_y0*(w_x0*a + w_x1*b) + w_y1*(w_x0*c + w_x1*d)
+  float4 o;
+  o.x = wy0 * (wx0 * a.x + wx1 * b.x) + wy1 * (wx0 * cc.x + wx1 * d.x);
+  o.y = wy0 * (wx0 * a.y + wx1 * b.y) + wy1 * (wx0 * cc.y + wx1 * d.y);
+  o.z = wy0 * (wx0 * a.z + wx1 * b.z) + wy1 * (wx0 * cc.z + wx1 * d.z);
+  o.w = wy0 * (wx0 * a.w + wx1 * b.w) + wy1 * (wx0 * cc.w + wx1 * d.w);
+  store4<T>(dst + pix * (size_t)(c4 * 4) + cq * 4, o);
+}
+
+// ---------------------------------------------------------------------------------------------
+// img = sigmoid(bias + wt . (x + head))   (predI 1x1 conv + Sigmoid, ...V5.py:195-197)
+// one thread per pixel; c <= 256, multiple of 4
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pred_sigmoid_kernel(const T* __restrict__ x, const T* __restrict__ head,
+                                    const float* __restrict__ wt, const float* __restrict__ bias, int c,
+                                    size_t n_pix, float* __restrict__ img) {
+  extern __shared__ float sw[];
+  for (int i = threadIdx.x; i < c; i += blockDim.x) sw[i] = wt[i];
+  __syncthreads();
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pix) return;
+  float acc = bias[0];
+  const T* xp = x + p * c;
+  const T* hp = head + p * c;
+  for (int k = 0; k < c; k += 4) {
+    float4 a = load4<T>(xp + k), b = load4<T>(hp + k);
+    acc = fmaf(sw[k + 0], a.x + b.x, acc);
+    acc = fmaf(sw[k + 1], a.y + b.y, acc);
+    acc = fmaf(sw[k + 2], a.z + b.z, acc);
+    acc = fmaf(sw[k + 3], a.w + b.w, acc);
+  }
+  img[p] = sigmoid_f(acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm helpers: one warp per row of c <= 1024 channels (c % 32 == 0 not required)
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxPerLane = 32;  // c <= 1024
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ void ln_row(const float* __restrict__ src /* may be nullptr = zeros */, int c,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       T* __restrict__ dst, int lane) {
+  float v[kMaxPerLane];
+  int cnt = 0;
+  float s = 0.f;
+  for (int k = lane; k < c; k += 32, ++cnt) {
+    v[cnt] = src != nullptr ? src[k] : 0.f;
+    s += v[cnt];
+  }
+  float mean = warp_sum(s) / (float)c;
+  float q = 0.f;
+  for (int i = 0; i < cnt; ++i) {
+    float d = v[i] - mean;
+    q += d * d;
+  }
+  float var = warp_sum(q) / (float)c;
+  float rstd = 1.0f / sqrtf(var + 1e-5f);
+  int i = 0;
+  for (int k = lane; k < c; k += 32, ++i) dst[k] = from_f32<T>((v[i] - mean) * rstd * gamma[k] + beta[k]);
+}
+
+struct FramePtrs {
+  const float* f[8];
+};
+
+// window_partition (DTransformer.py:41-60) + norm_q / norm_kv (:183-184)
+template <typename T>
+__global__ void ln_gather_kernel(FramePtrs frames, int D, const int* __restrict__ tok_map, int n_tok, int c,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 T* __restrict__ out, size_t total_rows) {
+  size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // (win, d, tok)
+  int lane = threadIdx.x & 31;
+  if (row >= total_rows) return;
+  int tok = (int)(row % n_tok);
+  size_t r = row / n_tok;
+  int d = (int)(r % D);
+  size_t win = r / D;
+  int pix = tok_map[win * n_tok + tok];
+  const float* fr = frames.f[d];
+  const float* src = (fr != nullptr && pix >= 0) ? fr + (size_t)pix * c : nullptr;
+  ln_row<T>(src, c, gamma, beta, out + row * c, lane);
+}
+
+template <typename T>
+__global__ void layernorm_kernel(const float* __restrict__ x, size_t rows, int c, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, T* __restrict__ out) {
+  size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  ln_row<T>(x + row * c, c, gamma, beta, out + row * c, lane);
+}
+
+template <typename TS, typename TD>
+__global__ void cast_kernel(const TS* __restrict__ src, TD* __restrict__ dst, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = from_f32<TD>(to_f32<TS>(src[i]));
+}
+
+}  // namespace bde
+
+using namespace bde;
+
+template <typename T>
+static int launch_add(const void* a, int a_f32, const void* b, int b_f32, float* out_f32, void* out_t, size_t n4,
+                      cudaStream_t s) {
+  unsigned blocks = (unsigned)ceil_div(n4, 256);
+  if (a_f32 && b_f32)
+    add_kernel<T, float, float><<<blocks, 256, 0, s>>>((const float*)a, (const float*)b, out_f32, (T*)out_t, n4);
+  else if (a_f32 && !b_f32)
+    add_kernel<T, float, T><<<blocks, 256, 0, s>>>((const float*)a, (const T*)b, out_f32, (T*)out_t, n4);
+  else if (!a_f32 && b_f32)
+    add_kernel<T, T, float><<<blocks, 256, 0, s>>>((const T*)a, (const float*)b, out_f32, (T*)out_t, n4);
+  else
+    add_kernel<T, T, T><<<blocks, 256, 0, s>>>((const T*)a, (const T*)b, out_f32, (T*)out_t, n4);
+  return check_launch("add_kernel");
+}
+
+extern "C" int bde_add(const void* a, int a_f32, const void* b, int b_f32, float* out_f32, void* out_t, size_t n,
+                       int dtype, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  BDE_REQUIRE(n % 4 == 0, "bde_add: n must be a multiple of 4");
+  BDE_REQUIRE(a != nullptr && b != nullptr, "bde_add: null input");
+  if (n == 0) return 0;
+  if (dtype == BDE_F32) return launch_add<float>(a, 1, b, 1, out_f32, out_t, n / 4, s);
+  return launch_add<__nv_bfloat16>(a, a_f32, b, b_f32, out_f32, out_t, n / 4, s);
+}
+
+template <typename T>
+static int launch_upsample(const void* skip, int skip_f32, const void* x, int x_f32, float x_scale, int n_img, int h,
+                           int w, int c, void* dst, cudaStream_t s) {
+  size_t total = (size_t)n_img * 2 * h * 2 * w * (c / 4);
+  unsigned blocks = (unsigned)ceil_div(total, 256);
+  T* d = (T*)dst;
+  if (skip_f32 && x_f32)
+    upsample2x_sum_kernel<T, float, float><<<blocks, 256, 0, s>>>((const float*)skip, (const float*)x, x_scale, h, w, c / 4, d, total);
+  else if (skip_f32 && !x_f32)
+    upsample2x_sum_kernel<T, float, T><<<blocks, 256, 0, s>>>((const float*)skip, (const T*)x, x_scale, h, w, c / 4, d, total);
+  else if (!skip_f32 && x_f32)
+    upsample2x_sum_kernel<T, T, float><<<blocks, 256, 0, s>>>((const T*)skip, (const float*)x, x_scale, h, w, c / 4, d, total);
+  else
+    upsample2x_sum_kernel<T, T, T><<<blocks, 256, 0, s>>>((const T*)skip, (const T*)x, x_scale, h, w, c / 4, d, total);
+  return check_launch("upsample2x_sum_kernel");
+}
+
+extern "C" int bde_upsample2x_sum(const void* skip, int skip_f32, const void* x, int x_f32, float x_scale, int n_img,
+                                  int h, int w, int c, void* dst, int dtype, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  BDE_REQUIRE(c % 4 == 0, "bde_upsample2x_sum: c must be a multiple of 4");
+  BDE_REQUIRE(x != nullptr && dst != nullptr, "bde_upsample2x_sum: null pointer");
+  if (n_img == 0) return 0;
+  if (dtype == BDE_F32) return launch_upsample<float>(skip, 1, x, 1, x_scale, n_img, h, w, c, dst, s);
+  return launch_upsample<__nv_bfloat16>(skip, skip_f32, x, x_f32, x_scale, n_img, h, w, c, dst, s);
+}
+
+extern "C" int bde_pred_sigmoid(const void* x, const void* head, const float* wt, const float* bias, int c,
+                                size_t n_pix, float* img, int dtype, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  BDE_REQUIRE(c % 4 == 0 && c <= 4096, "bde_pred_sigmoid: bad channel count");
+  if (n_pix == 0) return 0;
+  unsigned blocks = (unsigned)ceil_div(n_pix, 128);
+  if (dtype == BDE_F32)
+    pred_sigmoid_kernel<float><<<blocks, 128, c * sizeof(float), s>>>((const float*)x, (const float*)head, wt, bias, c, n_pix, img);
+  else
+    pred_sigmoid_kernel<__nv_bfloat16><<<blocks, 128, c * sizeof(float), s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)head, wt, bias, c, n_pix, img);
+  return check_launch("pred_sigmoid_kernel");
+}
+
+extern "C" int bde_ln_gather(const float* const* frames_host, int D, const int* tok_map, int n_win, int n_tok, int c,
+                             const float* gamma, const float* beta, void* out, int dtype, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  BDE_REQUIRE(D >= 1 && D <= 8, "bde_ln_gather: D must be in [1, 8]");
+  BDE_REQUIRE(c <= 32 * kMaxPerLane, "bde_ln_gather: c too large");
+  FramePtrs fp;
+  for (int i = 0; i < 8; ++i) fp.f[i] = i < D ? frames_host[i] : nullptr;
+  size_t rows = (size_t)n_win * D * n_tok;
+  if (rows == 0) return 0;
+  unsigned blocks = (unsigned)ceil_div(rows * 32, 256);
+  if (dtype == BDE_F32)
+    ln_gather_kernel<float><<<blocks, 256, 0, s>>>(fp, D, tok_map, n_tok, c, gamma, beta, (float*)out, rows);
+  else
+    ln_gather_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(fp, D, tok_map, n_tok, c, gamma, beta, (__nv_bfloat16*)out, rows);
+  return check_launch("ln_gather_kernel");
+}
+
+extern "C" int bde_layernorm(const float* x, size_t rows, int c, const float* gamma, const float* beta, void* out,
+                             int dtype, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  BDE_REQUIRE(c <= 32 * kMaxPerLane, "bde_layernorm: c too large");
+  if (rows == 0) return 0;
+  unsigned blocks = (unsigned)ceil_div(rows * 32, 256);
+  if (dtype == BDE_F32)
+    layernorm_kernel<float><<<blocks, 256, 0, s>>>(x, rows, c, gamma, beta, (float*)out);
+  else
+    layernorm_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(x, rows, c, gamma, beta, (__nv_bfloat16*)out);
+  return check_launch("layernorm_kernel");
+}
+
+extern "C" int bde_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n == 0) return 0;
+  unsigned blocks = (unsigned)ceil_div(n, 256);
+  if (src_dtype == BDE_F32 && dst_dtype == BDE_BF16)
+    cast_kernel<float, __nv_bfloat16><<<blocks, 256, 0, s>>>((const float*)src, (__nv_bfloat16*)dst, n);
+  else if (src_dtype == BDE_BF16 && dst_dtype == BDE_F32)
+    cast_kernel<__nv_bfloat16, float><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  else if (src_dtype == BDE_F32 && dst_dtype == BDE_F32)
+    cast_kernel<float, float><<<blocks, 256, 0, s>>>((const float*)src, (float*)dst, n);
+  else
+    BDE_REQUIRE(false, "bde_cast: unsupported dtype pair");
+  return check_launch("cast_kernel");
+}

@@ -1,0 +1,275 @@
+// Event -> voxel-grid kernels (HBM-bound scatter).
+//
+// Replaces events_to_voxel_torch / events_to_image_torch
+// (reference: events_contrast_maximization/utils/event_utils.py:466-509, :330-376) for a whole
+// sequence of windows per launch, writing straight into the zero-padded grid that Croper.pad
+// (utils_func/inference_utils.py:104-111) would produce.
+//
+// Arithmetic contract (bit-exact bin indices):
+//   dt = ts[last] - ts[first];  tn = ((t - ts[first]) / dt) * (B-1)      -- fp32, that op order
+//   for every bin b: w = p * max(0, 1 - |tn - b|);  grid[b, int(y), int(x)] += w
+// Only bins floor(tn) and floor(tn)+1 can receive a non-zero weight, so only those are touched.
+// A NaN tn (dt == 0) poisons every bin of the touched pixel exactly like the reference does.
+#include "common.cuh"
+
+namespace bde {
+
+__device__ __forceinline__ float tnorm(float t, float t0, float dt, float bm1) {
+  // __f*_rn intrinsics are never contracted into FMAs and ignore fast-math flags
+  return __fmul_rn(__fdiv_rn(__fsub_rn(t, t0), dt), bm1);
+}
+
+struct EventContrib {
+  int b0;       // left bin (floor(tn)); -1 -> NaN event (all bins)
+  float w0, w1; // weights for b0 and b0+1
+};
+
+__device__ __forceinline__ EventContrib contrib(float t, float p, float t0, float dt, float bm1, int bins) {
+  EventContrib c;
+  float tn = tnorm(t, t0, dt, bm1);
+  if (!(tn == tn)) {  // NaN
+    c.b0 = -1;
+    c.w0 = tn;
+    c.w1 = tn;
+    return c;
+  }
+  float fl = floorf(tn);
+  int b0 = (int)fl;
+  b0 = max(0, min(b0, bins - 1));
+  float fb0 = (float)b0;
+  // w = p * max(0, 1 - |tn - b|), evaluated exactly as written for both bins
+  c.w0 = __fmul_rn(p, fmaxf(0.0f, __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fb0)))));
+  c.w1 = __fmul_rn(p, fmaxf(0.0f, __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fb0 + 1.0f)))));
+  c.b0 = b0;
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Algorithm 1: one CTA per (row band, window).  The CTA scans the window's events once (coalesced,
+// float4-vectorised; re-reads by other bands hit L2), accumulates the events that fall into its
+// band in shared memory, then writes its band of the padded output exactly once, fully coalesced.
+// No memset pass and no global atomics: HBM traffic == algorithmic bytes.
+// Lanes of a warp that hit the same cell are combined before the shared-memory atomic.
+// ------------------------------------------------------------------------------------------------
+template <bool kAggregate>
+__device__ __forceinline__ void smem_accumulate(float* tile, int idx0, int idx1, float w0, float w1, bool live) {
+  if (kAggregate) {
+    // warp-aggregated: lanes targeting the same cell elect a leader which adds the group's sum
+    unsigned active = __activemask();
+    int key = live ? idx0 : -1 - (int)(threadIdx.x & 31);
+    unsigned peers = __match_any_sync(active, key);
+    int leader = __ffs(peers) - 1;
+    int lane = threadIdx.x & 31;
+    if (__popc(peers) > 1) {
+      float s0 = 0.f, s1 = 0.f;
+      unsigned rem = peers;
+      // every peer walks the same peer list so the shuffles are convergent within the group
+      while (rem) {
+        int src = __ffs(rem) - 1;
+        rem &= rem - 1;
+        s0 += __shfl_sync(peers, w0, src);
+        s1 += __shfl_sync(peers, w1, src);
+      }
+      w0 = s0;
+      w1 = s1;
+    }
+    if (live && lane == leader) {
+      if (w0 != 0.0f) atomicAdd(tile + idx0, w0);
+      if (idx1 >= 0 && w1 != 0.0f) atomicAdd(tile + idx1, w1);
+    }
+  } else {
+    if (live) {
+      if (w0 != 0.0f) atomicAdd(tile + idx0, w0);
+      if (idx1 >= 0 && w1 != 0.0f) atomicAdd(tile + idx1, w1);
+    }
+  }
+}
+
+template <bool kAggregate>
+__global__ void __launch_bounds__(512) voxel_band_kernel(
+    const float* __restrict__ xs, const float* __restrict__ ys, const float* __restrict__ ts,
+    const float* __restrict__ ps, const int64_t* __restrict__ offsets, int bins, int H, int W,
+    int pad_top, int pad_left, int Hp, int Wp, int band_rows, int vec_ok, float* __restrict__ out,
+    int* oob_count) {
+  extern __shared__ float tile[];  // [bins][band_rows][W]
+  const int win = blockIdx.y;
+  const int r0 = blockIdx.x * band_rows;           // first padded row of this band
+  const int r1 = min(Hp, r0 + band_rows);
+  const int y0 = r0 - pad_top;                     // sensor row of tile row 0 (may be negative)
+  const int plane = band_rows * W;
+  const int tile_elems = bins * plane;
+  for (int i = threadIdx.x; i < tile_elems; i += blockDim.x) tile[i] = 0.0f;
+  __syncthreads();
+
+  const int64_t ea = offsets[win], eb = offsets[win + 1];
+  if (eb > ea) {
+    const float t0 = ts[ea];
+    const float dt = __fsub_rn(ts[eb - 1], t0);
+    const float bm1 = (float)(bins - 1);
+    int oob = 0;
+    auto one = [&](float x, float y, float t, float p) {
+      int xi = (int)x, yi = (int)y;  // truncation == .long() (event_utils.py:371-374)
+      bool inside = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H);
+      if (!inside && blockIdx.x == 0) oob++;
+      int ty = yi - y0;
+      bool live = inside & (ty >= 0) & (yi < r1 - pad_top);
+      EventContrib c = contrib(t, p, t0, dt, bm1, bins);
+      if (c.b0 < 0) {  // NaN event: every bin of the pixel becomes NaN
+        if (live)
+          for (int b = 0; b < bins; ++b) atomicAdd(tile + b * plane + ty * W + xi, c.w0);
+        live = false;
+      }
+      int idx0 = live ? (c.b0 * plane + ty * W + xi) : 0;
+      int idx1 = (live && c.b0 + 1 < bins) ? idx0 + plane : -1;
+      smem_accumulate<kAggregate>(tile, idx0, idx1, c.w0, c.w1, live);
+    };
+    // scalar head up to 16-byte alignment, float4 body, scalar tail
+    int64_t body_a = vec_ok ? min(eb, (ea + 3) & ~(int64_t)3) : eb;
+    int64_t body_b = vec_ok ? max(body_a, eb & ~(int64_t)3) : eb;
+    // head + tail: at most 6 events, handled by the first lanes; everyone joins the warp-collective
+    int64_t n_edge = (body_a - ea) + (eb - body_b);
+    for (int64_t base = 0; base < n_edge; base += blockDim.x) {
+      int64_t i = base + threadIdx.x;
+      bool valid = i < n_edge;
+      int64_t e = valid ? (i < body_a - ea ? ea + i : body_b + (i - (body_a - ea))) : ea;
+      if (valid) one(xs[e], ys[e], ts[e], ps[e]);
+    }
+    const int64_t nvec = (body_b - body_a) >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(xs + body_a);
+    const float4* y4 = reinterpret_cast<const float4*>(ys + body_a);
+    const float4* t4 = reinterpret_cast<const float4*>(ts + body_a);
+    const float4* p4 = reinterpret_cast<const float4*>(ps + body_a);
+    for (int64_t v = threadIdx.x; v < nvec; v += blockDim.x) {
+      float4 x = __ldg(x4 + v), y = __ldg(y4 + v), t = __ldg(t4 + v), p = __ldg(p4 + v);
+      one(x.x, y.x, t.x, p.x);
+      one(x.y, y.y, t.y, p.y);
+      one(x.z, y.z, t.z, p.z);
+      one(x.w, y.w, t.w, p.w);
+    }
+    if (oob_count != nullptr && oob > 0) atomicAdd(oob_count, oob);
+  }
+  __syncthreads();
+
+  // coalesced write of the band, padding included
+  float* dst = out + (size_t)win * bins * Hp * Wp;
+  const int rows = r1 - r0;
+  const int total = bins * rows * Wp;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    int col = i % Wp;
+    int rr = (i / Wp) % rows;
+    int b = i / (Wp * rows);
+    int y = r0 + rr - pad_top, x = col - pad_left;
+    float v = 0.0f;
+    if (y >= 0 && y < H && x >= 0 && x < W) v = tile[b * plane + (y - y0) * W + x];
+    dst[((size_t)b * Hp + (r0 + rr)) * Wp + col] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Algorithm 2: global float atomics (RED) into a zeroed grid.  Used for sensors too large for the
+// row-band tiling (each band would have to re-scan the whole window).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) voxel_atomic_kernel(
+    const float* __restrict__ xs, const float* __restrict__ ys, const float* __restrict__ ts,
+    const float* __restrict__ ps, const int64_t* __restrict__ offsets, int bins, int H, int W,
+    int pad_top, int pad_left, int Hp, int Wp, float* __restrict__ out, int* oob_count) {
+  const int win = blockIdx.y;
+  const int64_t ea = offsets[win], eb = offsets[win + 1];
+  if (eb <= ea) return;
+  const float t0 = ts[ea];
+  const float dt = __fsub_rn(ts[eb - 1], t0);
+  const float bm1 = (float)(bins - 1);
+  float* dst = out + (size_t)win * bins * Hp * Wp;
+  const size_t plane = (size_t)Hp * Wp;
+  int oob = 0;
+  for (int64_t e = ea + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < eb;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    float x = __ldg(xs + e), y = __ldg(ys + e), t = __ldg(ts + e), p = __ldg(ps + e);
+    int xi = (int)x, yi = (int)y;
+    if (xi < 0 || xi >= W || yi < 0 || yi >= H) {
+      oob++;
+      continue;
+    }
+    EventContrib c = contrib(t, p, t0, dt, bm1, bins);
+    size_t pix = (size_t)(yi + pad_top) * Wp + (xi + pad_left);
+    if (c.b0 < 0) {
+      for (int b = 0; b < bins; ++b) atomicAdd(dst + b * plane + pix, c.w0);
+      continue;
+    }
+    if (c.w0 != 0.0f) atomicAdd(dst + c.b0 * plane + pix, c.w0);
+    if (c.b0 + 1 < bins && c.w1 != 0.0f) atomicAdd(dst + (c.b0 + 1) * plane + pix, c.w1);
+  }
+  if (oob_count != nullptr && oob > 0) atomicAdd(oob_count, oob);
+}
+
+// planar fp32 [T, bins, Hp, Wp] -> NHWC [T, Hp, Wp, c_pad] (zero-padded channels)
+template <typename T>
+__global__ void pack_voxel_kernel(const float* __restrict__ vox, int bins, size_t plane, int c_pad,
+                                  T* __restrict__ out, size_t total_pix) {
+  size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over T*Hp*Wp
+  if (pix >= total_pix) return;
+  size_t t = pix / plane, p = pix % plane;
+  const float* src = vox + t * bins * plane + p;
+  T* dst = out + pix * c_pad;
+  for (int c = 0; c < c_pad; ++c) dst[c] = from_f32<T>(c < bins ? __ldg(src + (size_t)c * plane) : 0.0f);
+}
+
+}  // namespace bde
+
+using namespace bde;
+
+extern "C" int bde_voxelize_seq(const float* xs, const float* ys, const float* ts, const float* ps,
+                                const int64_t* offsets, int T, int num_bins, int H, int W, int pad_top,
+                                int pad_left, int Hp, int Wp, float* out, int* oob_count, int algo,
+                                void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  BDE_REQUIRE(T >= 0 && num_bins >= 1 && H > 0 && W > 0, "bde_voxelize_seq: bad sizes");
+  BDE_REQUIRE(pad_top >= 0 && pad_left >= 0 && Hp >= H + pad_top && Wp >= W + pad_left,
+              "bde_voxelize_seq: padded grid %dx%d cannot hold %dx%d at (%d,%d)", Hp, Wp, H, W, pad_top, pad_left);
+  if (T == 0) return 0;
+  const size_t smem_budget = 200 * 1024;
+  int band_rows = (int)(smem_budget / ((size_t)num_bins * W * sizeof(float)));
+  band_rows = band_rows > Hp ? Hp : band_rows;
+  int bands = band_rows > 0 ? (int)ceil_div(Hp, band_rows) : 1 << 30;
+  if (algo == 0) algo = (bands <= 16) ? 1 : 2;
+  if (algo == 1) {
+    BDE_REQUIRE(band_rows >= 1, "bde_voxelize_seq: sensor row too wide for the shared-memory algorithm");
+    // balance the bands
+    band_rows = (int)ceil_div(Hp, bands);
+    size_t smem = (size_t)num_bins * band_rows * W * sizeof(float);
+    auto kern = voxel_band_kernel<true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    BDE_REQUIRE(e == cudaSuccess, "bde_voxelize_seq: smem attr: %s", cudaGetErrorString(e));
+    dim3 grid(bands, T);
+    int vec_ok = ((((uintptr_t)xs) | ((uintptr_t)ys) | ((uintptr_t)ts) | ((uintptr_t)ps)) & 15) == 0;
+    kern<<<grid, 512, smem, s>>>(xs, ys, ts, ps, offsets, num_bins, H, W, pad_top, pad_left, Hp, Wp,
+                                 band_rows, vec_ok, out, oob_count);
+    return check_launch("voxel_band_kernel");
+  }
+  BDE_REQUIRE(algo == 2, "bde_voxelize_seq: unknown algo %d", algo);
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)T * num_bins * Hp * Wp * sizeof(float), s);
+  BDE_REQUIRE(e == cudaSuccess, "bde_voxelize_seq: memset: %s", cudaGetErrorString(e));
+  // grid.x sized so the whole launch is a few waves over 148 SMs regardless of T
+  int bx = (int)ceil_div((size_t)kNumSMs * 8, (size_t)T);
+  bx = bx < 1 ? 1 : (bx > 1024 ? 1024 : bx);
+  dim3 grid(bx, T);
+  voxel_atomic_kernel<<<grid, 256, 0, s>>>(xs, ys, ts, ps, offsets, num_bins, H, W, pad_top, pad_left, Hp,
+                                           Wp, out, oob_count);
+  return check_launch("voxel_atomic_kernel");
+}
+
+extern "C" int bde_pack_voxel_nhwc(const float* vox, int T, int bins, int Hp, int Wp, int c_pad, void* out,
+                                   int dtype, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  BDE_REQUIRE(c_pad >= bins, "bde_pack_voxel_nhwc: c_pad < bins");
+  size_t plane = (size_t)Hp * Wp, total = plane * T;
+  if (total == 0) return 0;
+  unsigned blocks = (unsigned)ceil_div(total, 256);
+  if (dtype == BDE_F32)
+    pack_voxel_kernel<float><<<blocks, 256, 0, s>>>(vox, bins, plane, c_pad, (float*)out, total);
+  else if (dtype == BDE_BF16)
+    pack_voxel_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(vox, bins, plane, c_pad, (__nv_bfloat16*)out, total);
+  else
+    BDE_REQUIRE(false, "bde_pack_voxel_nhwc: bad dtype");
+  return check_launch("pack_voxel_kernel");
+}

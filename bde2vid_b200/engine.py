@@ -1,0 +1,395 @@
+"""Sequence executor for the BDE2VID generator.
+
+Implements the level-by-level bidirectional schedule of
+model/BDE2VID/bde2vid_cross_scale_propogation_V5.py:100-241 on top of the C-ABI kernels:
+
+  A  head conv, batched over all T frames                                  (:116)
+  B  per level: encoder conv batched over T, then the two ConvLSTM chains  (:122-135), the
+     ff + fb merge (:137-147) and the in-place sequential window attention (:151-169, quirks Q1,Q4)
+  C  decoders + prediction, batched over chunks of frames                  (:183-197, quirk Q2)
+
+All buffers are allocated once per (T, B, Hp, Wp) "plan"; the whole forward is captured into a
+CUDA graph on its second use so that replay costs one launch from the host.
+Weights are repacked once per engine (K-major [Cout, kh*kw*Cin], gate-interleaved LSTM rows,
+query scale folded into q, relative-position bias pre-gathered).
+"""
+import torch
+
+from . import ops
+from .ops import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_RELU6, ENGINE_SIMT, ENGINE_TCGEN05, EPI_LSTM, EPI_SCATTER,
+                  EPI_STORE)
+
+K_ALIGN = 64      # packed weight rows are zero-padded to a multiple of this (tcgen05 K block)
+VOX_CPAD = 8      # voxel channels padded 5 -> 8 so that a pixel is one 16-byte bf16 chunk
+
+
+def window_geometry(H, W, ws):
+    """Symmetric zero padding to window multiples (DTransformer.py:254-266)."""
+    wh = H if H <= ws[0] else ws[0]
+    ww = W if W <= ws[1] else ws[1]
+    pad_h = (wh - H % wh) % wh
+    pad_w = (ww - W % ww) % ww
+    return dict(wh=wh, ww=ww, pt=pad_h // 2, pl=pad_w // 2, nH=(H + pad_h) // wh, nW=(W + pad_w) // ww)
+
+
+def window_token_map(B, H, W, ws, dilated, device):
+    """int32 [B*nWin, wh*ww]: row of the [B*H*W, C] feature matrix feeding every window token, -1 for
+    tokens on zero padding.  Plain windows: token (a,b) of window (i,j) <-> padded pixel
+    (wh*i+a, ww*j+b); dilated windows (odd blocks, DTransformer.py:362, window_partition :53-59):
+    padded pixel (wh*i+2a, ww*j+2b) of the map padded by one more window bottom/right."""
+    g = window_geometry(H, W, ws)
+    wh, ww, nH, nW = g["wh"], g["ww"], g["nH"], g["nW"]
+    step = 2 if dilated else 1
+    i = torch.arange(nH).view(nH, 1, 1, 1)
+    j = torch.arange(nW).view(1, nW, 1, 1)
+    a = torch.arange(wh).view(1, 1, wh, 1)
+    b = torch.arange(ww).view(1, 1, 1, ww)
+    r = (wh * i + step * a - g["pt"]).expand(nH, nW, wh, ww)
+    c = (ww * j + step * b - g["pl"]).expand(nH, nW, wh, ww)
+    ok = (r >= 0) & (r < H) & (c >= 0) & (c < W)
+    idx = torch.where(ok, r * W + c, torch.full_like(r, -1)).reshape(1, nH * nW, wh * ww)
+    boff = (torch.arange(B) * (H * W)).view(B, 1, 1)
+    full = torch.where(idx >= 0, idx + boff, idx.expand(B, -1, -1))
+    return full.reshape(B * nH * nW, wh * ww).to(torch.int32).contiguous().to(device), g
+
+
+def _pack_conv(w, dtype, cin_pad=None):
+    """[Cout, Cin, kh, kw] -> K-major [Cout, Kpad], k = (ky*kw + kx)*Cin + c, zero padded to K_ALIGN."""
+    co, ci, kh, kw = w.shape
+    w = w.permute(0, 2, 3, 1)
+    if cin_pad is not None and cin_pad > ci:
+        w = torch.nn.functional.pad(w, (0, cin_pad - ci))
+    w = w.reshape(co, -1)
+    K = w.shape[1]
+    Kp = (K + K_ALIGN - 1) // K_ALIGN * K_ALIGN
+    out = torch.zeros(co, Kp, dtype=dtype, device=w.device)
+    out[:, :K] = w.to(dtype)
+    return out.contiguous(), Kp
+
+
+def _pack_linear(w, dtype, scale=1.0):
+    n, K = w.shape
+    Kp = (K + K_ALIGN - 1) // K_ALIGN * K_ALIGN
+    out = torch.zeros(n, Kp, dtype=dtype, device=w.device)
+    out[:, :K] = (w * scale).to(dtype)
+    return out.contiguous(), Kp
+
+
+class _Layer:
+    """Packed weights of one conv / linear."""
+
+    def __init__(self, w, w_ld, bias, n, ksize=1, stride=1, pad=0):
+        self.w, self.w_ld, self.bias, self.n = w, w_ld, bias, n
+        self.ksize, self.stride, self.pad = ksize, stride, pad
+
+
+class Engine:
+    def __init__(self, gen, precision):
+        from . import _lib
+        _lib.require_device()
+        if precision not in ("bf16", "fp32", "bf16-simt"):
+            raise ValueError("precision must be 'bf16' (tcgen05 tensor cores), 'fp32' (CUDA-core parity mode) or "
+                             "'bf16-simt' (debug)")
+        self.precision = precision
+        self.dtype = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.gemm_engine = ENGINE_TCGEN05 if precision == "bf16" else ENGINE_SIMT
+        cfg = gen.cfg
+        self.cfg = cfg
+        self.device = gen.head.conv2d.weight.device
+        if self.device.type != "cuda":
+            raise RuntimeError("BDE2VID (bde2vid_b200) must be on a CUDA device before forward(); no CPU path exists")
+        self.L = cfg["num_encoders"]
+        self.bc = cfg["basechannels"]
+        self.bins = cfg["num_bins"]
+        self.ks = cfg["ks"]
+        self.buf = cfg["buffer_index"]
+        self.q_ind = cfg["q_idx"]
+        self.D = len(self.buf)
+        self.heads = cfg["num_heads"]
+        self.ws = cfg["window_size"]
+        self.depths = cfg["depths"]
+        if self.bins > VOX_CPAD:
+            raise NotImplementedError("num_bins > %d" % VOX_CPAD)
+        dt = self.dtype
+        f32 = lambda t: t.detach().to(torch.float32).contiguous()  # noqa: E731
+
+        def conv_layer(conv, stride, cin_pad=None):
+            w, ld = _pack_conv(conv.weight.detach().float(), dt, cin_pad)
+            k = conv.weight.shape[-1]
+            return _Layer(w, ld, f32(conv.bias), conv.weight.shape[0], k, stride, k // 2)
+
+        def lstm_layer(conv):
+            # rows reordered so that n = 4*c + gate (gate order in, remember, out, cell: submodules.py:320)
+            w = conv.weight.detach().float()
+            hid = w.shape[0] // 4
+            w = w.view(4, hid, *w.shape[1:]).permute(1, 0, 2, 3, 4).reshape(4 * hid, *w.shape[1:])
+            b = conv.bias.detach().float().view(4, hid).t().reshape(-1)
+            pw, ld = _pack_conv(w, dt)
+            return _Layer(pw, ld, b.contiguous(), 4 * hid, 3, 1, 1)
+
+        def lin_layer(lin, scale=1.0):
+            w, ld = _pack_linear(lin.weight.detach().float(), dt, scale)
+            return _Layer(w, ld, f32(lin.bias * scale), lin.weight.shape[0])
+
+        with torch.no_grad():
+            self.head = conv_layer(gen.head.conv2d, 1, cin_pad=VOX_CPAD)
+            self.enc = []
+            for l in range(self.L):
+                self.enc.append(dict(
+                    f_conv=conv_layer(gen.forward_encoder[l].conv.conv2d, 2),
+                    b_conv=conv_layer(gen.backward_encoder[l].conv.conv2d, 2),
+                    f_lstm=lstm_layer(gen.forward_encoder[l].recurrent_block.Gates),
+                    b_lstm=lstm_layer(gen.backward_encoder[l].recurrent_block.Gates)))
+            self.attn = []
+            n_tok = self.ws[0] * self.ws[1]
+            for l in range(self.L):
+                blocks = []
+                if self.depths[l] > 0:
+                    C = self.bc * 2 ** (l + 1)
+                    hd = C // self.heads
+                    for blk in gen.feat_attns[l].blocks:
+                        a = blk.attn
+                        idx = a.relative_position_index[self.q_ind * n_tok:(self.q_ind + 1) * n_tok, :self.D * n_tok]
+                        bias = a.relative_position_bias_table.detach().float()[idx.reshape(-1)]
+                        bias = bias.reshape(n_tok, self.D * n_tok, self.heads).permute(2, 1, 0).contiguous()
+                        blocks.append(dict(
+                            nq_g=f32(a.norm_q.weight), nq_b=f32(a.norm_q.bias),
+                            nkv_g=f32(a.norm_kv.weight), nkv_b=f32(a.norm_kv.bias),
+                            q=lin_layer(a.q, hd ** -0.5), kv=lin_layer(a.kv), proj=lin_layer(a.proj),
+                            bias=bias,                              # [heads, D*n_tok, n_tok]
+                            n2_g=f32(blk.norm2.weight), n2_b=f32(blk.norm2.bias),
+                            fc1=lin_layer(blk.mlp.fc1), fc2=lin_layer(blk.mlp.fc2)))
+                self.attn.append(blocks)
+            self.dec = [conv_layer(gen.decoders[i][1].conv2d, 1) for i in range(self.L)]
+            self.pred_w = f32(gen.predI[1].weight.reshape(-1))
+            self.pred_b = f32(gen.predI[1].bias)
+        self.plans = {}
+        self.dec_chunk = 8
+
+    # ------------------------------------------------------------------------------------
+    def _gemm(self, layer, a0, out, n_img, h, w, c0, **kw):
+        return ops.gemm(a0, layer.w, layer.bias, out, n_img=n_img, h_in=h, w_in=w, c0=c0, n=layer.n,
+                        ksize=layer.ksize, stride=layer.stride, pad=layer.pad, w_ld=layer.w_ld,
+                        engine=self.gemm_engine, dtype=self.dtype, **kw)
+
+    def plan(self, T, B, Hp, Wp):
+        key = (T, B, Hp, Wp)
+        p = self.plans.get(key)
+        if p is None:
+            p = _Plan(self, T, B, Hp, Wp)
+            self.plans[key] = p
+        return p
+
+    def forward(self, vox_list, use_graph=True):
+        """vox_list: T tensors [B, bins, Hp, Wp] float32 (CUDA).  Returns T tensors [B, 1, Hp, Wp]."""
+        T = len(vox_list)
+        if T == 0:
+            return []
+        v0 = vox_list[0]
+        if not v0.is_cuda:
+            raise RuntimeError("BDE2VID.forward needs CUDA tensors (the reference driver moves voxels with "
+                               ".to(device), eval_models_seq.py:204); no CPU path exists")
+        B, bins, Hp, Wp = v0.shape
+        if bins != self.bins:
+            raise ValueError("expected %d voxel bins, got %d" % (self.bins, bins))
+        S = 2 ** self.L
+        if Hp % S or Wp % S:
+            raise ValueError("input %dx%d must be padded to a multiple of %d (Croper.pad)" % (Hp, Wp, S))
+        p = self.plan(T, B, Hp, Wp)
+        torch.stack([v.to(torch.float32) for v in vox_list], dim=0, out=p.vox_in)
+        p.run(use_graph, from_events=False)
+        img = p.img.clone().view(T, B, 1, Hp, Wp)
+        return list(img.unbind(0))
+
+    def forward_events(self, xs, ys, ts, ps, offsets, H, W, crop, use_graph=True):
+        """Fused path: raw events -> frames (voxeliser writes the padded grids the UNet reads)."""
+        T = offsets.numel() - 1
+        Hp, Wp = crop.height_crop_size, crop.width_crop_size
+        p = self.plan(T, 1, Hp, Wp)
+        p.set_events(xs, ys, ts, ps, offsets, H, W, crop.padding_top, crop.padding_left)
+        p.run(use_graph, from_events=True)
+        img = p.img.clone().view(T, 1, 1, Hp, Wp)
+        return list(img.unbind(0))
+
+
+class _Plan:
+    """Static buffers + launch sequence for one (T, B, Hp, Wp)."""
+
+    def __init__(self, eng, T, B, Hp, Wp):
+        self.eng, self.T, self.B, self.Hp, self.Wp = eng, T, B, Hp, Wp
+        dev, dt = eng.device, eng.dtype
+        f32 = torch.float32
+        E = lambda *s, dtype=dt: torch.empty(*s, dtype=dtype, device=dev)  # noqa: E731
+        N = T * B
+        self.vox_in = E(T, B, eng.bins, Hp, Wp, dtype=f32)
+        self.vox8 = E(N, Hp, Wp, VOX_CPAD)
+        self.head = E(N, Hp, Wp, eng.bc)
+        self.img = E(N, Hp, Wp, dtype=f32)
+        self.lv = []
+        for l in range(eng.L):
+            h, w, C = Hp >> (l + 1), Wp >> (l + 1), eng.bc * 2 ** (l + 1)
+            d = dict(h=h, w=w, C=C,
+                     ef=E(N, h, w, C), eb=E(N, h, w, C), hf=E(N, h, w, C), hb=E(N, h, w, C),
+                     cf=[E(B, h, w, C, dtype=f32) for _ in range(2)], cb=[E(B, h, w, C, dtype=f32) for _ in range(2)],
+                     zero=torch.zeros(B, h, w, C, dtype=dt, device=dev),
+                     feat=E(N, h, w, C, dtype=f32))
+            d["feat_t"] = d["feat"] if dt == f32 else E(N, h, w, C)
+            if eng.depths[l] > 0:
+                ws = eng.ws
+                if h < ws[0] or w < ws[1]:
+                    raise NotImplementedError(
+                        "feature map %dx%d at attention level %d is smaller than the %dx%d window; the reference "
+                        "fails on such inputs too (relative_position_index is built for full windows)" % (h, w, l, *ws))
+                tm_plain, g = window_token_map(B, h, w, ws, False, dev)
+                tm_dil, _ = window_token_map(B, h, w, ws, True, dev)
+                nwin = tm_plain.shape[0]
+                ntok = ws[0] * ws[1]
+                P = B * h * w
+                d.update(tm=[tm_plain, tm_dil], nwin=nwin, ntok=ntok,
+                         xs=E(P, C, dtype=f32), qn=E(nwin * ntok, C), kvn=E(nwin * eng.D * ntok, C),
+                         qb=E(nwin * ntok, C), kvb=E(nwin * eng.D * ntok, 2 * C), ob=E(nwin * ntok, C),
+                         yn=E(P, C), hid=E(P, 4 * C))
+            self.lv.append(d)
+        Tc = min(eng.dec_chunk, T)
+        self.Tc = Tc
+        self.dec = []
+        for i in range(eng.L):
+            l_in = eng.L - 1 - i                     # level whose resolution the decoder input has
+            h, w, C = self.lv[l_in]["h"], self.lv[l_in]["w"], self.lv[l_in]["C"]
+            self.dec.append(dict(h=h, w=w, C=C, up=E(Tc * B, 2 * h, 2 * w, C), out=E(Tc * B, 2 * h, 2 * w, C // 2)))
+        self.graphs = {}
+        self.runs = {}
+        self.ev = None
+
+    # ------------------------------------------------------------------------------------
+    def set_events(self, xs, ys, ts, ps, offsets, H, W, pad_top, pad_left):
+        """Stage one sequence's events into static buffers (host or device sources; the copies are
+        asynchronous on the current stream) so that the captured graph can include the voxeliser."""
+        n = xs.numel()
+        dev = self.eng.device
+        geom = (H, W, pad_top, pad_left)
+        if self.ev is None or self.ev_cap < n or self.ev_geom != geom:
+            self.ev_cap = max(int(n * 1.25) + 16, 1024)
+            self.ev = [torch.zeros(self.ev_cap, dtype=torch.float32, device=dev) for _ in range(4)]
+            self.ev_off = torch.zeros(self.T + 1, dtype=torch.int64, device=dev)
+            self.oob = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.ev_geom = geom
+            self.graphs.pop(True, None)
+            self.runs[True] = 0
+        for dst, src in zip(self.ev, (xs, ys, ts, ps)):
+            dst[:n].copy_(src, non_blocking=True)
+        self.ev_off.copy_(offsets, non_blocking=True)
+
+    def run(self, use_graph, from_events):
+        self.runs[from_events] = self.runs.get(from_events, 0) + 1
+        if not use_graph:
+            self._enqueue(from_events)
+            return
+        if from_events not in self.graphs and self.runs[from_events] >= 2:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self._enqueue(from_events)
+            self.graphs[from_events] = g
+        if from_events in self.graphs:
+            self.graphs[from_events].replay()
+        else:
+            self._enqueue(from_events)
+
+    # ------------------------------------------------------------------------------------
+    def _enqueue(self, from_events):
+        eng, T, B, Hp, Wp = self.eng, self.T, self.B, self.Hp, self.Wp
+        N = T * B
+        self.launches = 0
+        if from_events:
+            xs, ys, ts, ps = self.ev
+            H, W, pt, pl = self.ev_geom
+            ops.voxelize_seq(xs, ys, ts, ps, self.ev_off, eng.bins, H, W, pt, pl, Hp, Wp,
+                             out=self.vox_in.view(T, eng.bins, Hp, Wp), oob_count=self.oob)
+            self.launches += 1
+        ops.pack_voxel_nhwc(self.vox_in.view(N, eng.bins, Hp, Wp), VOX_CPAD, eng.dtype, out=self.vox8)
+        # A: head conv + ReLU over all frames (...V5.py:116)
+        eng._gemm(eng.head, self.vox8, self.head, N, Hp, Wp, VOX_CPAD, act=ACT_RELU)
+        self.launches += 2
+        x, xc, xh, xw = self.head, eng.bc, Hp, Wp
+        for l in range(eng.L):
+            d, e = self.lv[l], eng.enc[l]
+            h, w, C = d["h"], d["w"], d["C"]
+            # encoder convs are not recurrent: one launch per direction over all T (...V5.py:129-130, conv part)
+            eng._gemm(e["f_conv"], x, d["ef"], N, xh, xw, xc, act=ACT_RELU)
+            eng._gemm(e["b_conv"], x, d["eb"], N, xh, xw, xc, act=ACT_RELU)
+            self.launches += 2
+            # the two ConvLSTM chains (sequential in t; gates conv + pointwise fused in one kernel)
+            for k in range(T):
+                for (src, hbuf, cbuf, layer, t, tprev) in (
+                        (d["ef"], d["hf"], d["cf"], e["f_lstm"], k, k - 1),
+                        (d["eb"], d["hb"], d["cb"], e["b_lstm"], T - 1 - k, T - k)):
+                    first = k == 0
+                    eng._gemm(layer, src[t * B:(t + 1) * B], hbuf[t * B:(t + 1) * B], B, h, w, C,
+                              a1=d["zero"] if first else hbuf[tprev * B:(tprev + 1) * B], c1=C,
+                              epi=EPI_LSTM, c_prev=None if first else cbuf[(k + 1) & 1], c_out=cbuf[k & 1])
+                    self.launches += 1
+            # merged = ff + fb (...V5.py:137-147)
+            ops.add(d["hf"], d["hb"], out_f32=d["feat"], out_t=None if eng.dtype == torch.float32 else d["feat_t"],
+                    dtype=eng.dtype)
+            self.launches += 1
+            if eng.depths[l] > 0:
+                self._attention_level(l)
+            x, xc, xh, xw = d["feat_t"], C, h, w
+        # C: decoders + prediction, chunked over frames (...V5.py:183-197)
+        for t0 in range(0, T, self.Tc):
+            n = min(self.Tc, T - t0) * B
+            s = slice(t0 * B, t0 * B + n)
+            cur, cur_scale = None, 1.0
+            for i in range(eng.L):
+                dd = self.dec[i]
+                l_in = eng.L - 1 - i
+                feat = self.lv[l_in]["feat"][s]
+                if i == 0:    # quirk Q2: the last level is appended twice -> decoder 0 sees feat + feat
+                    ops.upsample2x_sum(None, feat, 2.0, n, dd["h"], dd["w"], dd["C"], dd["up"][:n])
+                else:
+                    ops.upsample2x_sum(feat, cur, 1.0, n, dd["h"], dd["w"], dd["C"], dd["up"][:n])
+                eng._gemm(eng.dec[i], dd["up"][:n], dd["out"][:n], n, 2 * dd["h"], 2 * dd["w"], dd["C"], act=ACT_RELU6)
+                cur = dd["out"][:n]
+                self.launches += 2
+            ops.pred_sigmoid(cur, self.head[s], eng.pred_w, eng.pred_b, eng.bc, n * Hp * Wp, self.img[s])
+            self.launches += 1
+
+    def _attention_level(self, l):
+        """In-place sequential multi-frame window attention (...V5.py:151-169; DTransformer.py:254-389)."""
+        eng, T, B = self.eng, self.T, self.B
+        d = self.lv[l]
+        h, w, C = d["h"], d["w"], d["C"]
+        P = B * h * w
+        nwin, ntok, D = d["nwin"], d["ntok"], eng.D
+        feat = d["feat"].view(T, P, C)
+        feat_t = d["feat_t"].view(T, P, C)
+        xs = d["xs"]
+        for t in range(T):
+            # past neighbours are already post-attention (updated in place), future ones are not: quirk Q1
+            frames = [feat[t + o] if 0 <= t + o < T else None for o in eng.buf]      # None = all-zero map (Q4)
+            qsrc = frames[eng.q_ind]
+            if qsrc is None:
+                xs.zero_()
+            else:
+                ops.cast(qsrc, xs)
+            self.launches += 1
+            for i, blk in enumerate(eng.attn[l]):
+                tm = d["tm"][i & 1]
+                fr = list(frames)
+                fr[eng.q_ind] = xs
+                ops.ln_gather([xs], tm, nwin, ntok, C, blk["nq_g"], blk["nq_b"], d["qn"])
+                ops.ln_gather(fr, tm, nwin, ntok, C, blk["nkv_g"], blk["nkv_b"], d["kvn"])
+                eng._gemm(blk["q"], d["qn"], d["qb"], 1, nwin * ntok, 1, C)
+                eng._gemm(blk["kv"], d["kvn"], d["kvb"], 1, nwin * D * ntok, 1, C)
+                ops.window_attention(d["qb"], d["kvb"], blk["bias"], nwin, ntok, D * ntok, C, eng.heads, d["ob"])
+                # proj + window_reverse + crop + shortcut: x[pixel] += proj(o); uncovered pixels keep x
+                eng._gemm(blk["proj"], d["ob"], xs, 1, nwin * ntok, 1, C, epi=EPI_SCATTER, row_map=tm.view(-1))
+                ops.layernorm(xs, P, C, blk["n2_g"], blk["n2_b"], d["yn"])
+                eng._gemm(blk["fc1"], d["yn"], d["hid"], 1, P, 1, C, act=ACT_GELU)
+                eng._gemm(blk["fc2"], d["hid"], xs, 1, P, 1, 4 * C, out_f32=True, residual=xs)
+                self.launches += 9
+            # x + merged[t], stored back in place (...V5.py:166-169)
+            ops.add(xs, feat[t], out_f32=feat[t], out_t=None if eng.dtype == torch.float32 else feat_t[t],
+                    dtype=eng.dtype)
+            self.launches += 1

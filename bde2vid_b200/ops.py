@@ -1,0 +1,117 @@
+"""Python-side wrappers of the C ABI (one function per entry point of include/bde2vid.h).
+
+All tensors are contiguous CUDA tensors owned by PyTorch; the wrappers only pass pointers and
+sizes and enqueue on ``torch.cuda.current_stream()``.  Nothing here computes on the host.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, BDE_DTYPE, BF16, ENGINE_SIMT,  # noqa: F401
+                   ENGINE_TCGEN05, EPI_LSTM, EPI_SCATTER, EPI_STORE, F32, TORCH_DTYPE, check, ptr, stream_ptr)
+
+
+def voxelize_seq(xs, ys, ts, ps, offsets, num_bins, H, W, pad_top=0, pad_left=0, Hp=None, Wp=None, out=None,
+                 oob_count=None, algo=0):
+    """float32 event arrays + int64 CSR offsets [T+1] -> float32 [T, bins, Hp, Wp]."""
+    lib = _lib.require_device()
+    Hp = H + pad_top if Hp is None else Hp
+    Wp = W + pad_left if Wp is None else Wp
+    T = offsets.numel() - 1
+    for t in (xs, ys, ts, ps):
+        assert t.dtype == torch.float32 and t.is_cuda
+    assert offsets.dtype == torch.int64 and offsets.is_cuda
+    if out is None:
+        out = torch.empty((T, num_bins, Hp, Wp), dtype=torch.float32, device=xs.device)
+    assert out.shape == (T, num_bins, Hp, Wp) and out.dtype == torch.float32
+    check(lib.bde_voxelize_seq(ptr(xs), ptr(ys), ptr(ts), ptr(ps), ptr(offsets), T, num_bins, H, W, pad_top, pad_left,
+                               Hp, Wp, ptr(out), ptr(oob_count), algo, stream_ptr()), "bde_voxelize_seq")
+    return out
+
+
+def pack_voxel_nhwc(vox, c_pad, dtype, out=None):
+    """[N, bins, Hp, Wp] float32 planar -> [N, Hp, Wp, c_pad] NHWC of ``dtype``."""
+    lib = _lib.require_device()
+    N, bins, Hp, Wp = vox.shape
+    if out is None:
+        out = torch.empty((N, Hp, Wp, c_pad), dtype=dtype, device=vox.device)
+    check(lib.bde_pack_voxel_nhwc(ptr(vox), N, bins, Hp, Wp, c_pad, ptr(out), BDE_DTYPE[dtype], stream_ptr()),
+          "bde_pack_voxel_nhwc")
+    return out
+
+
+def gemm(a0, w, bias, out, *, n_img, h_in, w_in, c0, n, ksize=1, stride=1, pad=0, a1=None, c1=0, w_ld=0,
+         epi=EPI_STORE, act=ACT_NONE, out_f32=False, residual=None, c_prev=None, c_out=None, row_map=None,
+         out2=None, engine=ENGINE_SIMT, dtype=None):
+    """Implicit-GEMM conv / linear (see bde_gemm in include/bde2vid.h).  Returns (h_out, w_out)."""
+    lib = _lib.require_device()
+    d = _lib.GemmDesc()
+    d.engine = engine
+    d.dtype = BDE_DTYPE[a0.dtype if dtype is None else dtype]
+    d.a0, d.a1 = ptr(a0), ptr(a1)
+    d.c0, d.c1 = c0, c1
+    d.n_img, d.h_in, d.w_in = n_img, h_in, w_in
+    d.h_out = (h_in + 2 * pad - ksize) // stride + 1
+    d.w_out = (w_in + 2 * pad - ksize) // stride + 1
+    d.ksize, d.stride, d.pad = ksize, stride, pad
+    d.w, d.bias, d.n, d.w_ld = ptr(w), ptr(bias), n, w_ld
+    d.epi, d.act, d.out_f32 = epi, act, int(out_f32)
+    d.out, d.residual, d.c_prev, d.c_out = ptr(out), ptr(residual), ptr(c_prev), ptr(c_out)
+    d.row_map, d.out2 = ptr(row_map), ptr(out2)
+    check(lib.bde_gemm(C.byref(d), stream_ptr()), "bde_gemm")
+    return d.h_out, d.w_out
+
+
+def add(a, b, out_f32=None, out_t=None, dtype=torch.float32):
+    lib = _lib.require_device()
+    n = a.numel()
+    assert b.numel() == n
+    check(lib.bde_add(ptr(a), int(a.dtype == torch.float32), ptr(b), int(b.dtype == torch.float32), ptr(out_f32),
+                      ptr(out_t), n, BDE_DTYPE[dtype], stream_ptr()), "bde_add")
+
+
+def upsample2x_sum(skip, x, x_scale, n_img, h, w, c, dst):
+    lib = _lib.require_device()
+    check(lib.bde_upsample2x_sum(ptr(skip), int(skip is not None and skip.dtype == torch.float32), ptr(x),
+                                 int(x.dtype == torch.float32), float(x_scale), n_img, h, w, c, ptr(dst),
+                                 BDE_DTYPE[dst.dtype], stream_ptr()), "bde_upsample2x_sum")
+    return dst
+
+
+def pred_sigmoid(x, head, wt, bias, c, n_pix, img):
+    lib = _lib.require_device()
+    check(lib.bde_pred_sigmoid(ptr(x), ptr(head), ptr(wt), ptr(bias), c, n_pix, ptr(img), BDE_DTYPE[x.dtype],
+                               stream_ptr()), "bde_pred_sigmoid")
+    return img
+
+
+def ln_gather(frames, tok_map, n_win, n_tok, c, gamma, beta, out):
+    """frames: list of float32 [*, c] tensors or None (zero frame)."""
+    lib = _lib.require_device()
+    D = len(frames)
+    arr = (C.c_void_p * D)(*[None if f is None else f.data_ptr() for f in frames])
+    check(lib.bde_ln_gather(arr, D, ptr(tok_map), n_win, n_tok, c, ptr(gamma), ptr(beta), ptr(out),
+                            BDE_DTYPE[out.dtype], stream_ptr()), "bde_ln_gather")
+    return out
+
+
+def layernorm(x, rows, c, gamma, beta, out):
+    lib = _lib.require_device()
+    check(lib.bde_layernorm(ptr(x), rows, c, ptr(gamma), ptr(beta), ptr(out), BDE_DTYPE[out.dtype], stream_ptr()),
+          "bde_layernorm")
+    return out
+
+
+def window_attention(q, kv, bias_t, n_win, n_q, n_kv, c, heads, out):
+    lib = _lib.require_device()
+    check(lib.bde_window_attention(ptr(q), ptr(kv), ptr(bias_t), n_win, n_q, n_kv, c, heads, ptr(out),
+                                   BDE_DTYPE[out.dtype], stream_ptr()), "bde_window_attention")
+    return out
+
+
+def cast(src, dst):
+    lib = _lib.require_device()
+    check(lib.bde_cast(ptr(src), BDE_DTYPE[src.dtype], ptr(dst), BDE_DTYPE[dst.dtype], src.numel(), stream_ptr()),
+          "bde_cast")
+    return dst

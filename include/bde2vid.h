@@ -1,0 +1,163 @@
+/*
+ * bde2vid.h -- C ABI of libbde2vid_sm100.so: hand-written sm_100a kernels for the BDE2VID
+ * inference hot path (event voxelisation + bidirectional recurrent conv UNet forward).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The reference
+ * (gaopinghai/BDE2VID) is pure Python/PyTorch, so "the FFI a maintainer would bind" is a
+ * ctypes stub; every entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work;
+ *   - return value 0 = ok, negative = error (see bde_last_error());
+ *   - the library never allocates or frees device memory: callers own every buffer;
+ *   - activations are NHWC ("pixels x channels"), element type selected by `dtype`.
+ */
+#ifndef BDE2VID_H_
+#define BDE2VID_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BDE_ABI_VERSION 1
+
+/* element types of activation / weight buffers */
+enum { BDE_F32 = 0, BDE_BF16 = 1 };
+
+/* activations applied in GEMM epilogues */
+enum { BDE_ACT_NONE = 0, BDE_ACT_RELU = 1, BDE_ACT_RELU6 = 2, BDE_ACT_GELU = 3, BDE_ACT_SIGMOID = 4 };
+
+/* epilogue kinds of bde_gemm */
+enum {
+  BDE_EPI_STORE = 0,   /* out[m,n] = act(acc + bias[n]) (+ residual[m,n])                       */
+  BDE_EPI_LSTM = 1,    /* N = 4*hidden, gate-interleaved rows; ConvLSTM pointwise update         */
+  BDE_EPI_SCATTER = 2  /* out_f32[row_map[m], n] += acc + bias[n]   (rows with map < 0 dropped)  */
+};
+
+/* GEMM engines */
+enum { BDE_ENGINE_SIMT = 0, BDE_ENGINE_TCGEN05 = 1 };
+
+const char* bde_last_error(void);
+int bde_abi_version(void);
+/* 1 if the device of the current context is compute capability 10.x, else 0 (negative on error) */
+int bde_device_ok(void);
+
+/* --------------------------------------------------------------------------------------------
+ * Voxeliser.  Replaces events_to_voxel_torch (events_contrast_maximization/utils/event_utils.py
+ * :466-509) and its callee events_to_image_torch (:330-376), for a whole sequence in one launch,
+ * and the zero padding of Croper.pad (utils_func/inference_utils.py:104-111).
+ *
+ *   xs, ys, ts, ps : float32[n_events]   loader format (h5_dataset.py:222-225,:414): x,y hold
+ *                    integers, ts is relative to the window's first event, ps is +-1
+ *   offsets        : int64[T+1]          CSR window boundaries into the event arrays
+ *   out            : float32[T, num_bins, Hp, Wp]; the H x W sensor area sits at (pad_top,
+ *                    pad_left); every byte of `out` is written (padding = 0)
+ *   oob_count      : optional int32[1], incremented for every event outside the sensor (the
+ *                    reference raises IndexError from index_put_; such events are dropped here)
+ *   algo           : 0 = auto, 1 = shared-memory row-band accumulation, 2 = global atomics
+ * Windows with fewer than 1 event produce zeros; dt == 0 reproduces the reference's NaNs.
+ */
+int bde_voxelize_seq(const float* xs, const float* ys, const float* ts, const float* ps,
+                     const int64_t* offsets, int T, int num_bins, int H, int W,
+                     int pad_top, int pad_left, int Hp, int Wp,
+                     float* out, int* oob_count, int algo, void* stream);
+
+/* planar voxel grids float32[T, bins, Hp, Wp] -> NHWC with channels padded to c_pad (zeros),
+ * element type `dtype`.  Feeds the head convolution (bde2vid_cross_scale_propogation_V5.py:116). */
+int bde_pack_voxel_nhwc(const float* vox, int T, int bins, int Hp, int Wp, int c_pad,
+                        void* out, int dtype, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear layer.
+ *
+ *   C[m, n] = sum_k A[m, k] * Wp[n, k],   m = (img, oy, ox),  k = (tap, channel)
+ *
+ * A is gathered on the fly from one or two NHWC sources (two sources = the channel concat of
+ * ConvLSTM, model/BDE2VID/submodules.py:316, without materialising it).  Replaces every
+ * nn.Conv2d / nn.Linear on the path: ConvLayer (submodules.py:85-114), ConvLSTM.Gates (:317),
+ * UpsampleConvLayer.conv2d (:139), predI, and the q/kv/proj/fc1/fc2 Linears of
+ * model/BDE2VID/DTransformer.py:188-204,28-36.
+ */
+typedef struct bde_gemm_desc {
+  int engine;            /* BDE_ENGINE_*                                                        */
+  int dtype;             /* element type of a0/a1/w and of `out` unless out_f32                  */
+  /* A operand */
+  const void* a0;        /* NHWC [n_img, h_in, w_in, c0]                                         */
+  const void* a1;        /* optional second source [n_img, h_in, w_in, c1] (c1 = 0 -> unused)    */
+  int c0, c1;
+  int n_img, h_in, w_in, h_out, w_out;
+  int ksize, stride, pad;
+  /* B operand: packed weights [n, ksize*ksize*(c0+c1)], K-major, k = (ky*ksize+kx)*(c0+c1)+c    */
+  const void* w;
+  const float* bias;     /* float32[n] (always fp32), may be NULL                                */
+  int n;
+  int w_ld;              /* row pitch of w in elements (>= K; 0 means K).  The tcgen05 engine    */
+                         /* needs w_ld % 64 == 0 with zero padding beyond K.                    */
+  /* epilogue */
+  int epi;               /* BDE_EPI_*                                                            */
+  int act;               /* BDE_ACT_* (STORE only)                                               */
+  int out_f32;           /* STORE: write float32 instead of `dtype`                              */
+  void* out;             /* STORE: [M, n]; LSTM: h_out [M, hidden] (dtype); SCATTER: f32 [P, n]  */
+  const float* residual; /* STORE: optional float32 [M, n] added after the activation            */
+  const float* c_prev;   /* LSTM: float32 [M, hidden] or NULL (= zeros)                          */
+  float* c_out;          /* LSTM: float32 [M, hidden]                                            */
+  const int* row_map;    /* SCATTER: int32 [M] destination row or -1                             */
+  void* out2;            /* STORE+out_f32: optional second copy of the result in `dtype`         */
+} bde_gemm_desc;
+
+int bde_gemm(const bde_gemm_desc* desc, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Element-wise / gather kernels around the GEMMs.
+ */
+
+/* sum = a + b over n elements (bidirectional merge ff + fb, ...V5.py:144; attention residual
+ * x + merged, ...V5.py:166).  a / b are float32 when the *_f32 flag is set, else `dtype`.
+ * The fp32 sum goes to out_f32 and/or a `dtype` copy to out_t (either may be NULL; in-place ok). */
+int bde_add(const void* a, int a_f32, const void* b, int b_f32, float* out_f32, void* out_t, size_t n,
+            int dtype, void* stream);
+
+/* dst = bilinear_x2(skip + x)  with align_corners=False (submodules.py:138 fed by skip_sum,
+ * ...V5.py:191-194); skip, x: NHWC [n_img, h, w, c] of `dtype`; either may also be float32 when
+ * the *_f32 flag is set; dst NHWC [n_img, 2h, 2w, c] of `dtype`.  x_scale multiplies x (Q2: the
+ * last level is added to itself -> skip = x, handled by passing skip = NULL, x_scale = 2). */
+int bde_upsample2x_sum(const void* skip, int skip_f32, const void* x, int x_f32, float x_scale,
+                       int n_img, int h, int w, int c, void* dst, int dtype, void* stream);
+
+/* img[p] = sigmoid(bias + sum_c wt[c] * (x[p,c] + head[p,c]))  (predI + Sigmoid, ...V5.py:195-197)
+ * x, head NHWC [P, c] of `dtype`; img float32[P]. */
+int bde_pred_sigmoid(const void* x, const void* head, const float* wt, const float* bias, int c,
+                     size_t n_pix, float* img, int dtype, void* stream);
+
+/* Window-token gather + LayerNorm (DTransformer.py:41-60 window_partition, :183-184 norm_q/kv).
+ *   frames[d]  : float32 NHWC [h*w, c] feature map of buffer slot d, or NULL (= all-zero frame)
+ *   tok_map    : int32 [n_win * n_tok] source pixel per window token or -1 (zero token)
+ *   out        : `dtype` [n_win, D, n_tok, c]  (kv token index d*n_tok + a*ww + b)
+ * Each token (including zero tokens) is normalised over c with (gamma, beta), eps 1e-5. */
+int bde_ln_gather(const float* const* frames_host, int D, const int* tok_map, int n_win, int n_tok,
+                  int c, const float* gamma, const float* beta, void* out, int dtype, void* stream);
+
+/* Row-wise LayerNorm of a float32 [rows, c] matrix -> `dtype` (norm2, DTransformer.py:281). */
+int bde_layernorm(const float* x, size_t rows, int c, const float* gamma, const float* beta,
+                  void* out, int dtype, void* stream);
+
+/* Window multi-head attention core (DTransformer.py:192-203):
+ *   q   : `dtype` [n_win, n_q, c]      (already scaled by head_dim^-0.5)
+ *   kv  : `dtype` [n_win, n_kv, 2c]    (k = [..., :c], v = [..., c:])
+ *   bias: float32 [heads, n_kv, n_q]   relative-position bias, pre-gathered and transposed
+ *   out : `dtype` [n_win, n_q, c]      softmax(q k^T + bias) v, heads concatenated
+ */
+int bde_window_attention(const void* q, const void* kv, const float* bias, int n_win, int n_q,
+                         int n_kv, int c, int heads, void* out, int dtype, void* stream);
+
+/* float32 -> dtype copy/cast (and back); n elements */
+int bde_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDE2VID_H_ */

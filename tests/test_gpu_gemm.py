@@ -1,0 +1,201 @@
+"""GPU parity: the implicit-GEMM engines (CUDA-core fp32 and tcgen05 bf16) through bde_gemm,
+against functional torch on the CPU (the oracle's arithmetic: conv2d / linear in fp32)."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def nhwc(x, dtype):
+    return x.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)
+
+
+def run_conv(x_list, w, b, stride, engine, dtype, epi="store", act=0, **extra):
+    """x_list: 1 or 2 NCHW cpu tensors (channel concat); w [Co, Ci_total, k, k]; returns NCHW cpu float."""
+    from bde2vid_b200 import ops
+    from bde2vid_b200.engine import _pack_conv
+    n, _, h, wd = x_list[0].shape
+    k = w.shape[-1]
+    pw, ld = _pack_conv(w.to(DEV), dtype)
+    a0 = nhwc(x_list[0], dtype)
+    a1 = nhwc(x_list[1], dtype) if len(x_list) > 1 else None
+    co = w.shape[0]
+    ho, wo = (h + 2 * (k // 2) - k) // stride + 1, (wd + 2 * (k // 2) - k) // stride + 1
+    out = torch.zeros(n, ho, wo, co, dtype=dtype, device=DEV)
+    ops.gemm(a0, pw, b.to(DEV).float().contiguous(), out, n_img=n, h_in=h, w_in=wd, c0=x_list[0].shape[1], n=co,
+             ksize=k, stride=stride, pad=k // 2, a1=a1, c1=0 if a1 is None else x_list[1].shape[1], w_ld=ld,
+             act=act, engine=engine, dtype=dtype, **extra)
+    torch.cuda.synchronize()
+    return out.float().cpu().permute(0, 3, 1, 2)
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+CONV_CASES = [
+    # n, cin, cout, h, w, k, stride
+    (2, 8, 32, 24, 40, 5, 1),      # head-like (cin padded to 8), K = 200 -> K tail
+    (3, 32, 64, 26, 38, 5, 2),     # encoder 0, ctot < 64 path, odd M
+    (1, 64, 128, 33, 44, 5, 2),    # encoder 1
+    (2, 128, 256, 16, 24, 5, 2),   # encoder 2
+    (1, 256, 128, 18, 22, 5, 1),   # decoder 0
+    (2, 64, 64, 20, 12, 3, 1),
+    (1, 64, 256, 30, 30, 1, 1),    # linear (fc1-like), M = 900
+    (1, 256, 1024, 7, 50, 1, 1),   # wide N
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_simt_fp32_conv(case):
+    from bde2vid_b200 import ops
+    n, ci, co, h, w, k, s = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(n, ci, h, w, generator=g)
+    wt = torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5
+    b = torch.randn(co, generator=g)
+    ref = F.relu(F.conv2d(x, wt, b, stride=s, padding=k // 2))
+    got = run_conv([x], wt, b, s, ops.ENGINE_SIMT, torch.float32, act=ops.ACT_RELU)
+    assert (got - ref).abs().max() <= 2e-5 * max(1.0, ref.abs().max())
+
+
+@pytest.mark.parametrize("b_cpasync", ["0", "1"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_tcgen05_bf16_conv(case, b_cpasync):
+    from bde2vid_b200 import ops
+    n, ci, co, h, w, k, s = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = bf16r(torch.randn(n, ci, h, w, generator=g))
+    wt = bf16r(torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5)
+    b = torch.randn(co, generator=g)
+    ref = F.relu(F.conv2d(x, wt, b, stride=s, padding=k // 2))
+    os.environ["BDE2VID_TC_B_CPASYNC"] = b_cpasync
+    try:
+        got = run_conv([x], wt, b, s, ops.ENGINE_TCGEN05, torch.bfloat16, act=ops.ACT_RELU)
+    finally:
+        os.environ["BDE2VID_TC_B_CPASYNC"] = "0"
+    err = (got - ref).abs().max()
+    print("tcgen05 conv", case, "b_cpasync", b_cpasync, "max err", float(err), "ref max", float(ref.abs().max()))
+    # operands are exactly representable; the only rounding is the bf16 store of the output
+    assert err <= 1e-2 * max(1.0, ref.abs().max())
+
+
+def lstm_ref(x, h, c, wt, b):
+    gates = F.conv2d(torch.cat([x, h], 1), wt, b, padding=1)
+    i, f, o, g = gates.chunk(4, 1)
+    c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+    return torch.sigmoid(o) * torch.tanh(c2), c2
+
+
+@pytest.mark.parametrize("engine_name", ["simt", "tcgen05"])
+@pytest.mark.parametrize("hid,h,w", [(64, 17, 22), (128, 9, 12), (256, 8, 11)])
+def test_lstm_epilogue(engine_name, hid, h, w):
+    from bde2vid_b200 import ops
+    from bde2vid_b200.engine import _pack_conv
+    tc = engine_name == "tcgen05"
+    dtype = torch.bfloat16 if tc else torch.float32
+    engine = ops.ENGINE_TCGEN05 if tc else ops.ENGINE_SIMT
+    g = torch.Generator().manual_seed(hid + h)
+    rnd = (lambda *s: bf16r(torch.randn(*s, generator=g))) if tc else (lambda *s: torch.randn(*s, generator=g))
+    B = 2
+    x, hp = rnd(B, hid, h, w), rnd(B, hid, h, w) * 0.5
+    cp = torch.randn(B, hid, h, w, generator=g)
+    wt = rnd(4 * hid, 2 * hid, 3, 3) / (18 * hid) ** 0.5
+    wt = bf16r(wt) if tc else wt
+    b = torch.randn(4 * hid, generator=g) * 0.1
+    h_ref, c_ref = lstm_ref(x, hp, cp, wt, b)
+    # gate-interleaved packing (n = 4*c + gate), as the engine does
+    wi = wt.view(4, hid, 2 * hid, 3, 3).permute(1, 0, 2, 3, 4).reshape(4 * hid, 2 * hid, 3, 3)
+    bi = b.view(4, hid).t().reshape(-1).contiguous()
+    pw, ld = _pack_conv(wi.to(DEV), dtype)
+    hout = torch.zeros(B, h, w, hid, dtype=dtype, device=DEV)
+    cout = torch.zeros(B, h, w, hid, dtype=torch.float32, device=DEV)
+    ops.gemm(nhwc(x, dtype), pw, bi.to(DEV), hout, n_img=B, h_in=h, w_in=w, c0=hid, n=4 * hid, ksize=3, stride=1, pad=1,
+             a1=nhwc(hp, dtype), c1=hid, w_ld=ld, epi=ops.EPI_LSTM, c_prev=nhwc(cp, torch.float32), c_out=cout,
+             engine=engine, dtype=dtype)
+    torch.cuda.synchronize()
+    eh = (hout.float().cpu().permute(0, 3, 1, 2) - h_ref).abs().max()
+    ec = (cout.cpu().permute(0, 3, 1, 2) - c_ref).abs().max()
+    print("lstm", engine_name, hid, "h err", float(eh), "c err", float(ec))
+    assert ec <= (2e-3 if tc else 2e-5) and eh <= (6e-3 if tc else 2e-5)
+    # first step: c_prev = None means zeros
+    h0_ref, c0_ref = lstm_ref(x, hp, torch.zeros_like(cp), wt, b)
+    ops.gemm(nhwc(x, dtype), pw, bi.to(DEV), hout, n_img=B, h_in=h, w_in=w, c0=hid, n=4 * hid, ksize=3, stride=1, pad=1,
+             a1=nhwc(hp, dtype), c1=hid, w_ld=ld, epi=ops.EPI_LSTM, c_prev=None, c_out=cout, engine=engine, dtype=dtype)
+    torch.cuda.synchronize()
+    assert (cout.cpu().permute(0, 3, 1, 2) - c0_ref).abs().max() <= (2e-3 if tc else 2e-5)
+
+
+@pytest.mark.parametrize("engine_name", ["simt", "tcgen05"])
+def test_store_variants_and_scatter(engine_name):
+    from bde2vid_b200 import ops
+    from bde2vid_b200.engine import _pack_linear
+    tc = engine_name == "tcgen05"
+    dtype = torch.bfloat16 if tc else torch.float32
+    engine = ops.ENGINE_TCGEN05 if tc else ops.ENGINE_SIMT
+    tol = 2e-2 if tc else 3e-5
+    g = torch.Generator().manual_seed(7)
+    M, K, N = 777, 256, 64
+    a = torch.randn(M, K, generator=g)
+    wt = torch.randn(N, K, generator=g) / K ** 0.5
+    if tc:
+        a, wt = bf16r(a), bf16r(wt)
+    b = torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+    pw, ld = _pack_linear(wt.to(DEV), dtype)
+    ad = a.to(DEV, dtype).contiguous()
+    bd = b.to(DEV)
+    # fp32 output + residual + second copy (fc2 + residual, DTransformer.py:302-304)
+    out = torch.zeros(M, N, dtype=torch.float32, device=DEV)
+    out2 = torch.zeros(M, N, dtype=dtype, device=DEV)
+    ops.gemm(ad, pw, bd, out, n_img=1, h_in=M, w_in=1, c0=K, n=N, w_ld=ld, out_f32=True, residual=res.to(DEV),
+             out2=out2, engine=engine, dtype=dtype)
+    ref = res + F.linear(a, wt, b)
+    torch.cuda.synchronize()
+    assert (out.cpu() - ref).abs().max() <= tol
+    assert (out2.float().cpu() - ref).abs().max() <= (5e-2 if tc else tol)
+    # GELU
+    outg = torch.zeros(M, N, dtype=dtype, device=DEV)
+    ops.gemm(ad, pw, bd, outg, n_img=1, h_in=M, w_in=1, c0=K, n=N, w_ld=ld, act=ops.ACT_GELU, engine=engine, dtype=dtype)
+    torch.cuda.synchronize()
+    assert (outg.float().cpu() - F.gelu(F.linear(a, wt, b))).abs().max() <= (3e-2 if tc else tol)
+    # in-place residual (out aliases residual), as the executor uses it
+    xs = res.to(DEV).clone()
+    ops.gemm(ad, pw, bd, xs, n_img=1, h_in=M, w_in=1, c0=K, n=N, w_ld=ld, out_f32=True, residual=xs, engine=engine, dtype=dtype)
+    torch.cuda.synchronize()
+    assert (xs.cpu() - ref).abs().max() <= tol
+    # scatter: rows -> destination rows (-1 dropped), accumulate into fp32
+    P = 900
+    perm = torch.randperm(P, generator=g)[:M].to(torch.int32)
+    perm[::7] = -1
+    dst0 = torch.randn(P, N, generator=g)
+    dst = dst0.to(DEV).clone()
+    ops.gemm(ad, pw, bd, dst, n_img=1, h_in=M, w_in=1, c0=K, n=N, w_ld=ld, epi=ops.EPI_SCATTER, row_map=perm.to(DEV),
+             engine=engine, dtype=dtype)
+    torch.cuda.synchronize()
+    refd = dst0.clone()
+    lin = F.linear(a, wt, b)
+    keep = perm >= 0
+    refd[perm[keep].long()] += lin[keep]
+    assert (dst.cpu() - refd).abs().max() <= tol
+
+
+def test_tcgen05_large_k_and_m_tiles():
+    """Long K loop (many pipeline wraps) and many M tiles, checked against the CUDA-core engine."""
+    from bde2vid_b200 import ops
+    from bde2vid_b200.engine import _pack_conv
+    g = torch.Generator().manual_seed(11)
+    n, ci, co, h, w = 2, 512, 128, 40, 44
+    x = bf16r(torch.randn(n, ci, h, w, generator=g))
+    wt = bf16r(torch.randn(co, ci, 3, 3, generator=g) / (9 * ci) ** 0.5)
+    b = torch.randn(co, generator=g)
+    got_tc = run_conv([x], wt, b, 1, ops.ENGINE_TCGEN05, torch.bfloat16)
+    got_simt = run_conv([x], wt, b, 1, ops.ENGINE_SIMT, torch.bfloat16)
+    ref = F.conv2d(x, wt, b, padding=1)
+    print("large: tc-vs-ref", float((got_tc - ref).abs().max()), "simt-vs-ref", float((got_simt - ref).abs().max()))
+    assert (got_tc - ref).abs().max() <= 2e-2
+    assert (got_simt - ref).abs().max() <= 2e-2

@@ -1,0 +1,118 @@
+"""GPU parity: the drop-in BDE2VID model (whole forward through the C ABI) against the reference's
+committed outputs (tests/golden) and against the oracle port on fresh inputs."""
+import numpy as np
+import pytest
+import torch
+
+from bde2vid_b200 import synth
+from conftest import load_golden
+from oracle import oracle_torch as O
+from oracle.make_golden import MODEL_CASES, voxel_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+# frame gate of the north star: max-abs <= 2e-3 vs the reference fp32 path (bf16 operands, fp32 accumulate);
+# the CUDA-core fp32 engine must be far tighter.
+TOL = {"fp32": 2e-4, "bf16": 2e-3, "bf16-simt": 2e-3}
+
+
+def build_model(over, wseed, precision):
+    from bde2vid_b200.model import BDE2VID
+    cfg = O.full_cfg(over)
+    gen_cfg = {k: cfg[k] for k in ("type", "num_bins", "basechannels", "num_encoders", "ks", "num_res_blocks",
+                                    "buffer_index", "q_idx", "depths", "num_heads", "losses")}
+    model = BDE2VID(generator=gen_cfg)
+    sd = synth.init_state_dict(cfg, wseed, stress=True)
+    missing = model.load_state_dict(sd, strict=True)
+    model = model.eval().to(DEV)
+    model.generator.precision = precision
+    return model, cfg, sd
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16-simt", "bf16"])
+@pytest.mark.parametrize("name", list(MODEL_CASES))
+def test_golden_frames(name, precision):
+    H, W, T, N, over, wseed, sid = MODEL_CASES[name]
+    g = load_golden(name)
+    model, cfg, sd = build_model(over, wseed, precision)
+    vox, _ = voxel_inputs(sid, T, H, W, N)
+    with torch.no_grad():
+        out = model([{"events": v.to(DEV)} for v in vox])
+    assert len(out) == T and out[0].shape == (1, 1, H, W) and out[0].dtype == torch.float32
+    frames = torch.cat(out, 0).cpu().numpy()
+    err = np.abs(frames - g["ref_frames"]).max()
+    mse_delta = abs(float(((frames - g["ref_frames"]) ** 2).mean()))
+    print(name, precision, "max-abs", float(err), "mse", mse_delta)
+    assert err <= TOL[precision]
+    assert mse_delta <= 1e-3
+    ssim = [O.ssim_uniform7(torch.from_numpy(frames[t]), torch.from_numpy(g["ref_frames"][t])) for t in range(T)]
+    assert min(ssim) >= 1 - 1e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graph_replay_and_repeatability(precision):
+    """Second and third calls go through the captured CUDA graph; results must not change and states
+    must not leak between calls (bde2vid.py:31 resets them)."""
+    H, W, T, N, over, wseed, sid = MODEL_CASES["bde2vid_56x80_T3_q0"]
+    model, cfg, sd = build_model(over, wseed, precision)
+    vox, _ = voxel_inputs(sid, T, H, W, N)
+    inp = [{"events": v.to(DEV)} for v in vox]
+    with torch.no_grad():
+        a = torch.cat(model(inp), 0)
+        b = torch.cat(model(inp), 0)
+        c = torch.cat(model(inp), 0)
+        other = torch.cat(model([{"events": torch.zeros_like(v["events"])} for v in inp]), 0)
+        d = torch.cat(model(inp), 0)
+    assert torch.equal(a, b) and torch.equal(b, c) and torch.equal(c, d)
+    assert not torch.equal(other, a)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fresh_inputs_vs_oracle_batch2(precision):
+    """Batch of 2 independent sequences, odd attention padding, against the oracle run here."""
+    over = dict(depths=[2, 0, 2])
+    model, cfg, sd = build_model(over, 4, precision)
+    g = torch.Generator().manual_seed(9)
+    T, H, W = 4, 72, 88
+    vox = [torch.randn(2, 5, H, W, generator=g) * (torch.rand(2, 5, H, W, generator=g) < 0.3) for _ in range(T)]
+    with torch.no_grad():
+        ref = O.bde2vid_forward(sd, cfg, vox)
+        out = model([{"events": v.to(DEV)} for v in vox])
+    err = max(float((a.cpu() - b).abs().max()) for a, b in zip(out, ref))
+    print("batch2", precision, err)
+    assert err <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fused_events_to_frames(precision):
+    """Raw events -> voxeliser -> UNet in one call, at a size that needs Croper padding."""
+    H, W, T, N = 60, 90, 3, 2500          # pads to 64 x 96
+    model, cfg, sd = build_model(dict(depths=[1, 0, 1]), 6, precision)
+    ev = synth.gen_events(31, T, H, W, N)
+    xs, ys, ts, ps, off = synth.to_loader_format_seq(ev)
+    prm = O.croper_params(W, H, 3)
+    vox = []
+    for w in range(T):
+        a, b = int(off[w]), int(off[w + 1])
+        vox.append(O.pad_voxel(torch.from_numpy(O.voxel_grid(xs[a:b], ys[a:b], ts[a:b], ps[a:b], 5, (H, W)))[None], prm))
+    with torch.no_grad():
+        ref = [O.crop_image(f, prm) for f in O.bde2vid_forward(sd, cfg, vox)]
+        for _ in range(3):   # eager, capture, replay
+            out = model.reconstruct_events(*(torch.from_numpy(a).to(DEV) for a in (xs, ys, ts, ps, off)), (H, W))
+    assert out[0].shape == (1, 1, H, W)
+    err = max(float((a.cpu() - b).abs().max()) for a, b in zip(out, ref))
+    print("fused", precision, err)
+    assert err <= TOL[precision]
+
+
+def test_no_cpu_fallback():
+    from bde2vid_b200.model import BDE2VID
+    cfg = O.full_cfg(dict(depths=[1, 0, 1]))
+    gen_cfg = {k: cfg[k] for k in ("type", "num_bins", "basechannels", "num_encoders", "ks", "num_res_blocks",
+                                    "buffer_index", "q_idx", "depths", "num_heads", "losses")}
+    model = BDE2VID(generator=gen_cfg).eval()
+    with pytest.raises(RuntimeError):
+        model([{"events": torch.zeros(1, 5, 64, 64)}])
+    with pytest.raises(NotImplementedError):
+        BDE2VID(generator=dict(gen_cfg, norm="BN"))

@@ -1,0 +1,128 @@
+"""GPU parity: element-wise / gather / attention kernels vs functional torch on the CPU."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import oracle_torch as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def nhwc(x, dtype=torch.float32):
+    return x.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)
+
+
+def nchw(x):
+    return x.float().cpu().permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_upsample2x_sum(dtype):
+    from bde2vid_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    n, c, h, w = 2, 64, 9, 13
+    skip = torch.randn(n, c, h, w, generator=g)
+    x = torch.randn(n, c, h, w, generator=g)
+    xr = x.to(dtype).float()
+    ref = F.interpolate(skip + xr, scale_factor=2, mode="bilinear", align_corners=False)
+    dst = torch.zeros(n, 2 * h, 2 * w, c, dtype=dtype, device=DEV)
+    ops.upsample2x_sum(nhwc(skip), nhwc(x, dtype), 1.0, n, h, w, c, dst)
+    torch.cuda.synchronize()
+    tol = 1e-5 if dtype == torch.float32 else 4e-2
+    assert (nchw(dst) - ref).abs().max() <= tol
+    # quirk Q2: skip = None, x_scale = 2 (fp32 source)
+    ref2 = F.interpolate(2 * skip, scale_factor=2, mode="bilinear", align_corners=False)
+    ops.upsample2x_sum(None, nhwc(skip), 2.0, n, h, w, c, dst)
+    torch.cuda.synchronize()
+    assert (nchw(dst) - ref2).abs().max() <= tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_pred_sigmoid_and_add(dtype):
+    from bde2vid_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    P, c = 1000, 32
+    x = torch.randn(P, c, generator=g).to(dtype)
+    hd = torch.randn(P, c, generator=g).to(dtype)
+    wt = torch.randn(c, generator=g) * 0.3
+    b = torch.randn(1, generator=g)
+    img = torch.zeros(P, device=DEV)
+    ops.pred_sigmoid(x.to(DEV), hd.to(DEV), wt.to(DEV), b.to(DEV), c, P, img)
+    ref = torch.sigmoid((x.float() + hd.float()) @ wt + b)
+    torch.cuda.synchronize()
+    assert (img.cpu() - ref).abs().max() <= 2e-6
+    a32 = torch.randn(P, c, generator=g)
+    of = torch.zeros(P, c, device=DEV)
+    ot = torch.zeros(P, c, device=DEV, dtype=dtype)
+    ops.add(x.to(DEV), a32.to(DEV), out_f32=of, out_t=None if dtype == torch.float32 else ot, dtype=dtype)
+    torch.cuda.synchronize()
+    assert (of.cpu() - (x.float() + a32)).abs().max() <= 1e-6
+    if dtype != torch.float32:
+        assert (ot.float().cpu() - (x.float() + a32)).abs().max() <= 3e-2
+
+
+@pytest.mark.parametrize("H,W", [(12, 20), (9, 13), (7, 30), (33, 44)])
+def test_window_token_map_matches_oracle(H, W):
+    """Host logic cross-check (runs on the GPU box because the product module needs the device for the map)."""
+    from bde2vid_b200.engine import window_token_map
+    for dil in (False, True):
+        mine, g = window_token_map(2, H, W, (7, 7), dil, "cpu")
+        idx, ok, g2 = O.window_token_map(H, W, dil)
+        nwin = idx.shape[0]
+        assert mine.shape == (2 * nwin, 49)
+        assert torch.equal(mine[:nwin].long(), idx)
+        second = torch.where(idx >= 0, idx + H * W, idx)
+        assert torch.equal(mine[nwin:].long(), second)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_ln_gather_and_layernorm(dtype):
+    from bde2vid_b200 import ops
+    from bde2vid_b200.engine import window_token_map
+    g = torch.Generator().manual_seed(2)
+    B, C, H, W, D = 2, 64, 9, 13, 3
+    frames = [torch.randn(B * H * W, C, generator=g) for _ in range(D)]
+    frames[2] = None
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    for dil in (False, True):
+        tm, geo = window_token_map(B, H, W, (7, 7), dil, DEV)
+        nwin = tm.shape[0]
+        out = torch.zeros(nwin, D, 49, C, dtype=dtype, device=DEV)
+        ops.ln_gather([None if f is None else f.to(DEV) for f in frames], tm, nwin, 49, C, gamma.to(DEV), beta.to(DEV), out)
+        torch.cuda.synchronize()
+        tmc = tm.cpu().long()
+        for d in range(D):
+            src = torch.zeros(B * H * W, C) if frames[d] is None else frames[d]
+            tok = src[tmc.clamp(min=0).reshape(-1)].reshape(nwin, 49, C) * (tmc >= 0).unsqueeze(-1)
+            ref = F.layer_norm(tok, (C,), gamma, beta, 1e-5)
+            err = (out[:, d].float().cpu() - ref).abs().max()
+            assert err <= (2e-5 if dtype == torch.float32 else 5e-2), (dil, d, float(err))
+    x = torch.randn(500, 256, generator=g) * 3 + 1
+    g2, b2 = torch.randn(256, generator=g), torch.randn(256, generator=g)
+    o = torch.zeros(500, 256, dtype=dtype, device=DEV)
+    ops.layernorm(x.to(DEV), 500, 256, g2.to(DEV), b2.to(DEV), o)
+    torch.cuda.synchronize()
+    assert (o.float().cpu() - F.layer_norm(x, (256,), g2, b2, 1e-5)).abs().max() <= (3e-5 if dtype == torch.float32 else 6e-2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,heads,D", [(64, 16, 3), (256, 16, 3), (128, 16, 5), (64, 16, 2)])
+def test_window_attention(dtype, C, heads, D):
+    from bde2vid_b200 import ops
+    g = torch.Generator().manual_seed(C + D)
+    nwin, nq = 5, 49
+    nkv = D * 49
+    hd = C // heads
+    q = (torch.randn(nwin, nq, C, generator=g) * hd ** -0.5).to(dtype)
+    kv = torch.randn(nwin, nkv, 2 * C, generator=g).to(dtype)
+    bias = torch.randn(heads, nq, nkv, generator=g)
+    qh = q.float().view(nwin, nq, heads, hd).permute(0, 2, 1, 3)
+    kh = kv.float()[..., :C].reshape(nwin, nkv, heads, hd).permute(0, 2, 1, 3)
+    vh = kv.float()[..., C:].reshape(nwin, nkv, heads, hd).permute(0, 2, 1, 3)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) + bias, -1) @ vh).permute(0, 2, 1, 3).reshape(nwin, nq, C)
+    out = torch.zeros(nwin, nq, C, dtype=dtype, device=DEV)
+    ops.window_attention(q.to(DEV), kv.to(DEV), bias.permute(0, 2, 1).contiguous().to(DEV), nwin, nq, nkv, C, heads, out)
+    torch.cuda.synchronize()
+    assert (out.float().cpu() - ref).abs().max() <= (2e-5 if dtype == torch.float32 else 2e-2)
