@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Headline benchmark: reconstructed frames/s of the BDE2VID hot path (voxelise + UNet forward).
+
+Workload (BASELINE.json configs[1]): one synthetic 346x260 event sequence per step, T windows of
+31,500 events, 5-bin voxels, batch 1, assumed cfg of SURVEY.md section 8, seed-0 random weights,
+fused voxelise + UNet on one B200.  With N GPUs every rank processes its own sequences (weak scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16|fp32]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from bde2vid_b200 import synth  # noqa: E402
+
+H, W, NEV, BINS = 260, 346, 31500, 5
+# algorithmic work per frame of the reference graph at 264x352: conv + linear FLOPs
+# are executed by the implicit-GEMM kernel, bmm FLOPs by the window-attention kernel.
+GF_CONV, GF_LINEAR, GF_BMM = 125.79, 32.36, 5.19
+VOXEL_BYTES_PER_WINDOW = 16 * NEV + 4 * BINS * H * W
+
+
+def cfg_dict():
+    ns = {}
+    exec(synth.ASSUMED_CFG_STR, ns)
+    return ns["model"]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return None
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores (bounded sample)
+# ------------------------------------------------------------------------------------------------
+
+def cpu_reference_fps(T_sample, seq_id=0, threads=None):
+    """frames/s of voxelise (numpy restatement) + oracle forward (functional torch, fp32) for T_sample
+    windows of the bench workload.  This is the reference algorithm on the CPU ('port')."""
+    from oracle import oracle_torch as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = O.full_cfg(cfg_dict()["generator"])
+    sd = synth.init_state_dict(cfg, 0)
+    ev = synth.gen_events(seq_id, T_sample, H, W, NEV)
+    prm = O.croper_params(W, H, 3)
+    t0 = time.perf_counter()
+    vox = []
+    for w in range(T_sample):
+        xs, ys, ts, ps = synth.to_loader_format(ev, w)
+        vox.append(O.pad_voxel(torch.from_numpy(O.voxel_grid(xs, ys, ts, ps, BINS, (H, W)))[None], prm))
+    with torch.no_grad():
+        out = O.bde2vid_forward(sd, cfg, vox)
+    _ = [O.crop_image(o, prm) for o in out]
+    dt = time.perf_counter() - t0
+    return T_sample / dt, dt, threads
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    T_s = args.ref_windows
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_reference_fps(2)
+    times = []
+    for _ in range(max(1, min(args.steps, 3))):
+        fps, dt, threads = cpu_reference_fps(T_s)
+        times.append(dt)
+    dt = float(np.mean(times))
+    val = T_s / dt
+    line = {
+        "impl": "reference", "metric": "reconstructed frames/s (346x260, 5-bin)", "value": val, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, T_s, note="CPU arm: bounded sample of the same workload"),
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": "%d of %d windows of one 346x260 sequence (oracle port of the reference path; the "
+                                   "reference itself cannot travel to the GPU box)" % (T_s, args.windows)},
+        "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, T, note=None):
+    c = {"workload": "BDE2VID assumed-cfg, seed-0 weights, one synthetic %dx%d sequence per step, T=%d windows x %d "
+                     "events, %d-bin voxels, batch 1, fused voxelise+UNet (BASELINE.json configs[1])" % (W, H, T, NEV, BINS),
+         "windows_per_step": T, "events_per_window": NEV, "padded": "264x352",
+         "l2_policy": "no flush: one step streams >2 GB of activations (>>126 MB L2) between re-reads of its inputs"}
+    if note:
+        c["note"] = note
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("BDE2VID_PRECISION", "bf16"))
+    ap.add_argument("--windows", type=int, default=100, help="T: windows (= frames) per sequence")
+    ap.add_argument("--ref-windows", type=int, default=6, help="windows of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-timing", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from bde2vid_b200 import ops
+    from bde2vid_b200.model import MODELS
+
+    warm = max(3, args.warmup)
+    T = args.windows
+    model = MODELS.build(cfg_dict())
+    model.load_state_dict(synth.init_state_dict(cfg_dict()["generator"], 0), strict=True)
+    model = model.eval().to(dev)
+    model.generator.precision = args.precision
+
+    # per-rank sequences: rank r processes seq ids r, r+world, ... (independent units; no data-path collective)
+    n_seq = 2
+    host = []
+    for i in range(n_seq):
+        ev = synth.gen_events(rank + i * world, T, H, W, NEV)
+        xs, ys, ts, ps, off = synth.to_loader_format_seq(ev)
+        host.append([torch.from_numpy(a).pin_memory() for a in (xs, ys, ts, ps, off)])
+    resident = [[a.to(dev) for a in h] for h in host]
+    h2d_bytes = sum(a.numel() * a.element_size() for a in host[0])
+    d2h_bytes = T * H * W * 4
+
+    def step_resident(i):
+        return model.reconstruct_events(*resident[i % n_seq], (H, W))
+
+    out_host = torch.empty(T, 1, 1, H, W).pin_memory()
+
+    def step_e2e(i):
+        # pinned host arrays go straight into the plan's static device buffers (async H2D on the stream)
+        frames = model.reconstruct_events(*host[i % n_seq], (H, W))
+        out_host.copy_(torch.stack(frames, 0), non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    with torch.no_grad():
+        for i in range(warm):
+            step_resident(i)
+        sampler = ClockSampler(local)
+        sampler.start()
+        ms = timed(step_resident, args.steps)
+        clocks = sampler.stop()
+        for i in range(2):
+            step_e2e(i)
+        ms_e2e = timed(step_e2e, args.steps)
+
+    eng = model.generator.engine()
+    plan = eng.plan(T, 1, 264, 352)
+    launches_per_step = plan.launches
+    fps = world * args.steps * T / (ms * 1e-3)
+    fps_e2e = world * args.steps * T / (ms_e2e * 1e-3)
+
+    # checksum of the reconstructed frames, reduced over ranks (the path's only collective: metric reduction)
+    with torch.no_grad():
+        frames = step_resident(0)
+        chk = torch.stack([f.double().mean() for f in frames]).sum().reshape(1)
+    if world > 1:
+        dist.all_reduce(chk)
+    chk = float(chk.item()) / (world * T)
+
+    pk = peaks()
+    roofline = None
+    voxel_roof = None
+    if not args.no_kernel_timing:
+        # live per-kernel timing: one eager (non-graph) pass with CUDA events around every launch of the
+        # dominant kernel (the implicit-GEMM engine) on the launching stream
+        from bde2vid_b200 import engine as engmod
+        rec = []
+        orig = ops.gemm
+
+        def timed_gemm(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig(*a, **k)
+            e.record()
+            rec.append((s, e))
+            return r
+        engmod.ops.gemm = timed_gemm
+        try:
+            with torch.no_grad():
+                plan._enqueue(True)
+            torch.cuda.synchronize()
+        finally:
+            engmod.ops.gemm = orig
+        gemm_ms = sum(s.elapsed_time(e) for s, e in rec)
+        flops = (GF_CONV + GF_LINEAR) * 1e9 * T
+        ach = flops / (gemm_ms * 1e-3) / 1e12
+        peak = pk["tc_sustained"]
+        roofline = {"kernel": "gemm_tc_kernel (tcgen05 implicit GEMM: all convs + linears)", "bound": "tensor",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "launches": len(rec), "avg_launch_us": gemm_ms * 1e3 / max(1, len(rec)),
+                    "kernel_ms_per_step": gemm_ms, "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
+                    "flops_per_step": flops}
+        # voxeliser alone, all T windows in one launch (HBM-bound)
+        xs, ys, ts, ps, off = resident[0]
+        vout = torch.empty(T, BINS, 264, 352, device=dev)
+        for _ in range(3):
+            ops.voxelize_seq(xs, ys, ts, ps, off, BINS, H, W, 2, 3, 264, 352, out=vout)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(10):
+            ops.voxelize_seq(xs, ys, ts, ps, off, BINS, H, W, 2, 3, 264, 352, out=vout)
+        e.record()
+        torch.cuda.synchronize()
+        vms = s.elapsed_time(e) / 10
+        vach = VOXEL_BYTES_PER_WINDOW * T / (vms * 1e-3) / 1e9
+        voxel_roof = {"kernel": "voxel_band_kernel", "bound": "hbm", "achieved": vach, "peak": pk["hbm"], "unit": "GB/s",
+                      "frac": vach / pk["hbm"], "traffic": None, "ms_per_launch": vms,
+                      "bytes_per_launch": VOXEL_BYTES_PER_WINDOW * T}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt, threads = cpu_reference_fps(args.ref_windows)
+        cpu = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": "%d of %d windows of the same 346x260 sequence, oracle port (numpy voxeliser + functional torch "
+                         "fp32), %.1f s" % (args.ref_windows, T, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": "reconstructed frames/s (346x260, 5-bin)", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision.startswith("bf16") else "f32",
+            "data": "synthetic", "config": workload_config(args, T),
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks, "roofline": roofline, "roofline_voxeliser": voxel_roof, "cpu_baseline": cpu,
+            "tflops_algorithmic": fps / world * (GF_CONV + GF_LINEAR + GF_BMM) / 1e3,
+            "frame_checksum": chk, "precision": args.precision,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
