@@ -53,6 +53,10 @@ EXPORTS = {
     "bde_layernorm": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                 C.c_void_p]),
     "bde_window_attention": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_void_p]),
+    "bde_ln_gather_qkv": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+                          + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]),
+    "bde_window_attention_mma_bias_stride": (C.c_int, [C.c_int]),
+    "bde_window_attention_mma": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "bde_cast": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
 }
 

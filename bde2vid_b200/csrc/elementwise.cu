@@ -144,6 +144,68 @@ __global__ void ln_gather_kernel(FramePtrs frames, int D, const int* __restrict_
   ln_row<T>(src, c, gamma, beta, out + row * c, lane);
 }
 
+// Fused q + kv variant: norm_q and norm_kv of the query frame share mean / rstd, so one pass over the
+// window tokens writes the kv tokens of every frame and, for the query slot, the q tokens as well.
+// Vectorised: each lane owns VEC consecutive channels (c == 32 * VEC).
+template <typename T, int VEC>
+__global__ void ln_gather_qkv_kernel(FramePtrs frames, int D, int q_slot, const int* __restrict__ tok_map, int n_tok,
+                                     const float* __restrict__ g_kv, const float* __restrict__ b_kv,
+                                     const float* __restrict__ g_q, const float* __restrict__ b_q,
+                                     T* __restrict__ out_kv, T* __restrict__ out_q, size_t total_rows) {
+  constexpr int C = 32 * VEC;
+  size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // (win, d, tok)
+  const int lane = threadIdx.x & 31;
+  if (row >= total_rows) return;
+  const int tok = (int)(row % n_tok);
+  const size_t r = row / n_tok;
+  const int d = (int)(r % D);
+  const size_t win = r / D;
+  const int pix = tok_map[win * n_tok + tok];
+  const float* fr = frames.f[d];
+  float v[VEC];
+  if (fr != nullptr && pix >= 0) {
+    const float* src = fr + (size_t)pix * C + lane * VEC;
+    if (VEC == 2) {
+      float2 t = *reinterpret_cast<const float2*>(src);
+      v[0] = t.x; v[1] = t.y;
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; i += 4) {
+        float4 t = *reinterpret_cast<const float4*>(src + i);
+        v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = 0.f;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s += v[i];
+  const float mean = warp_sum(s) / (float)C;
+  float qq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i] -= mean;
+    qq += v[i] * v[i];
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(qq) / (float)C + 1e-5f);
+  auto emit = [&](const float* gm, const float* bt, T* dst) {
+    float o[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] = v[i] * rstd * __ldg(gm + lane * VEC + i) + __ldg(bt + lane * VEC + i);
+    if (VEC == 2) {
+      dst[0] = from_f32<T>(o[0]);
+      dst[1] = from_f32<T>(o[1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; i += 4) store4<T>(dst + i, make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]));
+    }
+  };
+  emit(g_kv, b_kv, out_kv + row * C + lane * VEC);
+  if (d == q_slot && out_q != nullptr) emit(g_q, b_q, out_q + (win * n_tok + tok) * (size_t)C + lane * VEC);
+}
+
 template <typename T>
 __global__ void layernorm_kernel(const float* __restrict__ x, size_t rows, int c, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, T* __restrict__ out) {
@@ -243,6 +305,36 @@ extern "C" int bde_ln_gather(const float* const* frames_host, int D, const int* 
   else
     ln_gather_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(fp, D, tok_map, n_tok, c, gamma, beta, (__nv_bfloat16*)out, rows);
   return check_launch("ln_gather_kernel");
+}
+
+template <typename T>
+static int launch_ln_gather_qkv(const FramePtrs& fp, int D, int q_slot, const int* tok_map, int n_tok, int c,
+                                const float* g_kv, const float* b_kv, const float* g_q, const float* b_q, void* out_kv,
+                                void* out_q, size_t rows, cudaStream_t s) {
+  unsigned blocks = (unsigned)ceil_div(rows * 32, 256);
+#define BDE_LNQKV(VEC_)                                                                                              \
+  ln_gather_qkv_kernel<T, VEC_><<<blocks, 256, 0, s>>>(fp, D, q_slot, tok_map, n_tok, g_kv, b_kv, g_q, b_q, (T*)out_kv, \
+                                                       (T*)out_q, rows)
+  if (c == 64) BDE_LNQKV(2);
+  else if (c == 128) BDE_LNQKV(4);
+  else if (c == 256) BDE_LNQKV(8);
+  else BDE_REQUIRE(false, "bde_ln_gather_qkv: c must be 64, 128 or 256 (use bde_ln_gather otherwise)");
+#undef BDE_LNQKV
+  return check_launch("ln_gather_qkv_kernel");
+}
+
+extern "C" int bde_ln_gather_qkv(const float* const* frames_host, int D, int q_slot, const int* tok_map, int n_win,
+                                 int n_tok, int c, const float* g_kv, const float* b_kv, const float* g_q,
+                                 const float* b_q, void* out_kv, void* out_q, int dtype, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  BDE_REQUIRE(D >= 1 && D <= 8 && q_slot >= 0 && q_slot < D, "bde_ln_gather_qkv: bad D / q_slot");
+  FramePtrs fp;
+  for (int i = 0; i < 8; ++i) fp.f[i] = i < D ? frames_host[i] : nullptr;
+  size_t rows = (size_t)n_win * D * n_tok;
+  if (rows == 0) return 0;
+  if (dtype == BDE_F32)
+    return launch_ln_gather_qkv<float>(fp, D, q_slot, tok_map, n_tok, c, g_kv, b_kv, g_q, b_q, out_kv, out_q, rows, s);
+  return launch_ln_gather_qkv<__nv_bfloat16>(fp, D, q_slot, tok_map, n_tok, c, g_kv, b_kv, g_q, b_q, out_kv, out_q, rows, s);
 }
 
 extern "C" int bde_layernorm(const float* x, size_t rows, int c, const float* gamma, const float* beta, void* out,

@@ -2,14 +2,17 @@
 //
 //   C[m, n] = sum_k A[m, k] * W[n, k]      m = (img, oy, ox),  k = (tap, channel)
 //
-// One CTA computes a 128 x BN output tile.  Warp roles (192 threads):
-//   warps 0-3  A producers: thread r owns tile row r (one output pixel).  Per 64-wide K block it
-//              gathers the 128 bytes of that pixel's im2col row with 8 cp.async (zero fill for
-//              padding / K tail / M tail) into the 128B-swizzled K-major layout UMMA expects.
-//              After the main loop the same warps run the epilogue (warp w <-> TMEM lanes 32w..).
-//   warp 4     B producer: one thread issues a TMA 2D tiled load (SWIZZLE_128B) of the
+// One CTA computes a 128 x BN output tile.  Warp roles (320 threads):
+//   warps 0-7  A producers.  8 consecutive lanes fetch the 8 16-byte chunks of one 128-byte im2col
+//              row (cp.async, zero fill for padding / K tail / M tail) into the 128B-swizzled
+//              K-major layout UMMA expects, so a warp-wide copy touches 4 full cache lines.
+//              Everything that depends only on the output pixel (base index, per-tap validity
+//              mask) is computed once; the per-K-block work is a handful of integer ops per row.
+//              After the main loop the same warps run the epilogue (warp w <-> TMEM lanes
+//              32*(w&3).., column half w>>2).
+//   warp 8     B producer: one thread issues a TMA 2D tiled load (SWIZZLE_128B) of the
 //              [BN x 64] weight tile per K block.  (kBTma=false: cp.async gather, for bring-up.)
-//   warp 5     MMA issuer: one thread issues 4 x tcgen05.mma (M128 x BN x K16) per K block and
+//   warp 9     MMA issuer: one thread issues 4 x tcgen05.mma (M128 x BN x K16) per K block and
 //              commits to the stage's "empty" barrier; owns the TMEM allocation.
 // Pipelines: smem full/empty mbarriers per stage, one "accumulator ready" mbarrier.
 // Epilogues are fused: bias + activation (+ fp32 residual), ConvLSTM gate math, window scatter.
@@ -30,8 +33,11 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 elements = 128 bytes = one swizzle row
-constexpr int kNumProducerThreads = 128;
-constexpr int kThreads = 192;
+constexpr int kNumProducerWarps = 8;
+constexpr int kNumProducerThreads = kNumProducerWarps * 32;
+constexpr int kRowsPerThread = BM / (kNumProducerWarps * 4);  // 4
+constexpr int kThreads = kNumProducerThreads + 64;
+constexpr int kTmaWarp = kNumProducerWarps, kMmaWarp = kNumProducerWarps + 1;
 
 struct TcParams {
   const __nv_bfloat16* a0;
@@ -58,9 +64,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -86,10 +89,10 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+// arrive on `bar` once all cp.async issued so far by this thread have landed (counted in the
+// barrier's expected arrivals: .noinc)
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -155,6 +158,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 
 template <int BN>
 struct TileCfg {
+  // 3 stages of 32 KB keep two CTAs resident per SM (mainloop of one overlaps the epilogue of the other)
   static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
@@ -162,6 +166,23 @@ struct TileCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
+
+// fast transcendental forms for the bf16 path (relative error ~1e-6, far below bf16 resolution)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+  uint4 pk;
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 t1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]);
+  __nv_bfloat162 t3 = __floats2bfloat162_rn(v[6], v[7]);
+  pk.x = *reinterpret_cast<uint32_t*>(&t0);
+  pk.y = *reinterpret_cast<uint32_t*>(&t1);
+  pk.z = *reinterpret_cast<uint32_t*>(&t2);
+  pk.w = *reinterpret_cast<uint32_t*>(&t3);
+  return pk;
+}
 
 // ------------------------------------------------------------------------------------------
 // epilogue for one row (m) and 32 consecutive columns [nb, nb+32)
@@ -178,8 +199,16 @@ __device__ __forceinline__ void epilogue_row32(const TcParams& p, int m, int nb,
     }
   }
   if (p.epi == BDE_EPI_STORE) {
+    if (p.act == BDE_ACT_RELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+    } else if (p.act == BDE_ACT_RELU6) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], 0.0f), 6.0f);
+    } else if (p.act != BDE_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+    }
     const size_t o = (size_t)m * p.N + nb;
     if (p.residual != nullptr) {
 #pragma unroll
@@ -197,21 +226,10 @@ __device__ __forceinline__ void epilogue_row32(const TcParams& p, int m, int nb,
     if (dstb != nullptr) {
       dstb += o;
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 pk;
-        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-        __nv_bfloat162 t1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-        __nv_bfloat162 t3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-        pk.x = *reinterpret_cast<uint32_t*>(&t0);
-        pk.y = *reinterpret_cast<uint32_t*>(&t1);
-        pk.z = *reinterpret_cast<uint32_t*>(&t2);
-        pk.w = *reinterpret_cast<uint32_t*>(&t3);
-        *reinterpret_cast<uint4*>(dstb + j) = pk;
-      }
+      for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(dstb + j) = pack8_bf16(v + j);
     }
   } else if (p.epi == BDE_EPI_LSTM) {
-    // columns = 8 hidden channels x (in, remember, out, cell)
+    // columns = 8 hidden channels x (in, remember, out, cell)   (submodules.py:320-332)
     const int hid = p.N >> 2, ch = nb >> 2;
     const size_t o = (size_t)m * hid + ch;
     float cp[8];
@@ -224,17 +242,13 @@ __device__ __forceinline__ void epilogue_row32(const TcParams& p, int m, int nb,
     }
     float h[8], c[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) lstm_update(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3], cp[j], h[j], c[j]);
+    for (int j = 0; j < 8; ++j) {
+      c[j] = fast_sigmoid(v[4 * j + 1]) * cp[j] + fast_sigmoid(v[4 * j]) * fast_tanh(v[4 * j + 3]);
+      h[j] = fast_sigmoid(v[4 * j + 2]) * fast_tanh(c[j]);
+    }
     *reinterpret_cast<float4*>(p.c_out + o) = make_float4(c[0], c[1], c[2], c[3]);
     *reinterpret_cast<float4*>(p.c_out + o + 4) = make_float4(c[4], c[5], c[6], c[7]);
-    uint4 pk;
-    __nv_bfloat162 t0 = __floats2bfloat162_rn(h[0], h[1]), t1 = __floats2bfloat162_rn(h[2], h[3]);
-    __nv_bfloat162 t2 = __floats2bfloat162_rn(h[4], h[5]), t3 = __floats2bfloat162_rn(h[6], h[7]);
-    pk.x = *reinterpret_cast<uint32_t*>(&t0);
-    pk.y = *reinterpret_cast<uint32_t*>(&t1);
-    pk.z = *reinterpret_cast<uint32_t*>(&t2);
-    pk.w = *reinterpret_cast<uint32_t*>(&t3);
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pk;
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pack8_bf16(h);
   } else {  // BDE_EPI_SCATTER
     const int dst_row = p.row_map[m];
     if (dst_row >= 0) {
@@ -281,7 +295,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
     mbar_init(bar_acc, 1);
     fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
@@ -290,84 +304,96 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   tcgen05_fence_after();
   const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-  if (warp < 4) {
+  if (warp < kNumProducerWarps) {
     // =============================== A producers ========================================
-    const int r = threadIdx.x;  // tile row
-    const int m = m0 + r;
-    const bool row_ok = m < p.M;
-    int img = 0, oy = 0, ox = 0;
-    if (row_ok) {
+    // lane l owns 16-byte chunk j = l & 7 of rows warp*16 + 4*i + (l >> 3), i = 0..3
+    const int j = lane & 7;
+    const int rsub = lane >> 3;
+    const int ntaps = p.ksize * p.ksize;
+    int pix0[kRowsPerThread];        // linear input pixel index of tap (0,0) (may lie outside the image)
+    uint32_t vmask[kRowsPerThread];  // bit t set <=> tap t of this output pixel is inside the image
+    uint32_t dsto[kRowsPerThread];   // swizzled byte offset of this lane's chunk inside a stage
+    {
       const int hw = p.h_out * p.w_out;
-      img = m / hw;
-      const int rem = m - img * hw;
-      oy = rem / p.w_out;
-      ox = rem - oy * p.w_out;
+#pragma unroll
+      for (int i = 0; i < kRowsPerThread; ++i) {
+        const int row = warp * (4 * kRowsPerThread) + i * 4 + rsub;
+        dsto[i] = (uint32_t)row * 128u + (((uint32_t)j ^ (uint32_t)(row & 7)) << 4);
+        const int mm = m0 + row;
+        pix0[i] = 0;
+        vmask[i] = 0u;
+        if (mm < p.M) {
+          const int img = mm / hw;
+          const int rem = mm - img * hw;
+          const int oy = rem / p.w_out;
+          const int ox = rem - oy * p.w_out;
+          const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
+          pix0[i] = (img * p.h_in + iy0) * p.w_in + ix0;
+          // valid taps form a rectangle [ky_lo, ky_hi) x [kx_lo, kx_hi)
+          const int kx_lo = max(0, -ix0), kx_hi = min(p.ksize, p.w_in - ix0);
+          const int ky_lo = max(0, -iy0), ky_hi = min(p.ksize, p.h_in - iy0);
+          uint32_t msk = 0u;
+          if (kx_hi > kx_lo) {
+            const uint32_t xm = ((1u << (kx_hi - kx_lo)) - 1u) << kx_lo;
+            for (int ky = ky_lo; ky < ky_hi; ++ky) msk |= xm << (ky * p.ksize);
+          }
+          vmask[i] = msk;
+        }
+      }
     }
-    const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
-    const uint32_t row_off = (uint32_t)r * 128u;
-    const uint32_t sw = (uint32_t)(r & 7);
-    const bool fast = (p.ctot % BK) == 0;  // a K block never straddles taps or sources
-    constexpr int LAG = 2;                 // k-blocks in flight per thread before the arrive
+    // running (tap, channel) position of this lane's chunk: k = kb*64 + j*8
+    int tap = (j * 8) / p.ctot;
+    int c = (j * 8) - tap * p.ctot;
+    int ky = tap / p.ksize, kx = tap - ky * p.ksize;
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % S;
       const uint32_t ph = (uint32_t)(kb / S) & 1u;
+      const bool from0 = c < p.c0;
+      const __nv_bfloat16* sbase = from0 ? p.a0 + c : p.a1 + (c - p.c0);
+      const int cs = from0 ? p.c0 : p.c1;
+      const int tapoff = ky * p.w_in + kx;
+      const uint32_t tapbit = tap < ntaps ? (1u << tap) : 0u;  // K tail -> zero fill
       mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-      const uint32_t dst_row = smem_a + s * Cfg::kABytes + row_off;
-      if (fast) {
-        const int k0 = kb * BK;
-        const int tap = k0 / p.ctot, c = k0 - tap * p.ctot;
-        const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
-        const int iy = iy0 + ky, ix = ix0 + kx;
-        const bool ok = row_ok && k0 < p.K && iy >= 0 && iy < p.h_in && ix >= 0 && ix < p.w_in;
-        const __nv_bfloat16* src = p.a0;
-        if (ok) {
-          const size_t pix = ((size_t)img * p.h_in + iy) * p.w_in + ix;
-          src = (c < p.c0) ? p.a0 + pix * p.c0 + c : p.a1 + pix * p.c1 + (c - p.c0);
-        }
-        const uint32_t nbytes = ok ? 16u : 0u;
+      const uint32_t stage_a = smem_a + s * Cfg::kABytes;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cp_async_16(dst_row + (((uint32_t)j ^ sw) << 4), src + (ok ? j * 8 : 0), nbytes);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int k = kb * BK + j * 8;
-          const int tap = k / p.ctot, c = k - tap * p.ctot;
-          const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
-          const int iy = iy0 + ky, ix = ix0 + kx;
-          const bool ok = row_ok && k < p.K && iy >= 0 && iy < p.h_in && ix >= 0 && ix < p.w_in;
-          const __nv_bfloat16* src = p.a0;
-          if (ok) {
-            const size_t pix = ((size_t)img * p.h_in + iy) * p.w_in + ix;
-            src = (c < p.c0) ? p.a0 + pix * p.c0 + c : p.a1 + pix * p.c1 + (c - p.c0);
-          }
-          cp_async_16(dst_row + (((uint32_t)j ^ sw) << 4), src, ok ? 16u : 0u);
-        }
+      for (int i = 0; i < kRowsPerThread; ++i) {
+        const bool ok = (vmask[i] & tapbit) != 0u;
+        const __nv_bfloat16* src = ok ? sbase + (size_t)(pix0[i] + tapoff) * cs : p.a0;
+        cp_async_16(stage_a + dsto[i], src, ok ? 16u : 0u);
       }
-      cp_async_commit();
-      if (kb >= LAG) {
-        cp_async_wait<LAG>();
-        fence_proxy_async_smem();
-        mbar_arrive(bar_full + 8 * ((kb - LAG) % S));
+      // asynchronous arrive: fires when this thread's copies for the stage have landed, so the
+      // thread runs ahead by up to S stages without ever blocking on its own loads
+      cp_async_mbar_arrive_noinc(bar_full + 8 * s);
+      // advance to the next K block
+      c += BK;
+      while (c >= p.ctot) {
+        c -= p.ctot;
+        ++tap;
+        if (++kx == p.ksize) {
+          kx = 0;
+          ++ky;
+        }
       }
     }
-    // drain the last LAG groups
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (int kb = (num_kb > LAG ? num_kb - LAG : 0); kb < num_kb; ++kb) mbar_arrive(bar_full + 8 * (kb % S));
 
     // =============================== epilogue ===========================================
+    // thread <-> tile row (TMEM lane) 32*(warp & 3) + lane; the two warps sharing a lane quarter
+    // split the columns in alternating 32-wide chunks
+    const int q = warp & 3, half = warp >> 2;
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < p.M;
     mbar_wait(bar_acc, 0);
     tcgen05_fence_after();
-    const uint32_t lane_taddr = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int cb = 0; cb < BN; cb += 32) {
+    for (int cb = half * 32; cb < BN; cb += 64) {
       uint32_t raw[32];
       tmem_ld_32x32b_x32(lane_taddr + (uint32_t)cb, raw);
       tmem_ld_wait();
       if (row_ok) epilogue_row32(p, m, n0 + cb, raw);
     }
     tcgen05_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == kTmaWarp) {
     // =============================== B producer =========================================
     if (kBTma) {
       if (lane == 0) {
@@ -384,16 +410,12 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
         const int s = kb % S;
         const uint32_t ph = (uint32_t)(kb / S) & 1u;
         mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-        for (int row = lane; row < BN; row += 32) {
-          const __nv_bfloat16* src = p.w + (size_t)(n0 + row) * p.w_ld + kb * BK;
-          const uint32_t dst_row = smem_b + s * Cfg::kBBytes + (uint32_t)row * 128u;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) cp_async_16(dst_row + (((uint32_t)j ^ (uint32_t)(row & 7)) << 4), src + j * 8, 16u);
+        for (int row = lane >> 3; row < BN; row += 4) {
+          const int jj = lane & 7;
+          const __nv_bfloat16* src = p.w + (size_t)(n0 + row) * p.w_ld + kb * BK + jj * 8;
+          cp_async_16(smem_b + s * Cfg::kBBytes + (uint32_t)row * 128u + (((uint32_t)jj ^ (uint32_t)(row & 7)) << 4), src, 16u);
         }
-        cp_async_commit();
-        cp_async_wait<0>();
-        fence_proxy_async_smem();
-        mbar_arrive(bar_full + 8 * s);
+        cp_async_mbar_arrive_noinc(bar_full + 8 * s);
       }
     }
   } else {
@@ -404,6 +426,9 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
         const int s = kb % S;
         const uint32_t ph = (uint32_t)(kb / S) & 1u;
         mbar_wait(bar_full + 8 * s, ph);
+        // operands were written through the generic proxy (cp.async): order them before the
+        // tensor core's async-proxy reads
+        fence_proxy_async_smem();
         tcgen05_fence_after();
         const uint64_t adesc = make_smem_desc(smem_a + s * Cfg::kABytes);
         const uint64_t bdesc = make_smem_desc(smem_b + s * Cfg::kBBytes);
@@ -420,7 +445,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   }
 
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_acc, Cfg::kTmemCols);
   }
@@ -512,8 +537,10 @@ int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s) {
   p.out = d->out; p.out2 = d->out2; p.residual = d->residual; p.c_prev = d->c_prev; p.c_out = d->c_out;
   p.row_map = d->row_map;
   BDE_REQUIRE(p.c0 % 8 == 0 && p.c1 % 8 == 0, "bde_gemm(tcgen05): channel counts must be multiples of 8");
+  BDE_REQUIRE(p.ksize * p.ksize <= 32, "bde_gemm(tcgen05): kernel size up to 5x5");
   BDE_REQUIRE(p.w_ld % BK == 0 && p.w_ld >= p.num_kb * BK, "bde_gemm(tcgen05): w_ld must be a zero-padded multiple of 64");
   BDE_REQUIRE(p.N % 32 == 0, "bde_gemm(tcgen05): N must be a multiple of 32");
+  BDE_REQUIRE((size_t)d->n_img * d->h_in * d->w_in < ((size_t)1 << 31), "bde_gemm(tcgen05): input pixel count overflows int32");
   BDE_REQUIRE((((uintptr_t)d->a0) & 15) == 0 && (((uintptr_t)d->a1) & 15) == 0 && (((uintptr_t)d->w) & 127) == 0,
               "bde_gemm(tcgen05): operands must be 16-byte (weights 128-byte) aligned");
   if (p.M == 0) return 0;

@@ -151,8 +151,12 @@ class Engine:
                         a = blk.attn
                         idx = a.relative_position_index[self.q_ind * n_tok:(self.q_ind + 1) * n_tok, :self.D * n_tok]
                         bias = a.relative_position_bias_table.detach().float()[idx.reshape(-1)]
-                        bias = bias.reshape(n_tok, self.D * n_tok, self.heads).permute(2, 1, 0).contiguous()
+                        bias_hmn = bias.reshape(n_tok, self.D * n_tok, self.heads).permute(2, 0, 1).contiguous()
+                        bias = bias_hmn.permute(0, 2, 1).contiguous()
+                        use_mma = (dt == torch.bfloat16 and n_tok <= 64 and hd in (4, 8, 16) and self.heads % 2 == 0
+                                   and ops.attention_mma_bias_stride(self.D * n_tok) > 0)
                         blocks.append(dict(
+                            bias_mma=ops.pad_bias_for_mma(bias_hmn, self.D * n_tok) if use_mma else None,
                             nq_g=f32(a.norm_q.weight), nq_b=f32(a.norm_q.bias),
                             nkv_g=f32(a.norm_kv.weight), nkv_b=f32(a.norm_kv.bias),
                             q=lin_layer(a.q, hd ** -0.5), kv=lin_layer(a.kv), proj=lin_layer(a.proj),
@@ -172,15 +176,17 @@ class Engine:
                         ksize=layer.ksize, stride=layer.stride, pad=layer.pad, w_ld=layer.w_ld,
                         engine=self.gemm_engine, dtype=self.dtype, **kw)
 
-    def plan(self, T, B, Hp, Wp):
-        key = (T, B, Hp, Wp)
+    def plan(self, T, B, Hp, Wp, slot=0):
+        """``slot`` selects an independent set of buffers + graph, so that several sequences can be
+        in flight at once on different CUDA streams (one slot per stream)."""
+        key = (T, B, Hp, Wp, slot)
         p = self.plans.get(key)
         if p is None:
             p = _Plan(self, T, B, Hp, Wp)
             self.plans[key] = p
         return p
 
-    def forward(self, vox_list, use_graph=True):
+    def forward(self, vox_list, use_graph=True, slot=0):
         """vox_list: T tensors [B, bins, Hp, Wp] float32 (CUDA).  Returns T tensors [B, 1, Hp, Wp]."""
         T = len(vox_list)
         if T == 0:
@@ -195,17 +201,17 @@ class Engine:
         S = 2 ** self.L
         if Hp % S or Wp % S:
             raise ValueError("input %dx%d must be padded to a multiple of %d (Croper.pad)" % (Hp, Wp, S))
-        p = self.plan(T, B, Hp, Wp)
+        p = self.plan(T, B, Hp, Wp, slot)
         torch.stack([v.to(torch.float32) for v in vox_list], dim=0, out=p.vox_in)
         p.run(use_graph, from_events=False)
         img = p.img.clone().view(T, B, 1, Hp, Wp)
         return list(img.unbind(0))
 
-    def forward_events(self, xs, ys, ts, ps, offsets, H, W, crop, use_graph=True):
+    def forward_events(self, xs, ys, ts, ps, offsets, H, W, crop, use_graph=True, slot=0):
         """Fused path: raw events -> frames (voxeliser writes the padded grids the UNet reads)."""
         T = offsets.numel() - 1
         Hp, Wp = crop.height_crop_size, crop.width_crop_size
-        p = self.plan(T, 1, Hp, Wp)
+        p = self.plan(T, 1, Hp, Wp, slot)
         p.set_events(xs, ys, ts, ps, offsets, H, W, crop.padding_top, crop.padding_left)
         p.run(use_graph, from_events=True)
         img = p.img.clone().view(T, 1, 1, Hp, Wp)
@@ -378,11 +384,20 @@ class _Plan:
                 tm = d["tm"][i & 1]
                 fr = list(frames)
                 fr[eng.q_ind] = xs
-                ops.ln_gather([xs], tm, nwin, ntok, C, blk["nq_g"], blk["nq_b"], d["qn"])
-                ops.ln_gather(fr, tm, nwin, ntok, C, blk["nkv_g"], blk["nkv_b"], d["kvn"])
+                if C in (64, 128, 256):
+                    ops.ln_gather_qkv(fr, eng.q_ind, tm, nwin, ntok, C, blk["nkv_g"], blk["nkv_b"], blk["nq_g"],
+                                      blk["nq_b"], d["kvn"], d["qn"])
+                    self.launches -= 1
+                else:
+                    ops.ln_gather([xs], tm, nwin, ntok, C, blk["nq_g"], blk["nq_b"], d["qn"])
+                    ops.ln_gather(fr, tm, nwin, ntok, C, blk["nkv_g"], blk["nkv_b"], d["kvn"])
                 eng._gemm(blk["q"], d["qn"], d["qb"], 1, nwin * ntok, 1, C)
                 eng._gemm(blk["kv"], d["kvn"], d["kvb"], 1, nwin * D * ntok, 1, C)
-                ops.window_attention(d["qb"], d["kvb"], blk["bias"], nwin, ntok, D * ntok, C, eng.heads, d["ob"])
+                if blk["bias_mma"] is not None:
+                    ops.window_attention_mma(d["qb"], d["kvb"], blk["bias_mma"], nwin, ntok, D * ntok, C, eng.heads,
+                                             d["ob"])
+                else:
+                    ops.window_attention(d["qb"], d["kvb"], blk["bias"], nwin, ntok, D * ntok, C, eng.heads, d["ob"])
                 # proj + window_reverse + crop + shortcut: x[pixel] += proj(o); uncovered pixels keep x
                 eng._gemm(blk["proj"], d["ob"], xs, 1, nwin * ntok, 1, C, epi=EPI_SCATTER, row_map=tm.view(-1))
                 ops.layernorm(xs, P, C, blk["n2_g"], blk["n2_b"], d["yn"])

@@ -196,14 +196,17 @@ class BDE2VID(nn.Module):
         _unsupported("forward mode %r (only 'tensor' is on the inference path)" % (mode,))
 
     # fused entry point: raw events -> frames without materialising voxel grids on the host
-    def reconstruct_events(self, xs, ys, ts, ps, offsets, sensor_size, num_encoders=None):
-        """events (float32 loader format, CUDA) + CSR offsets -> list of T cropped frames [1,1,H,W]."""
+    def reconstruct_events(self, xs, ys, ts, ps, offsets, sensor_size, num_encoders=None, slot=0):
+        """events (float32 loader format; CUDA or pinned host) + CSR offsets -> list of T cropped frames
+        [1,1,H,W].  ``slot`` picks an independent buffer set so that several sequences can run
+        concurrently on different CUDA streams."""
         from .croper import Croper
         H, W = sensor_size
         crop = Croper(self.generator.num_encoders if num_encoders is None else num_encoders)
         crop.update_params(W, H)
         eng = self.generator.engine()
-        frames = eng.forward_events(xs, ys, ts, ps, offsets, H, W, crop, use_graph=self.generator.use_cuda_graph)
+        frames = eng.forward_events(xs, ys, ts, ps, offsets, H, W, crop, use_graph=self.generator.use_cuda_graph,
+                                    slot=slot)
         return [crop.crop(f) for f in frames]
 
 

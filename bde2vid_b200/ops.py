@@ -110,6 +110,39 @@ def window_attention(q, kv, bias_t, n_win, n_q, n_kv, c, heads, out):
     return out
 
 
+def ln_gather_qkv(frames, q_slot, tok_map, n_win, n_tok, c, g_kv, b_kv, g_q, b_q, out_kv, out_q):
+    """Fused window gather + norm_kv (all frames) + norm_q (query slot)."""
+    lib = _lib.require_device()
+    D = len(frames)
+    arr = (C.c_void_p * D)(*[None if f is None else f.data_ptr() for f in frames])
+    check(lib.bde_ln_gather_qkv(arr, D, q_slot, ptr(tok_map), n_win, n_tok, c, ptr(g_kv), ptr(b_kv), ptr(g_q), ptr(b_q),
+                                ptr(out_kv), ptr(out_q), BDE_DTYPE[out_kv.dtype], stream_ptr()), "bde_ln_gather_qkv")
+
+
+def attention_mma_bias_stride(n_kv):
+    return _lib.load().bde_window_attention_mma_bias_stride(n_kv)
+
+
+def pad_bias_for_mma(bias_hmn, n_kv):
+    """[heads, n_q, n_kv] float32 -> [heads, 64, stride] with -1e30 on the key padding."""
+    stride = attention_mma_bias_stride(n_kv)
+    if stride == 0:
+        return None
+    heads, n_q, _ = bias_hmn.shape
+    out = torch.zeros(heads, 64, stride, dtype=torch.float32, device=bias_hmn.device)
+    out[:, :, n_kv:] = -1e30
+    out[:, :n_q, :n_kv] = bias_hmn
+    return out.contiguous()
+
+
+def window_attention_mma(q, kv, bias_padded, n_win, n_q, n_kv, c, heads, out):
+    lib = _lib.require_device()
+    assert q.dtype == torch.bfloat16
+    check(lib.bde_window_attention_mma(ptr(q), ptr(kv), ptr(bias_padded), n_win, n_q, n_kv, c, heads, ptr(out),
+                                       stream_ptr()), "bde_window_attention_mma")
+    return out
+
+
 def cast(src, dst):
     lib = _lib.require_device()
     check(lib.bde_cast(ptr(src), BDE_DTYPE[src.dtype], ptr(dst), BDE_DTYPE[dst.dtype], src.numel(), stream_ptr()),

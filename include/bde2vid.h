@@ -141,6 +141,13 @@ int bde_pred_sigmoid(const void* x, const void* head, const float* wt, const flo
 int bde_ln_gather(const float* const* frames_host, int D, const int* tok_map, int n_win, int n_tok,
                   int c, const float* gamma, const float* beta, void* out, int dtype, void* stream);
 
+/* Fused form used by the executor: one pass produces the kv tokens of all D frames (norm_kv) and the
+ * q tokens of frame `q_slot` (norm_q; same mean / rstd, different affine).  c in {64, 128, 256}.
+ *   out_kv : `dtype` [n_win, D, n_tok, c];  out_q : `dtype` [n_win, n_tok, c] */
+int bde_ln_gather_qkv(const float* const* frames_host, int D, int q_slot, const int* tok_map, int n_win,
+                      int n_tok, int c, const float* g_kv, const float* b_kv, const float* g_q,
+                      const float* b_q, void* out_kv, void* out_q, int dtype, void* stream);
+
 /* Row-wise LayerNorm of a float32 [rows, c] matrix -> `dtype` (norm2, DTransformer.py:281). */
 int bde_layernorm(const float* x, size_t rows, int c, const float* gamma, const float* beta,
                   void* out, int dtype, void* stream);
@@ -153,6 +160,16 @@ int bde_layernorm(const float* x, size_t rows, int c, const float* gamma, const 
  */
 int bde_window_attention(const void* q, const void* kv, const float* bias, int n_win, int n_q,
                          int n_kv, int c, int heads, void* out, int dtype, void* stream);
+
+/* Tensor-core form of the same op for bf16 (mma.sync m16n8k16, scores kept in registers).
+ *   bias_padded: float32 [heads, 64, stride] with stride = bde_window_attention_mma_bias_stride(n_kv),
+ *                bias_padded[h, m, n] = bias for n < n_kv, a large negative number (-1e30) for
+ *                n_kv <= n < stride (masks the key padding), anything finite for m >= n_q.
+ * Supports n_q <= 64, n_kv <= 152, head_dim in {4, 8, 16}, even head count;
+ * bde_window_attention_mma_bias_stride returns 0 for an unsupported n_kv. */
+int bde_window_attention_mma_bias_stride(int n_kv);
+int bde_window_attention_mma(const void* q, const void* kv, const float* bias_padded, int n_win, int n_q,
+                             int n_kv, int c, int heads, void* out, void* stream);
 
 /* float32 -> dtype copy/cast (and back); n elements */
 int bde_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);

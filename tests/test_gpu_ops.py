@@ -126,3 +126,56 @@ def test_window_attention(dtype, C, heads, D):
     ops.window_attention(q.to(DEV), kv.to(DEV), bias.permute(0, 2, 1).contiguous().to(DEV), nwin, nq, nkv, C, heads, out)
     torch.cuda.synchronize()
     assert (out.float().cpu() - ref).abs().max() <= (2e-5 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("C,heads,D", [(64, 16, 3), (256, 16, 3), (128, 16, 3), (64, 16, 2), (64, 16, 1)])
+def test_window_attention_mma(C, heads, D):
+    """Tensor-core attention core (bf16 mma.sync) vs fp32 softmax attention on the same bf16 inputs."""
+    from bde2vid_b200 import ops
+    g = torch.Generator().manual_seed(C + 7 * D)
+    nwin, nq = 37, 49
+    nkv = D * 49
+    hd = C // heads
+    q = (torch.randn(nwin, nq, C, generator=g) * hd ** -0.5).to(torch.bfloat16)
+    kv = torch.randn(nwin, nkv, 2 * C, generator=g).to(torch.bfloat16)
+    bias = torch.randn(heads, nq, nkv, generator=g)
+    qh = q.float().view(nwin, nq, heads, hd).permute(0, 2, 1, 3)
+    kh = kv.float()[..., :C].reshape(nwin, nkv, heads, hd).permute(0, 2, 1, 3)
+    vh = kv.float()[..., C:].reshape(nwin, nkv, heads, hd).permute(0, 2, 1, 3)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) + bias, -1) @ vh).permute(0, 2, 1, 3).reshape(nwin, nq, C)
+    out = torch.full((nwin, nq, C), 7.0, dtype=torch.bfloat16, device=DEV)
+    bp = ops.pad_bias_for_mma(bias.to(DEV), nkv)
+    assert bp is not None and bp.shape[1] == 64
+    ops.window_attention_mma(q.to(DEV), kv.to(DEV), bp, nwin, nq, nkv, C, heads, out)
+    torch.cuda.synchronize()
+    err = (out.float().cpu() - ref).abs().max()
+    print("attention mma", C, heads, D, float(err))
+    assert err <= 3e-2
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C", [64, 128, 256])
+def test_ln_gather_qkv(dtype, C):
+    from bde2vid_b200 import ops
+    from bde2vid_b200.engine import window_token_map
+    g = torch.Generator().manual_seed(C)
+    B, H, W, D, qs = 2, 9, 13, 3, 1
+    frames = [torch.randn(B * H * W, C, generator=g) for _ in range(D)]
+    frames[0] = None
+    gk, bk, gq, bq = (torch.randn(C, generator=g) for _ in range(4))
+    for dil in (False, True):
+        tm, _ = window_token_map(B, H, W, (7, 7), dil, DEV)
+        nwin = tm.shape[0]
+        okv = torch.zeros(nwin, D, 49, C, dtype=dtype, device=DEV)
+        oq = torch.zeros(nwin, 49, C, dtype=dtype, device=DEV)
+        ops.ln_gather_qkv([None if f is None else f.to(DEV) for f in frames], qs, tm, nwin, 49, C, gk.to(DEV), bk.to(DEV),
+                          gq.to(DEV), bq.to(DEV), okv, oq)
+        torch.cuda.synchronize()
+        tmc = tm.cpu().long()
+        tol = 2e-5 if dtype == torch.float32 else 5e-2
+        for d in range(D):
+            src = torch.zeros(B * H * W, C) if frames[d] is None else frames[d]
+            tok = src[tmc.clamp(min=0).reshape(-1)].reshape(nwin, 49, C) * (tmc >= 0).unsqueeze(-1)
+            assert (okv[:, d].float().cpu() - F.layer_norm(tok, (C,), gk, bk, 1e-5)).abs().max() <= tol
+            if d == qs:
+                assert (oq.float().cpu() - F.layer_norm(tok, (C,), gq, bq, 1e-5)).abs().max() <= tol
