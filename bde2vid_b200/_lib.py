@@ -29,7 +29,7 @@ class GemmDesc(C.Structure):
         ("n_img", C.c_int), ("h_in", C.c_int), ("w_in", C.c_int), ("h_out", C.c_int), ("w_out", C.c_int),
         ("ksize", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
         ("w", C.c_void_p), ("bias", C.c_void_p),
-        ("n", C.c_int), ("w_ld", C.c_int),
+        ("n", C.c_int), ("w_ld", C.c_int), ("k_order", C.c_int),
         ("epi", C.c_int), ("act", C.c_int), ("out_f32", C.c_int),
         ("out", C.c_void_p), ("residual", C.c_void_p), ("c_prev", C.c_void_p), ("c_out", C.c_void_p),
         ("row_map", C.c_void_p), ("out2", C.c_void_p),

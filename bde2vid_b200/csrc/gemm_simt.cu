@@ -18,7 +18,7 @@ struct GemmParams {
   const float* bias;
   int c0, c1, ctot;
   int n_img, h_in, w_in, h_out, w_out, ksize, stride, pad;
-  int M, N, K, w_ld;
+  int M, N, K, w_ld, k_order;
   int epi, act, out_f32;
   void* out;
   void* out2;
@@ -67,7 +67,16 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmParams p) {
     if (k < p.K) {
       if (b_row_ok) bv = load4<T>(wrow + k);
       if (a_row_ok) {
-        int tap = k / p.ctot, c = k % p.ctot;
+        int tap, c;
+        if (p.k_order == 1) {  // k = (64-channel chunk, tap, channel in chunk)
+          const int per_chunk = p.ksize * p.ksize * 64;
+          const int chunk = k / per_chunk, rem = k - chunk * per_chunk;
+          tap = rem >> 6;
+          c = chunk * 64 + (rem & 63);
+        } else {
+          tap = k / p.ctot;
+          c = k % p.ctot;
+        }
         int ky = tap / p.ksize, kx = tap % p.ksize;
         int iy = oy * p.stride + ky - p.pad, ix = ox * p.stride + kx - p.pad;
         if (iy >= 0 && iy < p.h_in && ix >= 0 && ix < p.w_in) {
@@ -178,6 +187,8 @@ int gemm_simt(const bde_gemm_desc* d, cudaStream_t s) {
   p.K = d->ksize * d->ksize * p.ctot;
   p.w_ld = d->w_ld > 0 ? d->w_ld : p.K;
   BDE_REQUIRE(p.w_ld >= p.K && p.w_ld % 4 == 0, "bde_gemm(simt): bad w_ld");
+  p.k_order = d->k_order;
+  BDE_REQUIRE(p.k_order == 0 || (p.c0 % 64 == 0 && p.c1 % 64 == 0), "bde_gemm(simt): chunk-major K needs channels %% 64 == 0");
   p.epi = d->epi; p.act = d->act; p.out_f32 = d->out_f32;
   p.out = d->out; p.out2 = d->out2; p.residual = d->residual; p.c_prev = d->c_prev; p.c_out = d->c_out;
   p.row_map = d->row_map;

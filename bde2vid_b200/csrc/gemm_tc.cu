@@ -45,8 +45,12 @@ struct TcParams {
   const __nv_bfloat16* w;  // only used when !kBTma
   const float* bias;
   int c0, c1, ctot;
-  int h_in, w_in, h_out, w_out, ksize, stride, pad;
+  int n_img, h_in, w_in, h_out, w_out, ksize, stride, pad;
   int M, N, K, w_ld, num_kb;
+  int tiles_x, tiles_y;  // > 0: M tiles are 8 x 16 output-pixel patches (L1-friendly halo reuse); 0: 128 consecutive pixels
+  uint32_t ypat_all;     // bit (ky * ksize) set for every ky: multiplying by an x-bit mask replicates it per row
+  int dense;             // 1x1, stride 1, pad 0: A is a plain [M, K] matrix
+  int k_order;           // 0: k = (tap, channel);  1: k = (64-channel chunk, tap, channel in chunk)
   int epi, act, out_f32;
   void* out;
   void* out2;
@@ -54,7 +58,13 @@ struct TcParams {
   const float* c_prev;
   float* c_out;
   const int* row_map;
+  long long* dbg;  // optional per-CTA phase timestamps (clock64), 8 slots per CTA, for bring-up profiling
 };
+
+#define BDE_DBG(slot)                                                                     \
+  do {                                                                                    \
+    if (p.dbg != nullptr) p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = clock64(); \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -156,14 +166,65 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-template <int BN>
+constexpr int kTileH = 8, kTileW = 16;  // 2-D M tile (kTileH * kTileW == BM)
+
+// M-tile geometry.  The CTA-uniform part (integer divisions) is computed once; mapping a tile row to
+// its output pixel is then a handful of adds.  Three modes:
+//   2-D    : the tile is an 8 x 16 patch of output pixels of one image (convolutions)
+//   dense  : 1x1 / stride 1 / no padding: the "pixel" index is the row index itself (linear layers)
+//   linear : 128 consecutive output pixels in raster order (small images)
+struct TileGeom {
+  int img, oy0, ox0;  // 2-D mode
+  int m0;             // dense / linear mode
+  __device__ __forceinline__ void init(const TcParams& p, int tile) {
+    img = oy0 = ox0 = 0;
+    m0 = tile * BM;
+    if (p.tiles_x > 0) {
+      const int per_img = p.tiles_x * p.tiles_y;
+      img = tile / per_img;
+      const int t = tile - img * per_img;
+      const int ty = t / p.tiles_x;
+      oy0 = ty * kTileH;
+      ox0 = (t - ty * p.tiles_x) * kTileW;
+    }
+  }
+  // returns false for rows outside the problem; m = linear output index (epilogue addressing)
+  __device__ __forceinline__ bool row_pixel(const TcParams& p, int row, int& im, int& oy, int& ox, int& m) const {
+    if (p.tiles_x > 0) {
+      im = img;
+      oy = oy0 + (row >> 4);
+      ox = ox0 + (row & 15);
+      m = (im * p.h_out + oy) * p.w_out + ox;
+      return oy < p.h_out && ox < p.w_out;
+    }
+    m = m0 + row;
+    if (m >= p.M) return false;
+    if (p.dense) {  // no spatial structure needed
+      im = 0; oy = m; ox = 0;
+      return true;
+    }
+    const int hw = p.h_out * p.w_out;
+    im = m / hw;
+    const int rem = m - im * hw;
+    oy = rem / p.w_out;
+    ox = rem - oy * p.w_out;
+    return true;
+  }
+};
+
+// kDeep = false: few stages so that two CTAs share an SM (mainloop of one overlaps the epilogue of the
+//                other) -- used for linear layers, whose A operand has no reuse.
+// kDeep = true : one CTA per SM with a deep pipeline; the smaller shared-memory carve-out leaves
+//                >= 64 KB of L1 so that the im2col re-reads of a 2-D pixel tile (each input pixel is
+//                needed by up to k*k taps) are served by L1 instead of L2.
+template <int BN, bool kDeep>
 struct TileCfg {
-  // 3 stages of 32 KB keep two CTAs resident per SM (mainloop of one overlaps the epilogue of the other)
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 3 : 4);
+  static constexpr int kStages = kDeep ? (BN >= 256 ? 4 : (BN >= 128 ? 5 : (BN >= 64 ? 6 : 8)))
+                                       : (BN >= 256 ? 4 : (BN >= 128 ? 3 : 4));
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
 
@@ -185,80 +246,51 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// epilogue for one row (m) and 32 consecutive columns [nb, nb+32)
+// Epilogue on 4 consecutive columns [nb, nb+4) of output row m (after the shared-memory transpose every
+// lane owns such a quad, 8 lanes cover 32 contiguous columns of one row -> coalesced global traffic).
+// For the LSTM epilogue the quad is exactly (in, remember, out, cell) of hidden channel nb / 4.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_row32(const TcParams& p, int m, int nb, const uint32_t (&raw)[32]) {
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-  if (p.bias != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-    }
-  }
+__device__ __forceinline__ void epilogue_quad(const TcParams& p, int m, int nb, float4 acc, const float* bias_s4,
+                                              int dst_row) {
+  const float4 b = *reinterpret_cast<const float4*>(bias_s4);
+  float v0 = acc.x + b.x, v1 = acc.y + b.y, v2 = acc.z + b.z, v3 = acc.w + b.w;
   if (p.epi == BDE_EPI_STORE) {
     if (p.act == BDE_ACT_RELU) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+      v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
     } else if (p.act == BDE_ACT_RELU6) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], 0.0f), 6.0f);
+      v0 = fminf(fmaxf(v0, 0.f), 6.f); v1 = fminf(fmaxf(v1, 0.f), 6.f);
+      v2 = fminf(fmaxf(v2, 0.f), 6.f); v3 = fminf(fmaxf(v3, 0.f), 6.f);
     } else if (p.act != BDE_ACT_NONE) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+      v0 = apply_act(v0, p.act); v1 = apply_act(v1, p.act); v2 = apply_act(v2, p.act); v3 = apply_act(v3, p.act);
     }
     const size_t o = (size_t)m * p.N + nb;
     if (p.residual != nullptr) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 r = *reinterpret_cast<const float4*>(p.residual + o + j);
-        v[j] += r.x; v[j + 1] += r.y; v[j + 2] += r.z; v[j + 3] += r.w;
-      }
+      const float4 r = *reinterpret_cast<const float4*>(p.residual + o);
+      v0 += r.x; v1 += r.y; v2 += r.z; v3 += r.w;
     }
-    if (p.out_f32) {
-      float* dst = reinterpret_cast<float*>(p.out) + o;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    }
+    if (p.out_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) = make_float4(v0, v1, v2, v3);
     __nv_bfloat16* dstb = p.out_f32 ? reinterpret_cast<__nv_bfloat16*>(p.out2) : reinterpret_cast<__nv_bfloat16*>(p.out);
     if (dstb != nullptr) {
-      dstb += o;
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) *reinterpret_cast<uint4*>(dstb + j) = pack8_bf16(v + j);
+      const __nv_bfloat162 t0 = __floats2bfloat162_rn(v0, v1), t1 = __floats2bfloat162_rn(v2, v3);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&t0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&t1);
+      *reinterpret_cast<uint2*>(dstb + o) = pk;
     }
   } else if (p.epi == BDE_EPI_LSTM) {
-    // columns = 8 hidden channels x (in, remember, out, cell)   (submodules.py:320-332)
-    const int hid = p.N >> 2, ch = nb >> 2;
-    const size_t o = (size_t)m * hid + ch;
-    float cp[8];
-    if (p.c_prev != nullptr) {
-      float4 a = *reinterpret_cast<const float4*>(p.c_prev + o), b = *reinterpret_cast<const float4*>(p.c_prev + o + 4);
-      cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w; cp[4] = b.x; cp[5] = b.y; cp[6] = b.z; cp[7] = b.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) cp[j] = 0.f;
-    }
-    float h[8], c[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      c[j] = fast_sigmoid(v[4 * j + 1]) * cp[j] + fast_sigmoid(v[4 * j]) * fast_tanh(v[4 * j + 3]);
-      h[j] = fast_sigmoid(v[4 * j + 2]) * fast_tanh(c[j]);
-    }
-    *reinterpret_cast<float4*>(p.c_out + o) = make_float4(c[0], c[1], c[2], c[3]);
-    *reinterpret_cast<float4*>(p.c_out + o + 4) = make_float4(c[4], c[5], c[6], c[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pack8_bf16(h);
+    // (submodules.py:320-332)  c = sig(remember) * c_prev + sig(in) * tanh(cell);  h = sig(out) * tanh(c)
+    const size_t o = (size_t)m * (p.N >> 2) + (nb >> 2);
+    const float cprev = p.c_prev != nullptr ? p.c_prev[o] : 0.f;
+    const float c = fast_sigmoid(v1) * cprev + fast_sigmoid(v0) * fast_tanh(v3);
+    const float h = fast_sigmoid(v2) * fast_tanh(c);
+    p.c_out[o] = c;
+    reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(h);
   } else {  // BDE_EPI_SCATTER
-    const int dst_row = p.row_map[m];
     if (dst_row >= 0) {
-      float* dst = reinterpret_cast<float*>(p.out) + (size_t)dst_row * p.N + nb;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 cur = *reinterpret_cast<float4*>(dst + j);
-        cur.x += v[j]; cur.y += v[j + 1]; cur.z += v[j + 2]; cur.w += v[j + 3];
-        *reinterpret_cast<float4*>(dst + j) = cur;
-      }
+      float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)dst_row * p.N + nb);
+      float4 cur = *dst;
+      cur.x += v0; cur.y += v1; cur.z += v2; cur.w += v3;
+      *dst = cur;
     }
   }
 }
@@ -266,9 +298,9 @@ __device__ __forceinline__ void epilogue_row32(const TcParams& p, int m, int nb,
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <int BN, bool kBTma>
+template <int BN, bool kBTma, bool kDeep>
 __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, kDeep>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B tiles
@@ -281,11 +313,15 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   const uint32_t bar_acc = bar_base + 16 * S;              // 8B
   const uint32_t tmem_slot = bar_base + 16 * S + 8;        // 4B
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to smem_base
+  float* bias_s = reinterpret_cast<float*>(smem_gen + S * Cfg::kStageBytes + 256);  // BN floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int m_tile = blockIdx.x, n0 = blockIdx.y * BN;
   const int num_kb = p.num_kb;
 
+  if (threadIdx.x == 0) BDE_DBG(0);
+  // bias slice -> smem once (the epilogue then never waits on global memory for it)
+  if ((int)threadIdx.x < BN) bias_s[threadIdx.x] = p.bias != nullptr ? __ldg(p.bias + blockIdx.y * BN + threadIdx.x) : 0.0f;
   if (threadIdx.x == 0) {
     const uint32_t full_count = kNumProducerThreads + (kBTma ? 1 : 32);
     for (int s = 0; s < S; ++s) {
@@ -303,6 +339,9 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  if (threadIdx.x == 0) BDE_DBG(1);
+  TileGeom geom;
+  geom.init(p, m_tile);
 
   if (warp < kNumProducerWarps) {
     // =============================== A producers ========================================
@@ -314,36 +353,43 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
     uint32_t vmask[kRowsPerThread];  // bit t set <=> tap t of this output pixel is inside the image
     uint32_t dsto[kRowsPerThread];   // swizzled byte offset of this lane's chunk inside a stage
     {
-      const int hw = p.h_out * p.w_out;
 #pragma unroll
       for (int i = 0; i < kRowsPerThread; ++i) {
         const int row = warp * (4 * kRowsPerThread) + i * 4 + rsub;
         dsto[i] = (uint32_t)row * 128u + (((uint32_t)j ^ (uint32_t)(row & 7)) << 4);
-        const int mm = m0 + row;
         pix0[i] = 0;
         vmask[i] = 0u;
-        if (mm < p.M) {
-          const int img = mm / hw;
-          const int rem = mm - img * hw;
-          const int oy = rem / p.w_out;
-          const int ox = rem - oy * p.w_out;
+        int img, oy, ox, mm;
+        if (!geom.row_pixel(p, row, img, oy, ox, mm)) continue;
+        if (p.dense) {
+          pix0[i] = mm;
+          vmask[i] = 1u;
+        } else {
           const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
           pix0[i] = (img * p.h_in + iy0) * p.w_in + ix0;
-          // valid taps form a rectangle [ky_lo, ky_hi) x [kx_lo, kx_hi)
+          // valid taps form a rectangle [ky_lo, ky_hi) x [kx_lo, kx_hi): x bits times the pattern of valid rows
           const int kx_lo = max(0, -ix0), kx_hi = min(p.ksize, p.w_in - ix0);
           const int ky_lo = max(0, -iy0), ky_hi = min(p.ksize, p.h_in - iy0);
           uint32_t msk = 0u;
-          if (kx_hi > kx_lo) {
+          if (kx_hi > kx_lo && ky_hi > ky_lo) {
             const uint32_t xm = ((1u << (kx_hi - kx_lo)) - 1u) << kx_lo;
-            for (int ky = ky_lo; ky < ky_hi; ++ky) msk |= xm << (ky * p.ksize);
+            const uint32_t rows = ((1u << (ky_hi * p.ksize)) - 1u) & ~((1u << (ky_lo * p.ksize)) - 1u);
+            msk = xm * (p.ypat_all & rows);
           }
           vmask[i] = msk;
         }
       }
     }
+    if (threadIdx.x == 0) BDE_DBG(2);
     // running (tap, channel) position of this lane's chunk: k = kb*64 + j*8
-    int tap = (j * 8) / p.ctot;
-    int c = (j * 8) - tap * p.ctot;
+    int tap, c;
+    if (p.k_order == 1) {  // chunk-major: every lane is on the same tap; channel = chunk*64 + j*8
+      tap = 0;
+      c = j * 8;
+    } else {
+      tap = (j * 8) / p.ctot;
+      c = (j * 8) - tap * p.ctot;
+    }
     int ky = tap / p.ksize, kx = tap - ky * p.ksize;
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % S;
@@ -352,7 +398,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
       const __nv_bfloat16* sbase = from0 ? p.a0 + c : p.a1 + (c - p.c0);
       const int cs = from0 ? p.c0 : p.c1;
       const int tapoff = ky * p.w_in + kx;
-      const uint32_t tapbit = tap < ntaps ? (1u << tap) : 0u;  // K tail -> zero fill
+      const uint32_t tapbit = (tap < ntaps && c < p.ctot) ? (1u << tap) : 0u;  // K tail -> zero fill
       mbar_wait(bar_empty + 8 * s, ph ^ 1u);
       const uint32_t stage_a = smem_a + s * Cfg::kABytes;
 #pragma unroll
@@ -365,13 +411,25 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
       // thread runs ahead by up to S stages without ever blocking on its own loads
       cp_async_mbar_arrive_noinc(bar_full + 8 * s);
       // advance to the next K block
-      c += BK;
-      while (c >= p.ctot) {
-        c -= p.ctot;
+      if (p.k_order == 1) {
         ++tap;
         if (++kx == p.ksize) {
           kx = 0;
-          ++ky;
+          if (++ky == p.ksize) {  // all taps of this 64-channel chunk done -> next chunk
+            ky = 0;
+            tap = 0;
+            c += BK;
+          }
+        }
+      } else {
+        c += BK;
+        while (c >= p.ctot) {
+          c -= p.ctot;
+          ++tap;
+          if (++kx == p.ksize) {
+            kx = 0;
+            ++ky;
+          }
         }
       }
     }
@@ -380,19 +438,48 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
     // thread <-> tile row (TMEM lane) 32*(warp & 3) + lane; the two warps sharing a lane quarter
     // split the columns in alternating 32-wide chunks
     const int q = warp & 3, half = warp >> 2;
-    const int m = m0 + q * 32 + lane;
-    const bool row_ok = m < p.M;
+    if (threadIdx.x == 0) BDE_DBG(3);
+    // TMEM hands every thread one accumulator ROW (32 columns per load).  Writing rows straight to
+    // global memory would make every warp-wide store touch 32 different lines, so each warp first
+    // transposes its 32 x 32 chunk through shared memory (the pipeline stages are free once the
+    // accumulator is complete) and then works on quads: lane -> (row 4*it + lane/8, columns 4*(lane%8)..+3),
+    // i.e. 8 lanes cover 128 contiguous bytes of one output row.
+    constexpr int kPitch = 36;  // floats; 16-byte aligned rows, conflict-free for both access patterns
+    float* stg = reinterpret_cast<float*>(smem_gen) + warp * (32 * kPitch);
+    const int rq = lane >> 3, cq = (lane & 7) * 4;
+    int m_it[8];            // output row index of (4*it + rq), -1 if outside the problem
+    int dst_it[8];          // SCATTER destination
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      int im, oy, ox, mm;
+      const bool ok = geom.row_pixel(p, q * 32 + it * 4 + rq, im, oy, ox, mm);
+      m_it[it] = ok ? mm : -1;
+      dst_it[it] = (ok && p.epi == BDE_EPI_SCATTER) ? __ldg(p.row_map + mm) : -1;
+    }
     mbar_wait(bar_acc, 0);
     tcgen05_fence_after();
+    if (threadIdx.x == 0) BDE_DBG(5);
     const uint32_t lane_taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
     for (int cb = half * 32; cb < BN; cb += 64) {
       uint32_t raw[32];
       tmem_ld_32x32b_x32(lane_taddr + (uint32_t)cb, raw);
       tmem_ld_wait();
-      if (row_ok) epilogue_row32(p, m, n0 + cb, raw);
+      __syncwarp();  // previous chunk fully read back before it is overwritten
+#pragma unroll
+      for (int jq = 0; jq < 32; jq += 4)
+        *reinterpret_cast<float4*>(stg + lane * kPitch + jq) =
+            make_float4(__uint_as_float(raw[jq]), __uint_as_float(raw[jq + 1]), __uint_as_float(raw[jq + 2]),
+                        __uint_as_float(raw[jq + 3]));
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const float4 acc = *reinterpret_cast<const float4*>(stg + (it * 4 + rq) * kPitch + cq);
+        if (m_it[it] >= 0) epilogue_quad(p, m_it[it], n0 + cb + cq, acc, bias_s + cb + cq, dst_it[it]);
+      }
     }
     tcgen05_fence_before();
+    if (threadIdx.x == 0) BDE_DBG(6);
   } else if (warp == kTmaWarp) {
     // =============================== B producer =========================================
     if (kBTma) {
@@ -426,6 +513,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
         const int s = kb % S;
         const uint32_t ph = (uint32_t)(kb / S) & 1u;
         mbar_wait(bar_full + 8 * s, ph);
+        if (kb == 0) BDE_DBG(4);
         // operands were written through the generic proxy (cp.async): order them before the
         // tensor core's async-proxy reads
         fence_proxy_async_smem();
@@ -448,6 +536,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   if (warp == kMmaWarp) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_acc, Cfg::kTmemCols);
+    if (lane == 0) BDE_DBG(7);
   }
 }
 
@@ -495,22 +584,34 @@ int get_weight_tmap(const void* w, int n, int w_ld, int bn, CUtensorMap* out) {
   return 0;
 }
 
-template <int BN, bool kBTma>
+template <int BN, bool kBTma, bool kDeep>
 int launch(const CUtensorMap& tmap, const TcParams& p, cudaStream_t s) {
-  using Cfg = TileCfg<BN>;
-  auto kern = gemm_tc_kernel<BN, kBTma>;
+  using Cfg = TileCfg<BN, kDeep>;
+  auto kern = gemm_tc_kernel<BN, kBTma, kDeep>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     BDE_REQUIRE(e == cudaSuccess, "bde_gemm(tcgen05): smem attribute: %s", cudaGetErrorString(e));
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(p.M, BM), (unsigned)(p.N / BN));
+  const size_t m_tiles = p.tiles_x > 0 ? (size_t)p.n_img * p.tiles_x * p.tiles_y : ceil_div(p.M, BM);
+  dim3 grid((unsigned)m_tiles, (unsigned)(p.N / BN));
   kern<<<grid, kThreads, Cfg::kSmemBytes, s>>>(tmap, p);
   return check_launch("gemm_tc_kernel");
 }
 
 }  // namespace
+
+// bring-up profiling: bde_tc_debug_enable(n) allocates 8 timestamps per CTA for the next launches
+static long long* g_dbg = nullptr;
+static size_t g_dbg_ctas = 0;
+
+// tuning switches (read per call; used by tools/tc_phase_probe.py to compare configurations)
+static bool env_flag(const char* name, bool dflt) {
+  const char* e = getenv(name);
+  if (e == nullptr || e[0] == 0) return dflt;
+  return e[0] == '1';
+}
 
 // BDE2VID_TC_B_CPASYNC=1 loads the weight tile with cp.async instead of TMA (bring-up / bisecting)
 static bool b_via_tma() {
@@ -526,6 +627,7 @@ int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s) {
   p.w = (const __nv_bfloat16*)d->w;
   p.bias = d->bias;
   p.c0 = d->c0; p.c1 = d->c1; p.ctot = d->c0 + d->c1;
+  p.n_img = d->n_img;
   p.h_in = d->h_in; p.w_in = d->w_in; p.h_out = d->h_out; p.w_out = d->w_out;
   p.ksize = d->ksize; p.stride = d->stride; p.pad = d->pad;
   p.M = d->n_img * d->h_out * d->w_out;
@@ -536,6 +638,7 @@ int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s) {
   p.epi = d->epi; p.act = d->act; p.out_f32 = d->out_f32;
   p.out = d->out; p.out2 = d->out2; p.residual = d->residual; p.c_prev = d->c_prev; p.c_out = d->c_out;
   p.row_map = d->row_map;
+  p.dbg = nullptr;
   BDE_REQUIRE(p.c0 % 8 == 0 && p.c1 % 8 == 0, "bde_gemm(tcgen05): channel counts must be multiples of 8");
   BDE_REQUIRE(p.ksize * p.ksize <= 32, "bde_gemm(tcgen05): kernel size up to 5x5");
   BDE_REQUIRE(p.w_ld % BK == 0 && p.w_ld >= p.num_kb * BK, "bde_gemm(tcgen05): w_ld must be a zero-padded multiple of 64");
@@ -544,12 +647,28 @@ int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s) {
   BDE_REQUIRE((((uintptr_t)d->a0) & 15) == 0 && (((uintptr_t)d->a1) & 15) == 0 && (((uintptr_t)d->w) & 127) == 0,
               "bde_gemm(tcgen05): operands must be 16-byte (weights 128-byte) aligned");
   if (p.M == 0) return 0;
+  p.k_order = d->k_order;
+  p.dense = (p.ksize == 1 && p.stride == 1 && p.pad == 0) ? 1 : 0;
+  p.ypat_all = 0u;
+  for (int ky = 0; ky < p.ksize; ++ky) p.ypat_all |= 1u << (ky * p.ksize);
+  BDE_REQUIRE(p.k_order == 0 || (p.k_order == 1 && p.c0 % BK == 0 && p.c1 % BK == 0),
+              "bde_gemm(tcgen05): chunk-major K order needs channel counts that are multiples of 64");
+  // convolutions with a real footprint use 2-D pixel tiles + the deep one-CTA-per-SM configuration
+  const bool conv = p.ksize > 1 && p.h_out >= kTileH && p.w_out >= kTileW;
+  const bool tile2d = conv && env_flag("BDE2VID_TC_TILE2D", true);
+  const bool deep = conv && env_flag("BDE2VID_TC_DEEP", false);
+  p.tiles_x = tile2d ? (int)ceil_div(p.w_out, kTileW) : 0;
+  p.tiles_y = tile2d ? (int)ceil_div(p.h_out, kTileH) : 0;
   // tile width: widest tile that still gives every SM work
   int bn = 32;
   if (p.N % 128 == 0) bn = 128;
   else if (p.N % 64 == 0) bn = 64;
   const size_t m_tiles = ceil_div(p.M, BM);
   if (p.N % 256 == 0 && m_tiles * (p.N / 256) >= 2 * (size_t)kNumSMs) bn = 256;
+  if (g_dbg != nullptr) {
+    const size_t mt = p.tiles_x > 0 ? (size_t)p.n_img * p.tiles_x * p.tiles_y : ceil_div(p.M, BM);
+    if (mt * (p.N / bn) <= g_dbg_ctas) p.dbg = g_dbg;
+  }
   const bool tma = b_via_tma();
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
@@ -557,9 +676,10 @@ int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s) {
     int rc = get_weight_tmap(d->w, p.N, p.w_ld, bn, &tmap);
     if (rc != 0) return rc;
   }
-#define BDE_TC_LAUNCH(BN_)                                                   \
-  case BN_:                                                                  \
-    return tma ? launch<BN_, true>(tmap, p, s) : launch<BN_, false>(tmap, p, s);
+#define BDE_TC_LAUNCH(BN_)                                                                                   \
+  case BN_:                                                                                                  \
+    if (deep) return tma ? launch<BN_, true, true>(tmap, p, s) : launch<BN_, false, true>(tmap, p, s);       \
+    return tma ? launch<BN_, true, false>(tmap, p, s) : launch<BN_, false, false>(tmap, p, s);
   switch (bn) {
     BDE_TC_LAUNCH(32)
     BDE_TC_LAUNCH(64)
@@ -571,3 +691,19 @@ int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s) {
 }
 
 }  // namespace bde
+
+extern "C" int bde_tc_debug_enable(size_t max_ctas) {
+  if (bde::g_dbg != nullptr) cudaFree(bde::g_dbg);
+  bde::g_dbg = nullptr;
+  bde::g_dbg_ctas = 0;
+  if (max_ctas == 0) return 0;
+  if (cudaMalloc(&bde::g_dbg, max_ctas * 8 * sizeof(long long)) != cudaSuccess) return -1;
+  cudaMemset(bde::g_dbg, 0, max_ctas * 8 * sizeof(long long));
+  bde::g_dbg_ctas = max_ctas;
+  return 0;
+}
+
+extern "C" int bde_tc_debug_read(long long* host_out, size_t n_ctas) {
+  if (bde::g_dbg == nullptr || n_ctas > bde::g_dbg_ctas) return -1;
+  return cudaMemcpy(host_out, bde::g_dbg, n_ctas * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}

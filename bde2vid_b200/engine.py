@@ -53,12 +53,17 @@ def window_token_map(B, H, W, ws, dilated, device):
     return full.reshape(B * nH * nW, wh * ww).to(torch.int32).contiguous().to(device), g
 
 
-def _pack_conv(w, dtype, cin_pad=None):
-    """[Cout, Cin, kh, kw] -> K-major [Cout, Kpad], k = (ky*kw + kx)*Cin + c, zero padded to K_ALIGN."""
+def _pack_conv(w, dtype, cin_pad=None, chunk_major=False):
+    """[Cout, Cin, kh, kw] -> K-major [Cout, Kpad], zero padded to K_ALIGN.
+    k = (ky*kw + kx)*Cin + c by default; with ``chunk_major`` (Cin % 64 == 0, ``k_order=1`` of bde_gemm)
+    k = (c // 64)*(kh*kw*64) + (ky*kw + kx)*64 + c % 64."""
     co, ci, kh, kw = w.shape
     w = w.permute(0, 2, 3, 1)
     if cin_pad is not None and cin_pad > ci:
         w = torch.nn.functional.pad(w, (0, cin_pad - ci))
+    if chunk_major:
+        assert w.shape[-1] % 64 == 0
+        w = w.reshape(co, kh * kw, w.shape[-1] // 64, 64).permute(0, 2, 1, 3)
     w = w.reshape(co, -1)
     K = w.shape[1]
     Kp = (K + K_ALIGN - 1) // K_ALIGN * K_ALIGN
@@ -78,9 +83,9 @@ def _pack_linear(w, dtype, scale=1.0):
 class _Layer:
     """Packed weights of one conv / linear."""
 
-    def __init__(self, w, w_ld, bias, n, ksize=1, stride=1, pad=0):
+    def __init__(self, w, w_ld, bias, n, ksize=1, stride=1, pad=0, k_order=0):
         self.w, self.w_ld, self.bias, self.n = w, w_ld, bias, n
-        self.ksize, self.stride, self.pad = ksize, stride, pad
+        self.ksize, self.stride, self.pad, self.k_order = ksize, stride, pad, k_order
 
 
 class Engine:
@@ -113,10 +118,13 @@ class Engine:
         dt = self.dtype
         f32 = lambda t: t.detach().to(torch.float32).contiguous()  # noqa: E731
 
+        tc = self.gemm_engine == ENGINE_TCGEN05
+
         def conv_layer(conv, stride, cin_pad=None):
-            w, ld = _pack_conv(conv.weight.detach().float(), dt, cin_pad)
             k = conv.weight.shape[-1]
-            return _Layer(w, ld, f32(conv.bias), conv.weight.shape[0], k, stride, k // 2)
+            cm = tc and k > 1 and conv.weight.shape[1] % 64 == 0      # chunk-major K: L1-friendly im2col order
+            w, ld = _pack_conv(conv.weight.detach().float(), dt, cin_pad, chunk_major=cm)
+            return _Layer(w, ld, f32(conv.bias), conv.weight.shape[0], k, stride, k // 2, k_order=int(cm))
 
         def lstm_layer(conv):
             # rows reordered so that n = 4*c + gate (gate order in, remember, out, cell: submodules.py:320)
@@ -124,8 +132,9 @@ class Engine:
             hid = w.shape[0] // 4
             w = w.view(4, hid, *w.shape[1:]).permute(1, 0, 2, 3, 4).reshape(4 * hid, *w.shape[1:])
             b = conv.bias.detach().float().view(4, hid).t().reshape(-1)
-            pw, ld = _pack_conv(w, dt)
-            return _Layer(pw, ld, b.contiguous(), 4 * hid, 3, 1, 1)
+            cm = tc and hid % 64 == 0
+            pw, ld = _pack_conv(w, dt, chunk_major=cm)
+            return _Layer(pw, ld, b.contiguous(), 4 * hid, 3, 1, 1, k_order=int(cm))
 
         def lin_layer(lin, scale=1.0):
             w, ld = _pack_linear(lin.weight.detach().float(), dt, scale)
@@ -174,7 +183,7 @@ class Engine:
     def _gemm(self, layer, a0, out, n_img, h, w, c0, **kw):
         return ops.gemm(a0, layer.w, layer.bias, out, n_img=n_img, h_in=h, w_in=w, c0=c0, n=layer.n,
                         ksize=layer.ksize, stride=layer.stride, pad=layer.pad, w_ld=layer.w_ld,
-                        engine=self.gemm_engine, dtype=self.dtype, **kw)
+                        k_order=layer.k_order, engine=self.gemm_engine, dtype=self.dtype, **kw)
 
     def plan(self, T, B, Hp, Wp, slot=0):
         """``slot`` selects an independent set of buffers + graph, so that several sequences can be

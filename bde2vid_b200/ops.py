@@ -43,7 +43,7 @@ def pack_voxel_nhwc(vox, c_pad, dtype, out=None):
 
 def gemm(a0, w, bias, out, *, n_img, h_in, w_in, c0, n, ksize=1, stride=1, pad=0, a1=None, c1=0, w_ld=0,
          epi=EPI_STORE, act=ACT_NONE, out_f32=False, residual=None, c_prev=None, c_out=None, row_map=None,
-         out2=None, engine=ENGINE_SIMT, dtype=None):
+         out2=None, engine=ENGINE_SIMT, dtype=None, k_order=0):
     """Implicit-GEMM conv / linear (see bde_gemm in include/bde2vid.h).  Returns (h_out, w_out)."""
     lib = _lib.require_device()
     d = _lib.GemmDesc()
@@ -55,7 +55,7 @@ def gemm(a0, w, bias, out, *, n_img, h_in, w_in, c0, n, ksize=1, stride=1, pad=0
     d.h_out = (h_in + 2 * pad - ksize) // stride + 1
     d.w_out = (w_in + 2 * pad - ksize) // stride + 1
     d.ksize, d.stride, d.pad = ksize, stride, pad
-    d.w, d.bias, d.n, d.w_ld = ptr(w), ptr(bias), n, w_ld
+    d.w, d.bias, d.n, d.w_ld, d.k_order = ptr(w), ptr(bias), n, w_ld, k_order
     d.epi, d.act, d.out_f32 = epi, act, int(out_f32)
     d.out, d.residual, d.c_prev, d.c_out = ptr(out), ptr(residual), ptr(c_prev), ptr(c_out)
     d.row_map, d.out2 = ptr(row_map), ptr(out2)

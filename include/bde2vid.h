@@ -97,6 +97,10 @@ typedef struct bde_gemm_desc {
   int n;
   int w_ld;              /* row pitch of w in elements (>= K; 0 means K).  The tcgen05 engine    */
                          /* needs w_ld % 64 == 0 with zero padding beyond K.                    */
+  int k_order;           /* 0: k = (tap, channel) as above.  1: k = (chunk, tap, channel % 64) with  */
+                         /* chunk = channel / 64 (needs c0 % 64 == c1 % 64 == 0): all taps of one    */
+                         /* 64-channel slab are consecutive, which lets the tcgen05 engine serve the */
+                         /* im2col re-reads of a pixel tile from L1.                                 */
   /* epilogue */
   int epi;               /* BDE_EPI_*                                                            */
   int act;               /* BDE_ACT_* (STORE only)                                               */

@@ -14,13 +14,13 @@ def nhwc(x, dtype):
     return x.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)
 
 
-def run_conv(x_list, w, b, stride, engine, dtype, epi="store", act=0, **extra):
+def run_conv(x_list, w, b, stride, engine, dtype, epi="store", act=0, chunk_major=False, **extra):
     """x_list: 1 or 2 NCHW cpu tensors (channel concat); w [Co, Ci_total, k, k]; returns NCHW cpu float."""
     from bde2vid_b200 import ops
     from bde2vid_b200.engine import _pack_conv
     n, _, h, wd = x_list[0].shape
     k = w.shape[-1]
-    pw, ld = _pack_conv(w.to(DEV), dtype)
+    pw, ld = _pack_conv(w.to(DEV), dtype, chunk_major=chunk_major)
     a0 = nhwc(x_list[0], dtype)
     a1 = nhwc(x_list[1], dtype) if len(x_list) > 1 else None
     co = w.shape[0]
@@ -28,7 +28,7 @@ def run_conv(x_list, w, b, stride, engine, dtype, epi="store", act=0, **extra):
     out = torch.zeros(n, ho, wo, co, dtype=dtype, device=DEV)
     ops.gemm(a0, pw, b.to(DEV).float().contiguous(), out, n_img=n, h_in=h, w_in=wd, c0=x_list[0].shape[1], n=co,
              ksize=k, stride=stride, pad=k // 2, a1=a1, c1=0 if a1 is None else x_list[1].shape[1], w_ld=ld,
-             act=act, engine=engine, dtype=dtype, **extra)
+             act=act, engine=engine, dtype=dtype, k_order=int(chunk_major), **extra)
     torch.cuda.synchronize()
     return out.float().cpu().permute(0, 3, 1, 2)
 
@@ -199,3 +199,23 @@ def test_tcgen05_large_k_and_m_tiles():
     print("large: tc-vs-ref", float((got_tc - ref).abs().max()), "simt-vs-ref", float((got_simt - ref).abs().max()))
     assert (got_tc - ref).abs().max() <= 2e-2
     assert (got_simt - ref).abs().max() <= 2e-2
+
+
+@pytest.mark.parametrize("engine_name", ["simt", "tcgen05"])
+@pytest.mark.parametrize("case", [(2, 64, 128, 33, 44, 5, 2), (1, 128, 64, 19, 37, 3, 1), (2, 256, 128, 18, 22, 5, 1),
+                                  (3, 64, 32, 40, 56, 5, 1)])
+def test_chunk_major_k_order(engine_name, case):
+    """k_order=1 (64-channel chunk outermost) must give the same convolution; sizes exercise the 2-D pixel
+    tiles of the tcgen05 engine with ragged borders."""
+    from bde2vid_b200 import ops
+    tc = engine_name == "tcgen05"
+    n, ci, co, h, w, k, s = case
+    g = torch.Generator().manual_seed(sum(case) + 1)
+    x = bf16r(torch.randn(n, ci, h, w, generator=g))
+    wt = bf16r(torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5)
+    b = torch.randn(co, generator=g)
+    ref = F.conv2d(x, wt, b, stride=s, padding=k // 2)
+    got = run_conv([x], wt, b, s, ops.ENGINE_TCGEN05 if tc else ops.ENGINE_SIMT, torch.bfloat16, chunk_major=True)
+    err = (got - ref).abs().max()
+    print("chunk-major", engine_name, case, float(err))
+    assert err <= 1e-2 * max(1.0, ref.abs().max())
