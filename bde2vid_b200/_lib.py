@@ -30,6 +30,8 @@ class GemmDesc(C.Structure):
         ("ksize", C.c_int), ("stride", C.c_int), ("pad", C.c_int),
         ("w", C.c_void_p), ("bias", C.c_void_p),
         ("n", C.c_int), ("w_ld", C.c_int), ("k_order", C.c_int),
+        ("ln_mode", C.c_int), ("ln_D", C.c_int), ("ln_n_tok", C.c_int),
+        ("ln_frames", C.c_void_p * 8), ("ln_tok_map", C.c_void_p),
         ("epi", C.c_int), ("act", C.c_int), ("out_f32", C.c_int),
         ("out", C.c_void_p), ("residual", C.c_void_p), ("c_prev", C.c_void_p), ("c_out", C.c_void_p),
         ("row_map", C.c_void_p), ("out2", C.c_void_p),
@@ -57,6 +59,7 @@ EXPORTS = {
                           + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]),
     "bde_window_attention_mma_bias_stride": (C.c_int, [C.c_int]),
     "bde_window_attention_mma": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
+    "bde_window_attention_mma_qkv": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
     "bde_cast": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
 }
 

@@ -41,7 +41,8 @@ extern "C" int bde_gemm(const bde_gemm_desc* d, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   BDE_REQUIRE(d != nullptr, "bde_gemm: null descriptor");
   BDE_REQUIRE(d->dtype == BDE_F32 || d->dtype == BDE_BF16, "bde_gemm: bad dtype %d", d->dtype);
-  BDE_REQUIRE(d->a0 != nullptr && d->w != nullptr && d->out != nullptr, "bde_gemm: null operand");
+  BDE_REQUIRE((d->a0 != nullptr || d->ln_mode != 0) && d->w != nullptr && d->out != nullptr, "bde_gemm: null operand");
+  BDE_REQUIRE(d->ln_mode == 0 || d->engine == BDE_ENGINE_TCGEN05, "bde_gemm: ln_mode is only implemented by the tcgen05 engine");
   BDE_REQUIRE(d->c0 > 0 && d->c1 >= 0 && (d->c1 == 0 || d->a1 != nullptr), "bde_gemm: bad sources");
   BDE_REQUIRE(d->ksize >= 1 && d->stride >= 1 && d->pad >= 0 && d->n > 0, "bde_gemm: bad conv geometry");
   BDE_REQUIRE(d->h_out == (d->h_in + 2 * d->pad - d->ksize) / d->stride + 1 &&

@@ -42,6 +42,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// element strides of the q / k / v operands (they may live in one merged [rows, 3c] qkv buffer)
+struct AttnStrides {
+  int q_ld, q_rows_per_win, q_row0;   // q[w, m, :]  = q  + ((w * q_rows_per_win + q_row0 + m) * q_ld)
+  int kv_ld, kv_rows_per_win, v_off;  // k[w, n, :]  = kv + ((w * kv_rows_per_win + n) * kv_ld),  v = k + v_off
+};
+
 template <int NT>
 struct AttnSmem {
   static constexpr int kKeys = NT * 8;
@@ -55,7 +61,7 @@ template <int HD, int NT>
 __global__ void __launch_bounds__(256, 2) window_attention_mma_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
     const float* __restrict__ bias /* [heads][64][kBiasStride], -1e30 beyond n_kv */, int n_win, int n_q, int n_kv,
-    int c, __nv_bfloat16* __restrict__ out) {
+    int c, AttnStrides st, __nv_bfloat16* __restrict__ out) {
   using SM = AttnSmem<NT>;
   constexpr int KS = 2 * HD + 8;           // staged row: both heads' slices + pad (bf16 elements)
   constexpr int CH = (2 * HD) / 8;         // 16-byte chunks per row and tensor
@@ -87,27 +93,27 @@ __global__ void __launch_bounds__(256, 2) window_attention_mma_kernel(
   const uint32_t vs_u32 = (uint32_t)__cvta_generic_to_shared(vs);
 
   auto stage = [&](int w, int buf) {  // asynchronous copy of window w's K / V slices into buffer `buf`
-    const __nv_bfloat16* kvw = kv + (size_t)w * n_kv * 2 * c + h0 * HD;
+    const __nv_bfloat16* kvw = kv + (size_t)w * st.kv_rows_per_win * st.kv_ld + h0 * HD;
     for (int i = tid; i < n_kv * CH; i += 256) {
       const int n = i / CH, ch = i - n * CH;
-      const __nv_bfloat16* rowp = kvw + (size_t)n * 2 * c + ch * 8;
+      const __nv_bfloat16* rowp = kvw + (size_t)n * st.kv_ld + ch * 8;
       const uint32_t off = (uint32_t)((buf * kBufElems + n * KS + ch * 8) * 2);
       cp_async16(ks_u32 + off, rowp, 16u);
-      cp_async16(vs_u32 + off, rowp + c, 16u);
+      cp_async16(vs_u32 + off, rowp + st.v_off, 16u);
     }
     cp_async_commit();
   };
   auto load_q = [&](int w, uint32_t (&qa)[4]) {
     // a0:(row0, k 2t..2t+1) a1:(row1, same k) a2:(row0, k 2t+8..) a3:(row1, k 2t+8..)
-    const __nv_bfloat16* qw = q + (size_t)w * n_q * c + head * HD;
+    const __nv_bfloat16* qw = q + ((size_t)w * st.q_rows_per_win + st.q_row0) * st.q_ld + head * HD;
     qa[0] = qa[1] = qa[2] = qa[3] = 0u;
     if (2 * t < HD) {
-      if (row0 < n_q) qa[0] = __ldg(reinterpret_cast<const uint32_t*>(qw + (size_t)row0 * c + 2 * t));
-      if (row1 < n_q) qa[1] = __ldg(reinterpret_cast<const uint32_t*>(qw + (size_t)row1 * c + 2 * t));
+      if (row0 < n_q) qa[0] = __ldg(reinterpret_cast<const uint32_t*>(qw + (size_t)row0 * st.q_ld + 2 * t));
+      if (row1 < n_q) qa[1] = __ldg(reinterpret_cast<const uint32_t*>(qw + (size_t)row1 * st.q_ld + 2 * t));
     }
     if (2 * t + 8 < HD) {
-      if (row0 < n_q) qa[2] = __ldg(reinterpret_cast<const uint32_t*>(qw + (size_t)row0 * c + 2 * t + 8));
-      if (row1 < n_q) qa[3] = __ldg(reinterpret_cast<const uint32_t*>(qw + (size_t)row1 * c + 2 * t + 8));
+      if (row0 < n_q) qa[2] = __ldg(reinterpret_cast<const uint32_t*>(qw + (size_t)row0 * st.q_ld + 2 * t + 8));
+      if (row1 < n_q) qa[3] = __ldg(reinterpret_cast<const uint32_t*>(qw + (size_t)row1 * st.q_ld + 2 * t + 8));
     }
   };
 
@@ -225,8 +231,8 @@ __global__ void __launch_bounds__(256, 2) window_attention_mma_kernel(
 }
 
 template <int HD, int NT>
-int launch_mma(const void* q, const void* kv, const float* bias, int n_win, int n_q, int n_kv, int c, int heads, void* out,
-               cudaStream_t s) {
+int launch_mma(const void* q, const void* kv, const float* bias, int n_win, int n_q, int n_kv, int c, int heads,
+               const AttnStrides& st, void* out, cudaStream_t s) {
   using SM = AttnSmem<NT>;
   constexpr int KS = 2 * HD + 8;
   const size_t smem = (size_t)2 * 64 * SM::kBiasStride * sizeof(float) + (size_t)4 * SM::kRows * KS * 2;
@@ -242,7 +248,7 @@ int launch_mma(const void* q, const void* kv, const float* bias, int n_win, int 
   if (groups < 1) groups = 1;
   if (groups > n_win) groups = n_win;
   dim3 grid(heads / 2, groups);
-  kern<<<grid, 256, smem, s>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)kv, bias, n_win, n_q, n_kv, c,
+  kern<<<grid, 256, smem, s>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)kv, bias, n_win, n_q, n_kv, c, st,
                                (__nv_bfloat16*)out);
   return check_launch("window_attention_mma_kernel");
 }
@@ -259,12 +265,13 @@ int attn_mma_bias_stride(int n_kv) {
 }
 
 int window_attention_mma(const void* q, const void* kv, const float* bias, int n_win, int n_q, int n_kv, int c, int heads,
-                         void* out, cudaStream_t s) {
+                         const AttnStrides& st, void* out, cudaStream_t s) {
   const int hd = c / heads;
   const int nt = (n_kv + 7) / 8;
   BDE_REQUIRE(n_q <= 64 && nt <= 19 && heads % 2 == 0 && (hd == 4 || hd == 8 || hd == 16) && c % 8 == 0,
               "bde_window_attention_mma: unsupported shape (n_q=%d n_kv=%d hd=%d)", n_q, n_kv, hd);
-#define BDE_ATTN_MMA(HD_, NT_) return launch_mma<HD_, NT_>(q, kv, bias, n_win, n_q, n_kv, c, heads, out, s)
+  BDE_REQUIRE(st.q_ld % 2 == 0 && st.kv_ld % 8 == 0 && st.v_off % 8 == 0, "bde_window_attention_mma: misaligned strides");
+#define BDE_ATTN_MMA(HD_, NT_) return launch_mma<HD_, NT_>(q, kv, bias, n_win, n_q, n_kv, c, heads, st, out, s)
 #define BDE_ATTN_MMA_HD(NT_)              \
   switch (hd) {                           \
     case 4: BDE_ATTN_MMA(4, NT_);         \
@@ -287,5 +294,15 @@ extern "C" int bde_window_attention_mma_bias_stride(int n_kv) { return attn_mma_
 extern "C" int bde_window_attention_mma(const void* q, const void* kv, const float* bias_padded, int n_win, int n_q,
                                         int n_kv, int c, int heads, void* out, void* stream) {
   if (n_win == 0) return 0;
-  return window_attention_mma(q, kv, bias_padded, n_win, n_q, n_kv, c, heads, out, (cudaStream_t)stream);
+  AttnStrides st = {c, n_q, 0, 2 * c, n_kv, c};
+  return window_attention_mma(q, kv, bias_padded, n_win, n_q, n_kv, c, heads, st, out, (cudaStream_t)stream);
+}
+
+extern "C" int bde_window_attention_mma_qkv(const void* qkv, const float* bias_padded, int n_win, int n_q, int n_kv,
+                                            int q_row0, int c, int heads, void* out, void* stream) {
+  if (n_win == 0) return 0;
+  // rows of window w: [w * n_kv, (w + 1) * n_kv); columns [0, c) = q, [c, 2c) = k, [2c, 3c) = v
+  AttnStrides st = {3 * c, n_kv, q_row0, 3 * c, n_kv, c};
+  return window_attention_mma(qkv, (const __nv_bfloat16*)qkv + c, bias_padded, n_win, n_q, n_kv, c, heads, st, out,
+                              (cudaStream_t)stream);
 }

@@ -58,6 +58,11 @@ struct TcParams {
   const float* c_prev;
   float* c_out;
   const int* row_map;
+  // LayerNorm-gather A operand (kLn kernels): A[m, :] = (x - mean) / sqrt(var + 1e-5) of the fp32 row that
+  // token m = (win, d, tok) maps to (affine folded into the weights by the caller); zero tokens stay 0.
+  const float* ln_f[8];
+  const int* ln_map;
+  int ln_D, ln_ntok;
   long long* dbg;  // optional per-CTA phase timestamps (clock64), 8 slots per CTA, for bring-up profiling
 };
 
@@ -73,6 +78,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -217,15 +225,17 @@ struct TileGeom {
 // kDeep = true : one CTA per SM with a deep pipeline; the smaller shared-memory carve-out leaves
 //                >= 64 KB of L1 so that the im2col re-reads of a 2-D pixel tile (each input pixel is
 //                needed by up to k*k taps) are served by L1 instead of L2.
-template <int BN, bool kDeep>
+// kLn = true : the LayerNorm-gather producer fills all K blocks of the tile at once (K = C <= 256), so it
+//                needs >= 4 stages.
+template <int BN, bool kDeep, int kLn = 0>
 struct TileCfg {
-  static constexpr int kStages = kDeep ? (BN >= 256 ? 4 : (BN >= 128 ? 5 : (BN >= 64 ? 6 : 8)))
+  static constexpr int kStages = kLn > 0 ? kLn : kDeep ? (BN >= 256 ? 4 : (BN >= 128 ? 5 : (BN >= 64 ? 6 : 8)))
                                        : (BN >= 256 ? 4 : (BN >= 128 ? 3 : 4));
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr int kTmemCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
 };
 
 // fast transcendental forms for the bf16 path (relative error ~1e-6, far below bf16 resolution)
@@ -298,9 +308,9 @@ __device__ __forceinline__ void epilogue_quad(const TcParams& p, int m, int nb, 
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <int BN, bool kBTma, bool kDeep>
+template <int BN, bool kBTma, bool kDeep, int kLn>
 __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
-  using Cfg = TileCfg<BN, kDeep>;
+  using Cfg = TileCfg<BN, kDeep, kLn>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B tiles
@@ -349,6 +359,80 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
     const int j = lane & 7;
     const int rsub = lane >> 3;
     const int ntaps = p.ksize * p.ksize;
+    if (kLn > 0) {
+      // ---- LayerNorm-gather producer: fp32 rows -> normalised bf16 operand tile, all K blocks at once ----
+      constexpr int nchunk = kLn > 0 ? kLn : 1;  // K blocks = pipeline stages (C = 64 * nchunk)
+      constexpr int C = 64 * nchunk;
+      // rows are independent: unroll so that several rows' loads are in flight (all 4 for C <= 128)
+#pragma unroll(kLn <= 2 ? 4 : 2)
+      for (int i = 0; i < kRowsPerThread; ++i) {
+        const int row = warp * (4 * kRowsPerThread) + i * 4 + rsub;
+        const uint32_t dst = (uint32_t)row * 128u + (((uint32_t)j ^ (uint32_t)(row & 7)) << 4);
+        const int mm = geom.m0 + row;
+        const float* src = nullptr;
+        if (mm < p.M) {
+          int pix = mm, d = 0;
+          if (p.ln_map != nullptr) {
+            const int tok = mm % p.ln_ntok;
+            const int r2 = mm / p.ln_ntok;
+            d = r2 % p.ln_D;
+            pix = __ldg(p.ln_map + (r2 / p.ln_D) * p.ln_ntok + tok);
+          }
+          const float* fr = p.ln_f[0];
+#pragma unroll
+          for (int t = 1; t < 8; ++t) fr = (d == t) ? p.ln_f[t] : fr;
+          if (fr != nullptr && pix >= 0) src = fr + (size_t)pix * C + j * 8;
+        }
+        float v[nchunk][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < nchunk; ++kb) {
+          if (src != nullptr) {
+            const float4 t0 = *reinterpret_cast<const float4*>(src + kb * 64), t1 = *reinterpret_cast<const float4*>(src + kb * 64 + 4);
+            v[kb][0] = t0.x; v[kb][1] = t0.y; v[kb][2] = t0.z; v[kb][3] = t0.w;
+            v[kb][4] = t1.x; v[kb][5] = t1.y; v[kb][6] = t1.z; v[kb][7] = t1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[kb][e] = 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sum += v[kb][e];
+        }
+        // the 8 lanes of a row group (same rsub) reduce with xor 1, 2, 4
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        const float mean = sum / (float)C;
+        float sq = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < nchunk; ++kb)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float dlt = v[kb][e] - mean;
+            v[kb][e] = dlt;
+            sq += dlt * dlt;
+          }
+        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+        const float rstd = 1.0f / sqrtf(sq / (float)C + 1e-5f);
+#pragma unroll
+        for (int kb = 0; kb < nchunk; ++kb) {
+          {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = v[kb][e] * rstd;
+            const uint4 pk = pack8_bf16(o);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_a + kb * Cfg::kABytes + dst), "r"(pk.x), "r"(pk.y),
+                         "r"(pk.z), "r"(pk.w)
+                         : "memory");
+          }
+        }
+      }
+      // generic-proxy stores -> visible to the tensor core's async proxy, then one arrival per K block
+      fence_proxy_async_smem();
+      for (int kb = 0; kb < nchunk; ++kb) mbar_arrive(bar_full + 8 * kb);
+    } else {
     int pix0[kRowsPerThread];        // linear input pixel index of tap (0,0) (may lie outside the image)
     uint32_t vmask[kRowsPerThread];  // bit t set <=> tap t of this output pixel is inside the image
     uint32_t dsto[kRowsPerThread];   // swizzled byte offset of this lane's chunk inside a stage
@@ -433,6 +517,8 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
         }
       }
     }
+
+    }  // !kLn
 
     // =============================== epilogue ===========================================
     // thread <-> tile row (TMEM lane) 32*(warp & 3) + lane; the two warps sharing a lane quarter
@@ -584,10 +670,10 @@ int get_weight_tmap(const void* w, int n, int w_ld, int bn, CUtensorMap* out) {
   return 0;
 }
 
-template <int BN, bool kBTma, bool kDeep>
+template <int BN, bool kBTma, bool kDeep, int kLn = 0>
 int launch(const CUtensorMap& tmap, const TcParams& p, cudaStream_t s) {
-  using Cfg = TileCfg<BN, kDeep>;
-  auto kern = gemm_tc_kernel<BN, kBTma, kDeep>;
+  using Cfg = TileCfg<BN, kDeep, kLn>;
+  auto kern = gemm_tc_kernel<BN, kBTma, kDeep, kLn>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -639,11 +725,22 @@ int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s) {
   p.out = d->out; p.out2 = d->out2; p.residual = d->residual; p.c_prev = d->c_prev; p.c_out = d->c_out;
   p.row_map = d->row_map;
   p.dbg = nullptr;
+  const bool ln = d->ln_mode != 0;
+  for (int i = 0; i < 8; ++i) p.ln_f[i] = ln && i < d->ln_D ? d->ln_frames[i] : nullptr;
+  p.ln_map = d->ln_tok_map;
+  p.ln_D = ln ? d->ln_D : 1;
+  p.ln_ntok = ln ? (d->ln_n_tok > 0 ? d->ln_n_tok : 1) : 1;
+  if (ln) {
+    BDE_REQUIRE(d->ksize == 1 && d->stride == 1 && d->pad == 0 && d->c1 == 0, "bde_gemm(tcgen05): ln_mode needs a 1x1 / dense GEMM");
+    BDE_REQUIRE(d->c0 == 64 || d->c0 == 128 || d->c0 == 256, "bde_gemm(tcgen05): ln_mode supports C in {64, 128, 256}");
+    BDE_REQUIRE(d->ln_D >= 1 && d->ln_D <= 8, "bde_gemm(tcgen05): ln_D must be in [1, 8]");
+  }
   BDE_REQUIRE(p.c0 % 8 == 0 && p.c1 % 8 == 0, "bde_gemm(tcgen05): channel counts must be multiples of 8");
   BDE_REQUIRE(p.ksize * p.ksize <= 32, "bde_gemm(tcgen05): kernel size up to 5x5");
   BDE_REQUIRE(p.w_ld % BK == 0 && p.w_ld >= p.num_kb * BK, "bde_gemm(tcgen05): w_ld must be a zero-padded multiple of 64");
   BDE_REQUIRE(p.N % 32 == 0, "bde_gemm(tcgen05): N must be a multiple of 32");
   BDE_REQUIRE((size_t)d->n_img * d->h_in * d->w_in < ((size_t)1 << 31), "bde_gemm(tcgen05): input pixel count overflows int32");
+  BDE_REQUIRE(ln || d->a0 != nullptr, "bde_gemm(tcgen05): null A operand");
   BDE_REQUIRE((((uintptr_t)d->a0) & 15) == 0 && (((uintptr_t)d->a1) & 15) == 0 && (((uintptr_t)d->w) & 127) == 0,
               "bde_gemm(tcgen05): operands must be 16-byte (weights 128-byte) aligned");
   if (p.M == 0) return 0;
@@ -665,6 +762,10 @@ int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s) {
   else if (p.N % 64 == 0) bn = 64;
   const size_t m_tiles = ceil_div(p.M, BM);
   if (p.N % 256 == 0 && m_tiles * (p.N / 256) >= 2 * (size_t)kNumSMs) bn = 256;
+  if (ln) {
+    // the LayerNorm is recomputed by every N tile of a row block: prefer the widest tile
+    bn = (p.N % 256 == 0) ? 256 : (p.N % 192 == 0) ? 192 : (p.N % 128 == 0) ? 128 : (p.N % 64 == 0) ? 64 : 32;
+  }
   if (g_dbg != nullptr) {
     const size_t mt = p.tiles_x > 0 ? (size_t)p.n_img * p.tiles_x * p.tiles_y : ceil_div(p.M, BM);
     if (mt * (p.N / bn) <= g_dbg_ctas) p.dbg = g_dbg;
@@ -675,6 +776,24 @@ int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s) {
   if (tma) {
     int rc = get_weight_tmap(d->w, p.N, p.w_ld, bn, &tmap);
     if (rc != 0) return rc;
+  }
+  if (ln) {
+    const int chunks = p.c0 / 64;
+#define BDE_TC_LN(BN_, CH_) \
+  return tma ? launch<BN_, true, false, CH_>(tmap, p, s) : launch<BN_, false, false, CH_>(tmap, p, s)
+#define BDE_TC_LN_BN(CH_)                 \
+  switch (bn) {                           \
+    case 32: BDE_TC_LN(32, CH_);          \
+    case 64: BDE_TC_LN(64, CH_);          \
+    case 128: BDE_TC_LN(128, CH_);        \
+    case 192: BDE_TC_LN(192, CH_);        \
+    default: BDE_TC_LN(256, CH_);         \
+  }
+    if (chunks == 1) { BDE_TC_LN_BN(1) }
+    if (chunks == 2) { BDE_TC_LN_BN(2) }
+    BDE_TC_LN_BN(4)
+#undef BDE_TC_LN_BN
+#undef BDE_TC_LN
   }
 #define BDE_TC_LAUNCH(BN_)                                                                                   \
   case BN_:                                                                                                  \

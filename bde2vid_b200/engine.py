@@ -164,7 +164,27 @@ class Engine:
                         bias = bias_hmn.permute(0, 2, 1).contiguous()
                         use_mma = (dt == torch.bfloat16 and n_tok <= 64 and hd in (4, 8, 16) and self.heads % 2 == 0
                                    and ops.attention_mma_bias_stride(self.D * n_tok) > 0)
+                        # fused front end (tcgen05 only): LayerNorm folded into the projections.
+                        #   Linear(LN(x)) = (W diag(gamma)) xhat + (W beta + b),  xhat = (x - mean) / sqrt(var + eps)
+                        # q and kv share xhat, so ONE GEMM with N = 3C produces [q | k | v] for every kv token.
+                        fused = tc and use_mma and C in (64, 128, 256)
+                        qkv_l = fc1_l = None
+                        if fused:
+                            sc = hd ** -0.5
+                            Wq, bq = a.q.weight.detach().float(), a.q.bias.detach().float()
+                            Wkv, bkv = a.kv.weight.detach().float(), a.kv.bias.detach().float()
+                            gq, btq = a.norm_q.weight.detach().float(), a.norm_q.bias.detach().float()
+                            gk, btk = a.norm_kv.weight.detach().float(), a.norm_kv.bias.detach().float()
+                            Wqkv = torch.cat([sc * Wq * gq[None, :], Wkv * gk[None, :]], 0)
+                            bqkv = torch.cat([sc * (Wq @ btq + bq), Wkv @ btk + bkv], 0)
+                            w, ld = _pack_linear(Wqkv, dt)
+                            qkv_l = _Layer(w, ld, bqkv.contiguous(), 3 * C)
+                            W1, b1 = blk.mlp.fc1.weight.detach().float(), blk.mlp.fc1.bias.detach().float()
+                            g2, bt2 = blk.norm2.weight.detach().float(), blk.norm2.bias.detach().float()
+                            w, ld = _pack_linear(W1 * g2[None, :], dt)
+                            fc1_l = _Layer(w, ld, (W1 @ bt2 + b1).contiguous(), 4 * C)
                         blocks.append(dict(
+                            qkv=qkv_l, fc1_ln=fc1_l,
                             bias_mma=ops.pad_bias_for_mma(bias_hmn, self.D * n_tok) if use_mma else None,
                             nq_g=f32(a.norm_q.weight), nq_b=f32(a.norm_q.bias),
                             nkv_g=f32(a.norm_kv.weight), nkv_b=f32(a.norm_kv.bias),
@@ -263,6 +283,7 @@ class _Plan:
                 d.update(tm=[tm_plain, tm_dil], nwin=nwin, ntok=ntok,
                          xs=E(P, C, dtype=f32), qn=E(nwin * ntok, C), kvn=E(nwin * eng.D * ntok, C),
                          qb=E(nwin * ntok, C), kvb=E(nwin * eng.D * ntok, 2 * C), ob=E(nwin * ntok, C),
+                         qkv=E(nwin * eng.D * ntok, 3 * C),
                          yn=E(P, C), hid=E(P, 4 * C))
             self.lv.append(d)
         Tc = min(eng.dec_chunk, T)
@@ -393,6 +414,18 @@ class _Plan:
                 tm = d["tm"][i & 1]
                 fr = list(frames)
                 fr[eng.q_ind] = xs
+                if blk["qkv"] is not None:
+                    # fused: [window gather + LayerNorm + q/k/v projection] -> attention -> proj+scatter ->
+                    #        [LayerNorm + fc1 + GELU] -> fc2 + residual          (5 launches per block)
+                    M = nwin * D * ntok
+                    eng._gemm(blk["qkv"], None, d["qkv"], 1, M, 1, C, ln_frames=fr, ln_tok_map=tm.view(-1), ln_n_tok=ntok)
+                    ops.window_attention_mma_qkv(d["qkv"], blk["bias_mma"], nwin, ntok, D * ntok, eng.q_ind * ntok, C,
+                                                 eng.heads, d["ob"])
+                    eng._gemm(blk["proj"], d["ob"], xs, 1, nwin * ntok, 1, C, epi=EPI_SCATTER, row_map=tm.view(-1))
+                    eng._gemm(blk["fc1_ln"], None, d["hid"], 1, P, 1, C, act=ACT_GELU, ln_frames=[xs])
+                    eng._gemm(blk["fc2"], d["hid"], xs, 1, P, 1, 4 * C, out_f32=True, residual=xs)
+                    self.launches += 5
+                    continue
                 if C in (64, 128, 256):
                     ops.ln_gather_qkv(fr, eng.q_ind, tm, nwin, ntok, C, blk["nkv_g"], blk["nkv_b"], blk["nq_g"],
                                       blk["nq_b"], d["kvn"], d["qn"])

@@ -43,13 +43,20 @@ def pack_voxel_nhwc(vox, c_pad, dtype, out=None):
 
 def gemm(a0, w, bias, out, *, n_img, h_in, w_in, c0, n, ksize=1, stride=1, pad=0, a1=None, c1=0, w_ld=0,
          epi=EPI_STORE, act=ACT_NONE, out_f32=False, residual=None, c_prev=None, c_out=None, row_map=None,
-         out2=None, engine=ENGINE_SIMT, dtype=None, k_order=0):
-    """Implicit-GEMM conv / linear (see bde_gemm in include/bde2vid.h).  Returns (h_out, w_out)."""
+         out2=None, engine=ENGINE_SIMT, dtype=None, k_order=0, ln_frames=None, ln_tok_map=None, ln_n_tok=1):
+    """Implicit-GEMM conv / linear (see bde_gemm in include/bde2vid.h).  Returns (h_out, w_out).
+    ``ln_frames`` (list of float32 [*, c0] tensors or None) switches the A operand to the fused
+    LayerNorm-gather form (``a0`` is then ignored and may be None)."""
     lib = _lib.require_device()
     d = _lib.GemmDesc()
     d.engine = engine
     d.dtype = BDE_DTYPE[a0.dtype if dtype is None else dtype]
     d.a0, d.a1 = ptr(a0), ptr(a1)
+    if ln_frames is not None:
+        d.ln_mode, d.ln_D, d.ln_n_tok = 1, len(ln_frames), ln_n_tok
+        for i, f in enumerate(ln_frames):
+            d.ln_frames[i] = None if f is None else f.data_ptr()
+        d.ln_tok_map = ptr(ln_tok_map)
     d.c0, d.c1 = c0, c1
     d.n_img, d.h_in, d.w_in = n_img, h_in, w_in
     d.h_out = (h_in + 2 * pad - ksize) // stride + 1
@@ -140,6 +147,14 @@ def window_attention_mma(q, kv, bias_padded, n_win, n_q, n_kv, c, heads, out):
     assert q.dtype == torch.bfloat16
     check(lib.bde_window_attention_mma(ptr(q), ptr(kv), ptr(bias_padded), n_win, n_q, n_kv, c, heads, ptr(out),
                                        stream_ptr()), "bde_window_attention_mma")
+    return out
+
+
+def window_attention_mma_qkv(qkv, bias_padded, n_win, n_q, n_kv, q_row0, c, heads, out):
+    lib = _lib.require_device()
+    assert qkv.dtype == torch.bfloat16
+    check(lib.bde_window_attention_mma_qkv(ptr(qkv), ptr(bias_padded), n_win, n_q, n_kv, q_row0, c, heads, ptr(out),
+                                           stream_ptr()), "bde_window_attention_mma_qkv")
     return out
 
 

@@ -101,6 +101,17 @@ typedef struct bde_gemm_desc {
                          /* chunk = channel / 64 (needs c0 % 64 == c1 % 64 == 0): all taps of one    */
                          /* 64-channel slab are consecutive, which lets the tcgen05 engine serve the */
                          /* im2col re-reads of a pixel tile from L1.                                 */
+  /* LayerNorm-gather A operand (tcgen05 engine only).  ln_mode = 1: a0 is ignored and                */
+  /*   A[m, :] = (x - mean(x)) / sqrt(var(x) + 1e-5),  x = ln_frames[d][ln_tok_map[win*n_tok + tok], :]   */
+  /* with m = (win*ln_D + d)*ln_n_tok + tok (float32 rows of c0 channels; NULL frame or map < 0 = zero   */
+  /* token, which stays all-zero).  ln_tok_map = NULL means the identity map (plain rows, ln_D = 1).  */
+  /* The LayerNorm affine is NOT applied: fold gamma into w and beta into bias (W diag(g), W b + bias).  */
+  /* Replaces window_partition + norm_q / norm_kv (DTransformer.py:41-60, 183-184) and norm2 (:281).     */
+  int ln_mode;
+  int ln_D;
+  int ln_n_tok;
+  const float* ln_frames[8];
+  const int* ln_tok_map;
   /* epilogue */
   int epi;               /* BDE_EPI_*                                                            */
   int act;               /* BDE_ACT_* (STORE only)                                               */
@@ -174,6 +185,12 @@ int bde_window_attention(const void* q, const void* kv, const float* bias, int n
 int bde_window_attention_mma_bias_stride(int n_kv);
 int bde_window_attention_mma(const void* q, const void* kv, const float* bias_padded, int n_win, int n_q,
                              int n_kv, int c, int heads, void* out, void* stream);
+
+/* Same, reading q / k / v from ONE merged projection buffer qkv: bf16 [n_win * n_kv, 3c] whose row
+ * w * n_kv + n holds [q | k | v] of kv token n of window w (the fused LayerNorm + qkv GEMM writes it);
+ * the n_q query rows of a window start at row q_row0 (= q_slot * n_q) inside the window. */
+int bde_window_attention_mma_qkv(const void* qkv, const float* bias_padded, int n_win, int n_q, int n_kv,
+                                 int q_row0, int c, int heads, void* out, void* stream);
 
 /* float32 -> dtype copy/cast (and back); n elements */
 int bde_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);

@@ -219,3 +219,46 @@ def test_chunk_major_k_order(engine_name, case):
     err = (got - ref).abs().max()
     print("chunk-major", engine_name, case, float(err))
     assert err <= 1e-2 * max(1.0, ref.abs().max())
+
+
+@pytest.mark.parametrize("C,N,D", [(64, 192, 3), (256, 768, 3), (128, 384, 2), (64, 256, 1), (256, 1024, 1)])
+def test_tcgen05_layernorm_gather_gemm(C, N, D):
+    """Fused A operand: window-token gather + LayerNorm (affine folded into the weights) feeding the GEMM.
+    Reference: layer_norm + linear in fp32 on the CPU (DTransformer.py:183-189, :281)."""
+    from bde2vid_b200 import ops
+    from bde2vid_b200.engine import _pack_linear, window_token_map
+    g = torch.Generator().manual_seed(C + N)
+    B, H, W = 2, 9, 13
+    frames = [torch.randn(B * H * W, C, generator=g) * 2 + 0.5 for _ in range(D)]
+    if D >= 3:
+        frames[2] = None
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    Wt = torch.randn(N, C, generator=g) / C ** 0.5
+    b = torch.randn(N, generator=g)
+    Wf, bf = Wt * gamma[None, :], Wt @ beta + b            # folded affine
+    pw, ld = _pack_linear(Wf.to(DEV), torch.bfloat16)
+    if D == 1:
+        tm, rows = None, B * H * W
+        src = frames[0]
+        ref = F.linear(F.layer_norm(src, (C,), gamma, beta, 1e-5), Wt, b)
+        ntok = 1
+    else:
+        tmd, _ = window_token_map(B, H, W, (7, 7), True, DEV)
+        nwin, ntok = tmd.shape
+        tm = tmd.view(-1)
+        rows = nwin * D * ntok
+        tmc = tmd.cpu().long()
+        toks = []
+        for d in range(D):
+            s = torch.zeros(B * H * W, C) if frames[d] is None else frames[d]
+            toks.append(s[tmc.clamp(min=0).reshape(-1)].reshape(nwin, ntok, C) * (tmc >= 0).unsqueeze(-1))
+        x = torch.stack(toks, 1).reshape(rows, C)
+        ref = F.linear(F.layer_norm(x, (C,), gamma, beta, 1e-5), Wt, b)
+    out = torch.zeros(rows, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(None, pw, bf.to(DEV).contiguous(), out, n_img=1, h_in=rows, w_in=1, c0=C, n=N, w_ld=ld,
+             engine=ops.ENGINE_TCGEN05, dtype=torch.bfloat16,
+             ln_frames=[None if f is None else f.to(DEV) for f in frames], ln_tok_map=tm, ln_n_tok=ntok)
+    torch.cuda.synchronize()
+    err = (out.float().cpu() - ref).abs().max()
+    print("ln-gemm", C, N, D, float(err), float(ref.abs().max()))
+    assert err <= 3e-2 * max(1.0, float(ref.abs().max()))
