@@ -43,6 +43,8 @@ EXPORTS = {
     "bde_abi_version": (C.c_int, []),
     "bde_device_ok": (C.c_int, []),
     "bde_voxelize_seq": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "bde_voxelize_seq_strided": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 8 + [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+                                           C.c_void_p]),
     "bde_pack_voxel_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_void_p]),
     "bde_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     "bde_add": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(512) voxel_band_kernel(
     const float* __restrict__ xs, const float* __restrict__ ys, const float* __restrict__ ts,
     const float* __restrict__ ps, const int64_t* __restrict__ offsets, int bins, int H, int W,
     int pad_top, int pad_left, int Hp, int Wp, int band_rows, int vec_ok, float* __restrict__ out,
-    int* oob_count) {
+    size_t win_stride, int* oob_count) {
   extern __shared__ float tile[];  // [bins][band_rows][W]
   const int win = blockIdx.y;
   const int r0 = blockIdx.x * band_rows;           // first padded row of this band
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(512) voxel_band_kernel(
   __syncthreads();
 
   // coalesced write of the band, padding included
-  float* dst = out + (size_t)win * bins * Hp * Wp;
+  float* dst = out + (size_t)win * win_stride;
   const int rows = r1 - r0;
   const int total = bins * rows * Wp;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
@@ -172,14 +172,14 @@ __global__ void __launch_bounds__(512) voxel_band_kernel(
 __global__ void __launch_bounds__(256) voxel_atomic_kernel(
     const float* __restrict__ xs, const float* __restrict__ ys, const float* __restrict__ ts,
     const float* __restrict__ ps, const int64_t* __restrict__ offsets, int bins, int H, int W,
-    int pad_top, int pad_left, int Hp, int Wp, float* __restrict__ out, int* oob_count) {
+    int pad_top, int pad_left, int Hp, int Wp, float* __restrict__ out, size_t win_stride, int* oob_count) {
   const int win = blockIdx.y;
   const int64_t ea = offsets[win], eb = offsets[win + 1];
   if (eb <= ea) return;
   const float t0 = ts[ea];
   const float dt = __fsub_rn(ts[eb - 1], t0);
   const float bm1 = (float)(bins - 1);
-  float* dst = out + (size_t)win * bins * Hp * Wp;
+  float* dst = out + (size_t)win * win_stride;
   const size_t plane = (size_t)Hp * Wp;
   int oob = 0;
   for (int64_t e = ea + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < eb;
@@ -218,11 +218,26 @@ __global__ void pack_voxel_kernel(const float* __restrict__ vox, int bins, size_
 
 using namespace bde;
 
+extern "C" int bde_voxelize_seq_strided(const float* xs, const float* ys, const float* ts, const float* ps,
+                                        const int64_t* offsets, int T, int num_bins, int H, int W, int pad_top,
+                                        int pad_left, int Hp, int Wp, float* out, size_t out_window_stride,
+                                        int* oob_count, int algo, void* stream);
+
 extern "C" int bde_voxelize_seq(const float* xs, const float* ys, const float* ts, const float* ps,
                                 const int64_t* offsets, int T, int num_bins, int H, int W, int pad_top,
                                 int pad_left, int Hp, int Wp, float* out, int* oob_count, int algo,
                                 void* stream) {
+  return bde_voxelize_seq_strided(xs, ys, ts, ps, offsets, T, num_bins, H, W, pad_top, pad_left, Hp, Wp, out,
+                                  (size_t)num_bins * Hp * Wp, oob_count, algo, stream);
+}
+
+extern "C" int bde_voxelize_seq_strided(const float* xs, const float* ys, const float* ts, const float* ps,
+                                        const int64_t* offsets, int T, int num_bins, int H, int W, int pad_top,
+                                        int pad_left, int Hp, int Wp, float* out, size_t out_window_stride,
+                                        int* oob_count, int algo, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
+  const size_t grid_elems = (size_t)num_bins * Hp * Wp;
+  BDE_REQUIRE(out_window_stride >= grid_elems, "bde_voxelize_seq: window stride smaller than one grid");
   BDE_REQUIRE(T >= 0 && num_bins >= 1 && H > 0 && W > 0, "bde_voxelize_seq: bad sizes");
   BDE_REQUIRE(pad_top >= 0 && pad_left >= 0 && Hp >= H + pad_top && Wp >= W + pad_left,
               "bde_voxelize_seq: padded grid %dx%d cannot hold %dx%d at (%d,%d)", Hp, Wp, H, W, pad_top, pad_left);
@@ -243,18 +258,18 @@ extern "C" int bde_voxelize_seq(const float* xs, const float* ys, const float* t
     dim3 grid(bands, T);
     int vec_ok = ((((uintptr_t)xs) | ((uintptr_t)ys) | ((uintptr_t)ts) | ((uintptr_t)ps)) & 15) == 0;
     kern<<<grid, 512, smem, s>>>(xs, ys, ts, ps, offsets, num_bins, H, W, pad_top, pad_left, Hp, Wp,
-                                 band_rows, vec_ok, out, oob_count);
+                                 band_rows, vec_ok, out, out_window_stride, oob_count);
     return check_launch("voxel_band_kernel");
   }
   BDE_REQUIRE(algo == 2, "bde_voxelize_seq: unknown algo %d", algo);
-  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)T * num_bins * Hp * Wp * sizeof(float), s);
+  cudaError_t e = cudaMemset2DAsync(out, out_window_stride * sizeof(float), 0, grid_elems * sizeof(float), (size_t)T, s);
   BDE_REQUIRE(e == cudaSuccess, "bde_voxelize_seq: memset: %s", cudaGetErrorString(e));
   // grid.x sized so the whole launch is a few waves over 148 SMs regardless of T
   int bx = (int)ceil_div((size_t)kNumSMs * 8, (size_t)T);
   bx = bx < 1 ? 1 : (bx > 1024 ? 1024 : bx);
   dim3 grid(bx, T);
   voxel_atomic_kernel<<<grid, 256, 0, s>>>(xs, ys, ts, ps, offsets, num_bins, H, W, pad_top, pad_left, Hp,
-                                           Wp, out, oob_count);
+                                           Wp, out, out_window_stride, oob_count);
   return check_launch("voxel_atomic_kernel");
 }
 

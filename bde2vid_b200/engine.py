@@ -238,13 +238,22 @@ class Engine:
 
     def forward_events(self, xs, ys, ts, ps, offsets, H, W, crop, use_graph=True, slot=0):
         """Fused path: raw events -> frames (voxeliser writes the padded grids the UNet reads)."""
-        T = offsets.numel() - 1
+        return self.forward_events_batch([(xs, ys, ts, ps, offsets)], H, W, crop, use_graph, slot)[0]
+
+    def forward_events_batch(self, seqs, H, W, crop, use_graph=True, slot=0):
+        """B independent sequences (each a tuple xs, ys, ts, ps, offsets with the same number of windows)
+        processed as one batch: every kernel of the schedule runs once for all B sequences.  Returns a list
+        (per sequence) of T frames [1, 1, Hp, Wp]."""
+        B = len(seqs)
+        T = seqs[0][4].numel() - 1
+        if any(s[4].numel() - 1 != T for s in seqs):
+            raise ValueError("sequences batched together must have the same number of windows")
         Hp, Wp = crop.height_crop_size, crop.width_crop_size
-        p = self.plan(T, 1, Hp, Wp, slot)
-        p.set_events(xs, ys, ts, ps, offsets, H, W, crop.padding_top, crop.padding_left)
+        p = self.plan(T, B, Hp, Wp, slot)
+        p.set_events(seqs, H, W, crop.padding_top, crop.padding_left)
         p.run(use_graph, from_events=True)
-        img = p.img.clone().view(T, 1, 1, Hp, Wp)
-        return list(img.unbind(0))
+        img = p.img.clone().view(T, B, 1, 1, Hp, Wp)
+        return [list(img[:, b].unbind(0)) for b in range(B)]
 
 
 class _Plan:
@@ -298,23 +307,27 @@ class _Plan:
         self.ev = None
 
     # ------------------------------------------------------------------------------------
-    def set_events(self, xs, ys, ts, ps, offsets, H, W, pad_top, pad_left):
-        """Stage one sequence's events into static buffers (host or device sources; the copies are
+    def set_events(self, seqs, H, W, pad_top, pad_left):
+        """Stage the events of the B sequences into static buffers (host or device sources; the copies are
         asynchronous on the current stream) so that the captured graph can include the voxeliser."""
-        n = xs.numel()
+        assert len(seqs) == self.B
+        n = max(s[0].numel() for s in seqs)
         dev = self.eng.device
         geom = (H, W, pad_top, pad_left)
         if self.ev is None or self.ev_cap < n or self.ev_geom != geom:
             self.ev_cap = max(int(n * 1.25) + 16, 1024)
-            self.ev = [torch.zeros(self.ev_cap, dtype=torch.float32, device=dev) for _ in range(4)]
-            self.ev_off = torch.zeros(self.T + 1, dtype=torch.int64, device=dev)
+            self.ev = [[torch.zeros(self.ev_cap, dtype=torch.float32, device=dev) for _ in range(4)]
+                       for _ in range(self.B)]
+            self.ev_off = [torch.zeros(self.T + 1, dtype=torch.int64, device=dev) for _ in range(self.B)]
             self.oob = torch.zeros(1, dtype=torch.int32, device=dev)
             self.ev_geom = geom
             self.graphs.pop(True, None)
             self.runs[True] = 0
-        for dst, src in zip(self.ev, (xs, ys, ts, ps)):
-            dst[:n].copy_(src, non_blocking=True)
-        self.ev_off.copy_(offsets, non_blocking=True)
+        for b, (xs, ys, ts, ps, offsets) in enumerate(seqs):
+            m = xs.numel()
+            for dst, src in zip(self.ev[b], (xs, ys, ts, ps)):
+                dst[:m].copy_(src, non_blocking=True)
+            self.ev_off[b].copy_(offsets, non_blocking=True)
 
     def run(self, use_graph, from_events):
         self.runs[from_events] = self.runs.get(from_events, 0) + 1
@@ -338,11 +351,13 @@ class _Plan:
         N = T * B
         self.launches = 0
         if from_events:
-            xs, ys, ts, ps = self.ev
             H, W, pt, pl = self.ev_geom
-            ops.voxelize_seq(xs, ys, ts, ps, self.ev_off, eng.bins, H, W, pt, pl, Hp, Wp,
-                             out=self.vox_in.view(T, eng.bins, Hp, Wp), oob_count=self.oob)
-            self.launches += 1
+            # sequence b writes windows t = 0..T-1 at vox_in[t, b]: window stride = B grids
+            for b in range(B):
+                xs, ys, ts, ps = self.ev[b]
+                ops.voxelize_seq_into(xs, ys, ts, ps, self.ev_off[b], eng.bins, H, W, pt, pl, Hp, Wp,
+                                      self.vox_in[0, b], B * eng.bins * Hp * Wp, oob_count=self.oob)
+                self.launches += 1
         ops.pack_voxel_nhwc(self.vox_in.view(N, eng.bins, Hp, Wp), VOX_CPAD, eng.dtype, out=self.vox8)
         # A: head conv + ReLU over all frames (...V5.py:116)
         eng._gemm(eng.head, self.vox8, self.head, N, Hp, Wp, VOX_CPAD, act=ACT_RELU)

@@ -209,6 +209,17 @@ class BDE2VID(nn.Module):
                                     slot=slot)
         return [crop.crop(f) for f in frames]
 
+    def reconstruct_events_batch(self, seqs, sensor_size, num_encoders=None, slot=0):
+        """Several independent event sequences (same window count) reconstructed as ONE batch: ``seqs`` is a
+        list of (xs, ys, ts, ps, offsets) tuples; returns a list (per sequence) of T cropped frames."""
+        from .croper import Croper
+        H, W = sensor_size
+        crop = Croper(self.generator.num_encoders if num_encoders is None else num_encoders)
+        crop.update_params(W, H)
+        eng = self.generator.engine()
+        out = eng.forward_events_batch(seqs, H, W, crop, use_graph=self.generator.use_cuda_graph, slot=slot)
+        return [[crop.crop(f) for f in frames] for frames in out]
+
 
 def load_checkpoint(path_or_dict, device="cuda"):
     """Reference loading path (eval_models_seq.py:41-60,:86) for mmengine-style checkpoints."""

@@ -30,6 +30,17 @@ def voxelize_seq(xs, ys, ts, ps, offsets, num_bins, H, W, pad_top=0, pad_left=0,
     return out
 
 
+def voxelize_seq_into(xs, ys, ts, ps, offsets, num_bins, H, W, pad_top, pad_left, Hp, Wp, out_view, window_stride,
+                      oob_count=None, algo=0):
+    """Voxelise one sequence into a strided destination: ``out_view`` is the tensor element where window 0's grid
+    starts and consecutive windows are ``window_stride`` floats apart (batch buffers [T, B, bins, Hp, Wp])."""
+    lib = _lib.require_device()
+    T = offsets.numel() - 1
+    check(lib.bde_voxelize_seq_strided(ptr(xs), ptr(ys), ptr(ts), ptr(ps), ptr(offsets), T, num_bins, H, W, pad_top,
+                                       pad_left, Hp, Wp, C.c_void_p(out_view.data_ptr()), window_stride, ptr(oob_count),
+                                       algo, stream_ptr()), "bde_voxelize_seq_strided")
+
+
 def pack_voxel_nhwc(vox, c_pad, dtype, out=None):
     """[N, bins, Hp, Wp] float32 planar -> [N, Hp, Wp, c_pad] NHWC of ``dtype``."""
     lib = _lib.require_device()

@@ -66,6 +66,13 @@ int bde_voxelize_seq(const float* xs, const float* ys, const float* ts, const fl
                      int pad_top, int pad_left, int Hp, int Wp,
                      float* out, int* oob_count, int algo, void* stream);
 
+/* Same, with `out_window_stride` floats between the grids of consecutive windows (>= bins*Hp*Wp).  Lets B
+ * sequences be voxelised straight into one [T, B, bins, Hp, Wp] batch buffer (stride B*bins*Hp*Wp). */
+int bde_voxelize_seq_strided(const float* xs, const float* ys, const float* ts, const float* ps,
+                             const int64_t* offsets, int T, int num_bins, int H, int W,
+                             int pad_top, int pad_left, int Hp, int Wp,
+                             float* out, size_t out_window_stride, int* oob_count, int algo, void* stream);
+
 /* planar voxel grids float32[T, bins, Hp, Wp] -> NHWC with channels padded to c_pad (zeros),
  * element type `dtype`.  Feeds the head convolution (bde2vid_cross_scale_propogation_V5.py:116). */
 int bde_pack_voxel_nhwc(const float* vox, int T, int bins, int Hp, int Wp, int c_pad,

@@ -116,3 +116,22 @@ def test_no_cpu_fallback():
         model([{"events": torch.zeros(1, 5, 64, 64)}])
     with pytest.raises(NotImplementedError):
         BDE2VID(generator=dict(gen_cfg, norm="BN"))
+
+
+def test_batched_event_sequences_match_single():
+    """reconstruct_events_batch(B sequences) must equal B separate reconstruct_events calls (same kernels,
+    different M), and the oracle."""
+    H, W, T, N = 60, 90, 3, 2500
+    model, cfg, sd = build_model(dict(depths=[1, 0, 1]), 6, "bf16")
+    seqs = []
+    for sid in (31, 32, 33):
+        ev = synth.gen_events(sid, T, H, W, N)
+        seqs.append(tuple(torch.from_numpy(a).to(DEV) for a in synth.to_loader_format_seq(ev)))
+    with torch.no_grad():
+        single = [model.reconstruct_events(*s, (H, W)) for s in seqs]
+        for _ in range(3):
+            batched = model.reconstruct_events_batch(seqs, (H, W))
+    for b in range(3):
+        err = max(float((x - y).abs().max()) for x, y in zip(single[b], batched[b]))
+        print("batched vs single", b, err)
+        assert err <= 1e-3
