@@ -46,6 +46,8 @@ EXPORTS = {
     "bde_voxelize_seq_strided": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 8 + [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
                                            C.c_void_p]),
     "bde_pack_voxel_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_void_p]),
+    "bde_profile_begin": (C.c_int, [C.c_int]),
+    "bde_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "bde_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     "bde_add": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                           C.c_void_p]),

@@ -37,6 +37,50 @@ extern "C" int bde_device_ok(void) {
   return major == 10 ? 1 : 0;
 }
 
+// ---- optional per-launch timing of the tcgen05 GEMM kernel (used by bench.py's roofline measurement) ----
+// CUDA events are recorded on the launching stream right around the kernel, from C, so that the pair
+// brackets nothing but the launch itself.
+#include <vector>
+namespace {
+std::vector<cudaEvent_t> g_prof_ev;  // start/stop pairs
+size_t g_prof_used = 0;
+bool g_prof_on = false;
+}  // namespace
+
+extern "C" int bde_profile_begin(int max_launches) {
+  for (cudaEvent_t e : g_prof_ev) cudaEventDestroy(e);
+  g_prof_ev.clear();
+  g_prof_used = 0;
+  g_prof_on = false;
+  if (max_launches <= 0) return 0;
+  g_prof_ev.resize((size_t)max_launches * 2);
+  for (auto& e : g_prof_ev)
+    if (cudaEventCreate(&e) != cudaSuccess) {
+      set_error("bde_profile_begin: cudaEventCreate failed");
+      return -2;
+    }
+  g_prof_on = true;
+  return 0;
+}
+
+extern "C" int bde_profile_end(double* total_ms, int* n_launches) {
+  g_prof_on = false;
+  double tot = 0.0;
+  const size_t n = g_prof_used / 2;
+  for (size_t i = 0; i < n; ++i) {
+    float ms = 0.f;
+    cudaEventSynchronize(g_prof_ev[2 * i + 1]);
+    if (cudaEventElapsedTime(&ms, g_prof_ev[2 * i], g_prof_ev[2 * i + 1]) != cudaSuccess) {
+      set_error("bde_profile_end: cudaEventElapsedTime failed");
+      return -2;
+    }
+    tot += ms;
+  }
+  if (total_ms != nullptr) *total_ms = tot;
+  if (n_launches != nullptr) *n_launches = (int)n;
+  return 0;
+}
+
 extern "C" int bde_gemm(const bde_gemm_desc* d, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   BDE_REQUIRE(d != nullptr, "bde_gemm: null descriptor");
@@ -58,6 +102,15 @@ extern "C" int bde_gemm(const bde_gemm_desc* d, void* stream) {
     BDE_REQUIRE(d->epi == BDE_EPI_STORE, "bde_gemm: unknown epilogue %d", d->epi);
   }
   if (d->engine == BDE_ENGINE_SIMT) return gemm_simt(d, s);
-  if (d->engine == BDE_ENGINE_TCGEN05) return gemm_tcgen05(d, s);
+  if (d->engine == BDE_ENGINE_TCGEN05) {
+    const bool prof = g_prof_on && g_prof_used + 2 <= g_prof_ev.size();
+    if (prof) cudaEventRecord(g_prof_ev[g_prof_used], s);
+    const int rc = gemm_tcgen05(d, s);
+    if (prof) {
+      cudaEventRecord(g_prof_ev[g_prof_used + 1], s);
+      g_prof_used += 2;
+    }
+    return rc;
+  }
   BDE_REQUIRE(false, "bde_gemm: unknown engine %d", d->engine);
 }

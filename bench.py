@@ -299,33 +299,28 @@ def main():
     roofline = None
     voxel_roof = None
     if not args.no_kernel_timing:
-        # live per-kernel timing: one eager (non-graph) pass with CUDA events around every launch of the
-        # dominant kernel (the implicit-GEMM engine) on the launching stream
-        from bde2vid_b200 import engine as engmod
-        rec = []
-        orig = ops.gemm
-
-        def timed_gemm(*a, **k):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            r = orig(*a, **k)
-            e.record()
-            rec.append((s, e))
-            return r
-        engmod.ops.gemm = timed_gemm
-        try:
-            with torch.no_grad():
-                plan._enqueue(True)
-            torch.cuda.synchronize()
-        finally:
-            engmod.ops.gemm = orig
-        gemm_ms = sum(s.elapsed_time(e) for s, e in rec)
+        # live per-kernel timing of the dominant kernel (the tcgen05 implicit-GEMM engine): one eager
+        # (non-graph) pass of the same step with a CUDA event pair recorded in C right around every launch on
+        # the launching stream.  A spin kernel first puts the GPU ~150 ms behind the host so that launches
+        # queue up and the event pairs measure kernel time, not Python launch gaps.
+        import ctypes as C
+        from bde2vid_b200 import _lib
+        lib = _lib.load()
+        torch.cuda.synchronize()
+        lib.bde_profile_begin(200000)
+        torch.cuda._sleep(int(0.15 * 1.9e9))
+        with torch.no_grad():
+            plan._enqueue(True)
+        torch.cuda.synchronize()
+        tot, cnt = C.c_double(0.0), C.c_int(0)
+        lib.bde_profile_end(C.byref(tot), C.byref(cnt))
+        gemm_ms, n_rec = float(tot.value), int(cnt.value)
         flops = (GF_CONV + GF_LINEAR) * 1e9 * T * NB
         ach = flops / (gemm_ms * 1e-3) / 1e12
         peak = pk["tc_sustained"]
         roofline = {"kernel": "gemm_tc_kernel (tcgen05 implicit GEMM: all convs + linears)", "bound": "tensor",
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                    "launches": len(rec), "avg_launch_us": gemm_ms * 1e3 / max(1, len(rec)),
+                    "launches": n_rec, "avg_launch_us": gemm_ms * 1e3 / max(1, n_rec),
                     "kernel_ms_per_step": gemm_ms, "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
                     "flops_per_step": flops}
         # voxeliser alone, all T windows in one launch (HBM-bound)

@@ -133,6 +133,12 @@ typedef struct bde_gemm_desc {
 
 int bde_gemm(const bde_gemm_desc* desc, void* stream);
 
+/* Measurement hook: between bde_profile_begin(max) and bde_profile_end every tcgen05 bde_gemm launch is
+ * bracketed by a pair of CUDA events on its stream; bde_profile_end returns the summed kernel time (ms)
+ * and the number of launches.  Not for use under stream capture. */
+int bde_profile_begin(int max_launches);
+int bde_profile_end(double* total_ms, int* n_launches);
+
 /* --------------------------------------------------------------------------------------------
  * Element-wise / gather kernels around the GEMMs.
  */
