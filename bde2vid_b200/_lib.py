@@ -34,7 +34,7 @@ class GemmDesc(C.Structure):
         ("ln_frames", C.c_void_p * 8), ("ln_tok_map", C.c_void_p),
         ("epi", C.c_int), ("act", C.c_int), ("out_f32", C.c_int),
         ("out", C.c_void_p), ("residual", C.c_void_p), ("c_prev", C.c_void_p), ("c_out", C.c_void_p),
-        ("row_map", C.c_void_p), ("out2", C.c_void_p),
+        ("row_map", C.c_void_p), ("out2", C.c_void_p), ("res_mode", C.c_int),
     ]
 
 

@@ -22,7 +22,8 @@ struct GemmParams {
   int epi, act, out_f32;
   void* out;
   void* out2;
-  const float* residual;
+  const void* residual;
+  int res_mode;
   const float* c_prev;
   float* c_out;
   const int* row_map;
@@ -139,11 +140,16 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + b4[j];
     if (p.epi == BDE_EPI_STORE) {
+      size_t o = (size_t)m * p.N + nb;
+      if (p.res_mode == 1 && p.residual != nullptr) {
+        const T* r = reinterpret_cast<const T*>(p.residual) + o;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += to_f32(r[j]);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], p.act);
-      size_t o = (size_t)m * p.N + nb;
-      if (p.residual != nullptr) {
-        float4 r = *reinterpret_cast<const float4*>(p.residual + o);
+      if (p.res_mode == 0 && p.residual != nullptr) {
+        float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + o);
         v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
       }
       float4 ov = make_float4(v[0], v[1], v[2], v[3]);
@@ -190,7 +196,7 @@ int gemm_simt(const bde_gemm_desc* d, cudaStream_t s) {
   p.k_order = d->k_order;
   BDE_REQUIRE(p.k_order == 0 || (p.c0 % 64 == 0 && p.c1 % 64 == 0), "bde_gemm(simt): chunk-major K needs channels %% 64 == 0");
   p.epi = d->epi; p.act = d->act; p.out_f32 = d->out_f32;
-  p.out = d->out; p.out2 = d->out2; p.residual = d->residual; p.c_prev = d->c_prev; p.c_out = d->c_out;
+  p.out = d->out; p.out2 = d->out2; p.residual = d->residual; p.res_mode = d->res_mode; p.c_prev = d->c_prev; p.c_out = d->c_out;
   p.row_map = d->row_map;
   BDE_REQUIRE(p.c0 % 4 == 0 && p.c1 % 4 == 0 && p.N % 4 == 0, "bde_gemm(simt): channels and N must be multiples of 4");
   if (p.M == 0) return 0;

@@ -442,7 +442,7 @@ int fill_params(const bde_gemm_desc* d, TcParams& p, bool& ln) {
   p.w_ld = d->w_ld > 0 ? d->w_ld : p.K;
   p.num_kb = (p.K + BK - 1) / BK;
   p.epi = d->epi; p.act = d->act; p.out_f32 = d->out_f32;
-  p.out = d->out; p.out2 = d->out2; p.residual = d->residual; p.c_prev = d->c_prev; p.c_out = d->c_out;
+  p.out = d->out; p.out2 = d->out2; p.residual = d->residual; p.res_mode = d->res_mode; p.c_prev = d->c_prev; p.c_out = d->c_out;
   p.row_map = d->row_map;
   p.dbg = nullptr;
   ln = d->ln_mode != 0;

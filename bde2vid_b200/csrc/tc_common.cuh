@@ -33,7 +33,8 @@ struct TcParams {
   int epi, act, out_f32;
   void* out;
   void* out2;
-  const float* residual;
+  const void* residual;
+  int res_mode;
   const float* c_prev;
   float* c_out;
   const int* row_map;
@@ -255,6 +256,13 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
 __device__ __forceinline__ void epilogue_quad(const TcParams& p, int m, int nb, float4 acc, float4 b, int dst_row) {
   float v0 = acc.x + b.x, v1 = acc.y + b.y, v2 = acc.z + b.z, v3 = acc.w + b.w;
   if (p.epi == BDE_EPI_STORE) {
+    const size_t o = (size_t)m * p.N + nb;
+    if (p.res_mode == 1 && p.residual != nullptr) {  // pre-activation residual in the operand type (bf16)
+      const uint2 rr = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + o);
+      const float2 r0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr.x));
+      const float2 r1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr.y));
+      v0 += r0.x; v1 += r0.y; v2 += r1.x; v3 += r1.y;
+    }
     if (p.act == BDE_ACT_RELU) {
       v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
     } else if (p.act == BDE_ACT_RELU6) {
@@ -265,9 +273,8 @@ __device__ __forceinline__ void epilogue_quad(const TcParams& p, int m, int nb, 
     } else if (p.act != BDE_ACT_NONE) {
       v0 = apply_act(v0, p.act); v1 = apply_act(v1, p.act); v2 = apply_act(v2, p.act); v3 = apply_act(v3, p.act);
     }
-    const size_t o = (size_t)m * p.N + nb;
-    if (p.residual != nullptr) {
-      const float4 r = *reinterpret_cast<const float4*>(p.residual + o);
+    if (p.res_mode == 0 && p.residual != nullptr) {
+      const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + o);
       v0 += r.x; v1 += r.y; v2 += r.z; v3 += r.w;
     }
     if (p.out_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) = make_float4(v0, v1, v2, v3);

@@ -13,6 +13,8 @@ CUDA graph on its second use so that replay costs one launch from the host.
 Weights are repacked once per engine (K-major [Cout, kh*kw*Cin], gate-interleaved LSTM rows,
 query scale folded into q, relative-position bias pre-gathered).
 """
+import os
+
 import torch
 
 from . import ops
@@ -305,6 +307,9 @@ class _Plan:
         self.graphs = {}
         self.runs = {}
         self.ev = None
+        self.side = torch.cuda.Stream(device=dev)
+        # two-stream schedule (backward chain / decoders on `side`); False serialises everything on one stream
+        self.overlap = os.environ.get("BDE2VID_OVERLAP", "1") != "0"
 
     # ------------------------------------------------------------------------------------
     def set_events(self, seqs, H, W, pad_top, pad_left):
@@ -366,47 +371,71 @@ class _Plan:
         for l in range(eng.L):
             d, e = self.lv[l], eng.enc[l]
             h, w, C = d["h"], d["w"], d["C"]
-            # encoder convs are not recurrent: one launch per direction over all T (...V5.py:129-130, conv part)
-            eng._gemm(e["f_conv"], x, d["ef"], N, xh, xw, xc, act=ACT_RELU)
-            eng._gemm(e["b_conv"], x, d["eb"], N, xh, xw, xc, act=ACT_RELU)
-            self.launches += 2
-            # the two ConvLSTM chains (sequential in t; gates conv + pointwise fused in one kernel)
-            for k in range(T):
-                for (src, hbuf, cbuf, layer, t, tprev) in (
-                        (d["ef"], d["hf"], d["cf"], e["f_lstm"], k, k - 1),
-                        (d["eb"], d["hb"], d["cb"], e["b_lstm"], T - 1 - k, T - k)):
-                    first = k == 0
-                    eng._gemm(layer, src[t * B:(t + 1) * B], hbuf[t * B:(t + 1) * B], B, h, w, C,
-                              a1=d["zero"] if first else hbuf[tprev * B:(tprev + 1) * B], c1=C,
-                              epi=EPI_LSTM, c_prev=None if first else cbuf[(k + 1) & 1], c_out=cbuf[k & 1])
-                    self.launches += 1
+            # the two ConvLSTM chains (sequential in t; gates conv + pointwise fused in one kernel) are independent
+            # of each other: the backward direction (conv + chain) runs on a second stream
+            main = torch.cuda.current_stream()
+            side = self.side if self.overlap else main
+            side.wait_stream(main)
+            for (strm, conv, src, hbuf, cbuf, layer, rev) in (
+                    (main, e["f_conv"], d["ef"], d["hf"], d["cf"], e["f_lstm"], False),
+                    (side, e["b_conv"], d["eb"], d["hb"], d["cb"], e["b_lstm"], True)):
+                with torch.cuda.stream(strm):
+                    # encoder conv is not recurrent: one launch over all T (...V5.py:129-130, conv part)
+                    eng._gemm(conv, x, src, N, xh, xw, xc, act=ACT_RELU)
+                    for k in range(T):
+                        t, tprev = (T - 1 - k, T - k) if rev else (k, k - 1)
+                        first = k == 0
+                        eng._gemm(layer, src[t * B:(t + 1) * B], hbuf[t * B:(t + 1) * B], B, h, w, C,
+                                  a1=d["zero"] if first else hbuf[tprev * B:(tprev + 1) * B], c1=C,
+                                  epi=EPI_LSTM, c_prev=None if first else cbuf[(k + 1) & 1], c_out=cbuf[k & 1])
+                    self.launches += 1 + T
+            main.wait_stream(side)
             # merged = ff + fb (...V5.py:137-147)
             ops.add(d["hf"], d["hb"], out_f32=d["feat"], out_t=None if eng.dtype == torch.float32 else d["feat_t"],
                     dtype=eng.dtype)
             self.launches += 1
             if eng.depths[l] > 0:
-                self._attention_level(l)
+                # the last level's frames are final as soon as their attention step is done: the decoders of a
+                # finished chunk of frames run on the side stream while the (latency-bound) chain continues
+                self._attention_level(l, self._decode_chunk_async if l == eng.L - 1 else None)
             x, xc, xh, xw = d["feat_t"], C, h, w
-        # C: decoders + prediction, chunked over frames (...V5.py:183-197)
-        for t0 in range(0, T, self.Tc):
-            n = min(self.Tc, T - t0) * B
-            s = slice(t0 * B, t0 * B + n)
-            cur, cur_scale = None, 1.0
-            for i in range(eng.L):
-                dd = self.dec[i]
-                l_in = eng.L - 1 - i
-                feat = self.lv[l_in]["feat"][s]
-                if i == 0:    # quirk Q2: the last level is appended twice -> decoder 0 sees feat + feat
-                    ops.upsample2x_sum(None, feat, 2.0, n, dd["h"], dd["w"], dd["C"], dd["up"][:n])
-                else:
-                    ops.upsample2x_sum(feat, cur, 1.0, n, dd["h"], dd["w"], dd["C"], dd["up"][:n])
-                eng._gemm(eng.dec[i], dd["up"][:n], dd["out"][:n], n, 2 * dd["h"], 2 * dd["w"], dd["C"], act=ACT_RELU6)
-                cur = dd["out"][:n]
-                self.launches += 2
-            ops.pred_sigmoid(cur, self.head[s], eng.pred_w, eng.pred_b, eng.bc, n * Hp * Wp, self.img[s])
-            self.launches += 1
+        if self.overlap:
+            torch.cuda.current_stream().wait_stream(self.side)
 
-    def _attention_level(self, l):
+    def _decode_chunk_async(self, t):
+        """Called after frame t of the last level is final; launches the decoder of a completed chunk."""
+        T, Tc = self.T, self.Tc
+        if (t + 1) % Tc != 0 and t != T - 1:
+            return
+        t0 = (t // Tc) * Tc
+        if not self.overlap:
+            self._decode_chunk(t0)
+            return
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            self._decode_chunk(t0)
+
+    def _decode_chunk(self, t0):
+        """C: decoders + prediction for frames [t0, t0 + Tc) (...V5.py:183-197)."""
+        eng, T, B, Hp, Wp = self.eng, self.T, self.B, self.Hp, self.Wp
+        n = min(self.Tc, T - t0) * B
+        s = slice(t0 * B, t0 * B + n)
+        cur = None
+        for i in range(eng.L):
+            dd = self.dec[i]
+            l_in = eng.L - 1 - i
+            feat = self.lv[l_in]["feat"][s]
+            if i == 0:    # quirk Q2: the last level is appended twice -> decoder 0 sees feat + feat
+                ops.upsample2x_sum(None, feat, 2.0, n, dd["h"], dd["w"], dd["C"], dd["up"][:n])
+            else:
+                ops.upsample2x_sum(feat, cur, 1.0, n, dd["h"], dd["w"], dd["C"], dd["up"][:n])
+            eng._gemm(eng.dec[i], dd["up"][:n], dd["out"][:n], n, 2 * dd["h"], 2 * dd["w"], dd["C"], act=ACT_RELU6)
+            cur = dd["out"][:n]
+            self.launches += 2
+        ops.pred_sigmoid(cur, self.head[s], eng.pred_w, eng.pred_b, eng.bc, n * Hp * Wp, self.img[s])
+        self.launches += 1
+
+    def _attention_level(self, l, on_frame_done=None):
         """In-place sequential multi-frame window attention (...V5.py:151-169; DTransformer.py:254-389)."""
         eng, T, B = self.eng, self.T, self.B
         d = self.lv[l]
@@ -465,3 +494,5 @@ class _Plan:
             ops.add(xs, feat[t], out_f32=feat[t], out_t=None if eng.dtype == torch.float32 else feat_t[t],
                     dtype=eng.dtype)
             self.launches += 1
+            if on_frame_done is not None:
+                on_frame_done(t)

@@ -54,7 +54,8 @@ def pack_voxel_nhwc(vox, c_pad, dtype, out=None):
 
 def gemm(a0, w, bias, out, *, n_img, h_in, w_in, c0, n, ksize=1, stride=1, pad=0, a1=None, c1=0, w_ld=0,
          epi=EPI_STORE, act=ACT_NONE, out_f32=False, residual=None, c_prev=None, c_out=None, row_map=None,
-         out2=None, engine=ENGINE_SIMT, dtype=None, k_order=0, ln_frames=None, ln_tok_map=None, ln_n_tok=1):
+         out2=None, engine=ENGINE_SIMT, dtype=None, k_order=0, ln_frames=None, ln_tok_map=None, ln_n_tok=1,
+         res_mode=0):
     """Implicit-GEMM conv / linear (see bde_gemm in include/bde2vid.h).  Returns (h_out, w_out).
     ``ln_frames`` (list of float32 [*, c0] tensors or None) switches the A operand to the fused
     LayerNorm-gather form (``a0`` is then ignored and may be None)."""
@@ -76,7 +77,7 @@ def gemm(a0, w, bias, out, *, n_img, h_in, w_in, c0, n, ksize=1, stride=1, pad=0
     d.w, d.bias, d.n, d.w_ld, d.k_order = ptr(w), ptr(bias), n, w_ld, k_order
     d.epi, d.act, d.out_f32 = epi, act, int(out_f32)
     d.out, d.residual, d.c_prev, d.c_out = ptr(out), ptr(residual), ptr(c_prev), ptr(c_out)
-    d.row_map, d.out2 = ptr(row_map), ptr(out2)
+    d.row_map, d.out2, d.res_mode = ptr(row_map), ptr(out2), res_mode
     check(lib.bde_gemm(C.byref(d), stream_ptr()), "bde_gemm")
     return d.h_out, d.w_out
 

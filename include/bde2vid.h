@@ -124,11 +124,15 @@ typedef struct bde_gemm_desc {
   int act;               /* BDE_ACT_* (STORE only)                                               */
   int out_f32;           /* STORE: write float32 instead of `dtype`                              */
   void* out;             /* STORE: [M, n]; LSTM: h_out [M, hidden] (dtype); SCATTER: f32 [P, n]  */
-  const float* residual; /* STORE: optional float32 [M, n] added after the activation            */
+  const void* residual;  /* STORE: optional [M, n] residual, see res_mode                        */
   const float* c_prev;   /* LSTM: float32 [M, hidden] or NULL (= zeros)                          */
   float* c_out;          /* LSTM: float32 [M, hidden]                                            */
   const int* row_map;    /* SCATTER: int32 [M] destination row or -1                             */
   void* out2;            /* STORE+out_f32: optional second copy of the result in `dtype`         */
+  int res_mode;          /* STORE: 0 = `residual` is float32, added AFTER the activation (attention  */
+                         /* MLP, DTransformer.py:302-304); 1 = `residual` has element type `dtype`   */
+                         /* and is added BEFORE the activation (ResidualBlock,                        */
+                         /* model/e2vid/submodules.py:234-247: out = relu(conv2(..) + x))            */
 } bde_gemm_desc;
 
 int bde_gemm(const bde_gemm_desc* desc, void* stream);

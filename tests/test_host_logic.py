@@ -92,3 +92,15 @@ def test_synthetic_events_follow_loader_contract():
     xs, ys, ts, ps = synth.to_loader_format(ev, 1)
     assert xs.dtype.name == "float32" and ts[0] == 0.0 and set(ps.tolist()) <= {-1.0, 1.0}
     assert (ts[1:] >= ts[:-1]).all() and xs.max() < 30 and ys.max() < 20
+
+
+def test_e2vid_state_dict_keys_match_reference(manifest):
+    """Strict load of a reference-layout E2VIDRecurrent checkpoint (keys recorded from the reference's own
+    state_dict by oracle/make_golden.py)."""
+    from bde2vid_b200.e2vid import E2VIDRecurrent
+    rec = manifest["e2vid_64x96_B2_T3"]
+    m = E2VIDRecurrent({"num_bins": 5})
+    sd = m.state_dict()
+    assert list(sd.keys()) == rec["keys"]
+    assert [list(v.shape) for v in sd.values()] == rec["shapes"]
+    assert m.num_encoders == 4
