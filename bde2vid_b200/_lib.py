@@ -64,6 +64,9 @@ EXPORTS = {
     "bde_window_attention_mma_bias_stride": (C.c_int, [C.c_int]),
     "bde_window_attention_mma": (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_void_p, C.c_void_p]),
     "bde_window_attention_mma_qkv": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]),
+    "bde_window_attention_fused_supported": (C.c_int, [C.c_int] * 4),
+    "bde_window_attention_fused": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+                                   + [C.c_void_p] * 8),
     "bde_cast": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
 }
 

@@ -1,0 +1,528 @@
+// Fused multi-frame window attention for one SwinTransformerBlock3D attention half
+// (model/BDE2VID/DTransformer.py:254-299, WindowAttention3D :164-207):
+//
+//   window gather (plain or dilated, via a token map) -> LayerNorm (norm_q / norm_kv, affine folded
+//   into the projections) -> q, k, v projections -> softmax(q k^T + relative-position bias) v
+//   -> [C == 64: output projection + window_reverse + crop + shortcut, scatter-added into x]
+//      [C == 256: bf16 attention output, the projection runs as a tcgen05 GEMM with a scatter epilogue]
+//
+// One CTA = one window x one group of 64 projection columns (= 64 / head_dim heads), so q, k and v never
+// leave shared memory: the unfused path wrote a [tokens, 3C] bf16 buffer to HBM and read it back.
+// The GEMMs here are small (<= 160 x 64 x C per CTA) and the softmax needs the scores in registers,
+// so the kernel uses warp-level mma.sync (bf16, fp32 accumulate) fed by ldmatrix from padded smem rows.
+// The relative-position bias is rebuilt from the compact per-head table (D x 13 x 13 entries) instead
+// of the expanded [heads, 49, D*49] tensor, which would not fit in shared memory next to the operands.
+#include "common.cuh"
+
+namespace bde {
+namespace {
+
+constexpr int kTok = 49;       // 7 x 7 window
+constexpr int kRel = 169;      // 13 x 13 relative offsets per frame pair
+constexpr int kThreadsF = 256;
+
+struct FusedAttnParams {
+  const float* frames[8];        // D fp32 [P, C] frame maps (query slot = the running x), NULL = all-zero frame
+  const int* tok_map;            // int32 [n_win * 49]: source / destination pixel row or -1
+  const __nv_bfloat16* wqkv;     // [3C, C] rows q | k | v, LayerNorm gamma and the q scale folded in
+  const float* bqkv;             // [3C]
+  const float* tbl;              // [heads, D * 169] bias table rows of the query slot
+  const __nv_bfloat16* wproj;    // [C, C]   (C == 64)
+  const float* bproj;            // [C]      (C == 64)
+  float* xs;                     // fp32 [P, C] += proj(attn)      (C == 64)
+  __nv_bfloat16* o_out;          // bf16 [n_win * 49, C]           (C == 256)
+  int n_win, D, q_slot, heads;
+};
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void cpa16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cpa_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int C, int HD, int NT>
+struct FusedCfg {
+  static constexpr int HG = 64 / HD;              // heads per CTA
+  static constexpr int PX = C + 8;                // pitch (bf16 elements) of the LayerNorm'ed tokens and weight slices
+  static constexpr int PQ = 72;                   // pitch of q / k / v / o tiles
+  static constexpr int KSTEPS = (NT + 1) / 2;     // k16 steps of P.V
+  static constexpr int XROWS = KSTEPS * 16;       // token rows staged (zero beyond n_kv)
+  static constexpr int NKEY = NT * 8;
+  static constexpr int DMAX = NT <= 7 ? 1 : (NT <= 13 ? 2 : 3);
+  static constexpr int NW = C == 64 ? 3 : 2;      // weight-slice buffers
+  static constexpr int XN_BYTES = XROWS * PX * 2;
+  static constexpr int W_BYTES = NW * 64 * PX * 2;
+  static constexpr int TBL_BYTES = HG * DMAX * kRel * 4;
+  static constexpr int OS_BYTES = 64 * PQ * 2;
+  static constexpr int WP_BYTES = C == 64 ? 64 * PX * 2 : 0;
+  // C == 64: the bias table, the attention-output tile and the projection weights reuse the token / weight
+  // region once the q, k, v projections are done (keeps the CTA under half an SM's shared memory)
+  static constexpr int A_BYTES = C == 64 ? (XN_BYTES + W_BYTES > TBL_BYTES + OS_BYTES + WP_BYTES ? XN_BYTES + W_BYTES
+                                                                                                  : TBL_BYTES + OS_BYTES + WP_BYTES)
+                                         : XN_BYTES + W_BYTES + TBL_BYTES;
+  static constexpr int OFF_XN = 0;
+  static constexpr int OFF_W = XN_BYTES;
+  static constexpr int OFF_TBL = C == 64 ? 0 : XN_BYTES + W_BYTES;
+  static constexpr int OFF_OS = TBL_BYTES;               // C == 64 only
+  static constexpr int OFF_WP = TBL_BYTES + OS_BYTES;    // C == 64 only
+  static constexpr int OFF_Q = A_BYTES;
+  static constexpr int OFF_K = OFF_Q + 64 * PQ * 2;
+  static constexpr int OFF_V = OFF_K + NKEY * PQ * 2;
+  static constexpr int OFF_COFF = OFF_V + XROWS * PQ * 2;   // int16 [NKEY]
+  static constexpr int OFF_ROFF = OFF_COFF + ((NKEY * 2 + 15) / 16) * 16;  // int16 [64]
+  static constexpr int OFF_PIX = OFF_ROFF + 128;            // int32 [64]
+  static constexpr int SMEM = OFF_PIX + 256;
+};
+
+// acc[mt][nt][4] += A[rows, C] (smem, pitch PX) * Wslice[64, C]^T (smem, pitch PX) for this warp's
+// (m-tile list, n-tile pair).  a_row(mt, r) gives the smem row of tile row r.
+template <int C, int PX, int MT, typename RowFn>
+__device__ __forceinline__ void warp_gemm(float (&acc)[MT][2][4], int n_mt, uint32_t a_base, RowFn a_row, uint32_t w_base,
+                                          int npair, int lane) {
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int n = 0; n < 2; ++n) acc[i][n][0] = acc[i][n][1] = acc[i][n][2] = acc[i][n][3] = 0.f;
+  // B: matrices (n 0-7, k 0-7) (n 0-7, k 8-15) (n 8-15, k 0-7) (n 8-15, k 8-15)
+  const int bm = lane >> 3;
+  const uint32_t b_addr0 = w_base + (uint32_t)(((npair * 16 + (bm >> 1) * 8 + (lane & 7)) * PX + (bm & 1) * 8) * 2);
+#pragma unroll 4
+  for (int kk = 0; kk < C / 16; ++kk) {
+    uint32_t b[4];
+    ldsm_x4(b, b_addr0 + (uint32_t)(kk * 32));
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      if (i < n_mt) {
+        uint32_t a[4];
+        ldsm_x4(a, a_base + (uint32_t)((a_row(i, lane & 15) * PX + kk * 16 + (lane >> 4) * 8) * 2));
+        mma16816(acc[i][0], a, b[0], b[1]);
+        mma16816(acc[i][1], a, b[2], b[3]);
+      }
+    }
+  }
+}
+
+template <int C, int HD, int NT>
+__global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(const FusedAttnParams p) {
+  using Cfg = FusedCfg<C, HD, NT>;
+  constexpr int PX = Cfg::PX, PQ = Cfg::PQ, HG = Cfg::HG, KSTEPS = Cfg::KSTEPS, XROWS = Cfg::XROWS, NKEY = Cfg::NKEY;
+  constexpr int NW = Cfg::NW;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
+  __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_XN);
+  float* tbl_s = reinterpret_cast<float*>(smem + Cfg::OFF_TBL);
+  __nv_bfloat16* qs = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_Q);
+  __nv_bfloat16* ks = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_K);
+  __nv_bfloat16* vs = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_V);
+  short* coff = reinterpret_cast<short*>(smem + Cfg::OFF_COFF);
+  short* roff = reinterpret_cast<short*>(smem + Cfg::OFF_ROFF);
+  int* pix_s = reinterpret_cast<int*>(smem + Cfg::OFF_PIX);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  constexpr int NHG = C / 64;
+  const int w = blockIdx.x / NHG, hg = blockIdx.x - w * NHG;
+  const int n_kv = p.D * kTok;
+  const int tbl_ld = p.D * kRel;
+
+  // ---- weight slices (q, k, v rows of this head group) -> smem, asynchronously ----------------------
+  auto load_w_slice = [&](int which, int buf) {  // which: 0 = q, 1 = k, 2 = v
+    const __nv_bfloat16* src = p.wqkv + (size_t)(which * C + hg * 64) * C;
+    const uint32_t dst = sb + Cfg::OFF_W + (uint32_t)(buf * 64 * PX * 2);
+    for (int i = tid; i < 64 * (C / 8); i += kThreadsF) {
+      const int r = i / (C / 8), ch = i - r * (C / 8);
+      cpa16(dst + (uint32_t)((r * PX + ch * 8) * 2), src + (size_t)r * C + ch * 8);
+    }
+    cpa_commit();
+  };
+#pragma unroll
+  for (int i = 0; i < NW; ++i) load_w_slice(i, i);
+
+  // ---- index tables -----------------------------------------------------------------------------------
+  for (int n = tid; n < NKEY; n += kThreadsF) {
+    int v = -1;
+    if (n < n_kv) {
+      const int d = n / kTok, r = n - d * kTok, a = r / 7, b = r - a * 7;
+      v = d * kRel + (6 - a) * 13 + (6 - b);
+    }
+    coff[n] = (short)v;
+  }
+  if (tid < 64) {
+    const int a = tid / 7, b = tid - a * 7;
+    roff[tid] = (short)(tid < kTok ? a * 13 + b : 0);
+    pix_s[tid] = tid < kTok ? __ldg(p.tok_map + (size_t)w * kTok + tid) : -1;
+  }
+  __syncthreads();
+
+  // ---- gather + LayerNorm: 8 lanes per token, 4 tokens per warp pass ----------------------------------
+  {
+    constexpr int NCH = C / 64;
+    const int j = lane & 7, sub = lane >> 3;
+    for (int n0 = warp * 4; n0 < XROWS; n0 += 32) {
+      const int n = n0 + sub;
+      const float* src = nullptr;
+      if (n < n_kv) {
+        const int d = n / kTok, tok = n - d * kTok;
+        const int pix = pix_s[tok];
+        const float* fr = p.frames[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) fr = (d == q) ? p.frames[q] : fr;
+        if (fr != nullptr && pix >= 0) src = fr + (size_t)pix * C + j * 8;
+      }
+      float v[NCH][8];
+      float sum = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < NCH; ++kb) {
+        if (src != nullptr) {
+          const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + kb * 64));
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + kb * 64 + 4));
+          v[kb][0] = t0.x; v[kb][1] = t0.y; v[kb][2] = t0.z; v[kb][3] = t0.w;
+          v[kb][4] = t1.x; v[kb][5] = t1.y; v[kb][6] = t1.z; v[kb][7] = t1.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[kb][e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += v[kb][e];
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      const float mean = sum / (float)C;
+      float sq = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < NCH; ++kb)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dlt = v[kb][e] - mean;
+          v[kb][e] = dlt;
+          sq += dlt * dlt;
+        }
+      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+      const float rstd = 1.0f / sqrtf(sq / (float)C + 1e-5f);
+#pragma unroll
+      for (int kb = 0; kb < NCH; ++kb) {
+        uint4 pk;
+        pk.x = pack2(v[kb][0] * rstd, v[kb][1] * rstd);
+        pk.y = pack2(v[kb][2] * rstd, v[kb][3] * rstd);
+        pk.z = pack2(v[kb][4] * rstd, v[kb][5] * rstd);
+        pk.w = pack2(v[kb][6] * rstd, v[kb][7] * rstd);
+        *reinterpret_cast<uint4*>(xn + (size_t)n * PX + kb * 64 + j * 8) = pk;
+      }
+    }
+  }
+
+  // ---- q, k, v projections (mma.sync): warp = (n-tile pair, m half) --------------------------------------
+  const int npair = warp & 3, mh = warp >> 2;
+  const uint32_t xn_u32 = sb + Cfg::OFF_XN;
+  constexpr int MTK = (KSTEPS + 1) / 2;  // k / v m-tiles per warp
+  for (int which = 0; which < 3; ++which) {
+    // slices were committed in order: wait until slice `which` has landed
+    if (which == 0) {
+      if (NW == 3) cpa_wait<2>(); else cpa_wait<1>();
+    } else if (which == 1) {
+      if (NW == 3) cpa_wait<1>(); else cpa_wait<1>();
+    } else {
+      cpa_wait<0>();
+    }
+    __syncthreads();  // slice + (first pass) the LayerNorm'ed tokens visible to every warp
+    const uint32_t w_base = sb + Cfg::OFF_W + (uint32_t)((which % NW) * 64 * PX * 2);
+    const float* bsrc = p.bqkv + which * C + hg * 64 + npair * 16 + 2 * t;
+    const float2 bia0 = __ldg(reinterpret_cast<const float2*>(bsrc));
+    const float2 bia1 = __ldg(reinterpret_cast<const float2*>(bsrc + 8));
+    if (which == 0) {
+      // q: the 49 tokens of the query slot (4 m-tiles, 2 per warp); rows past the staged block are clamped
+      float acc[2][2][4];
+      const int qrow0 = p.q_slot * kTok;
+      warp_gemm<C, PX, 2>(acc, 2, xn_u32, [&](int i, int r) { return min(qrow0 + (mh * 2 + i) * 16 + r, XROWS - 1); }, w_base,
+                          npair, lane);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r0 = (mh * 2 + i) * 16 + g;
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          const float2 bb = n == 0 ? bia0 : bia1;
+          const int col = npair * 16 + n * 8 + 2 * t;
+          *reinterpret_cast<uint32_t*>(qs + r0 * PQ + col) = pack2(acc[i][n][0] + bb.x, acc[i][n][1] + bb.y);
+          *reinterpret_cast<uint32_t*>(qs + (r0 + 8) * PQ + col) = pack2(acc[i][n][2] + bb.x, acc[i][n][3] + bb.y);
+        }
+      }
+    } else {
+      float acc[MTK][2][4];
+      const int mt0 = mh * MTK;
+      const int n_mt = min(MTK, KSTEPS - mt0);
+      warp_gemm<C, PX, MTK>(acc, n_mt, xn_u32, [&](int i, int r) { return (mt0 + i) * 16 + r; }, w_base, npair, lane);
+      __nv_bfloat16* dstm = which == 1 ? ks : vs;
+      const int row_lim = which == 1 ? NKEY : XROWS;
+#pragma unroll
+      for (int i = 0; i < MTK; ++i) {
+        if (i < n_mt) {
+          const int r0 = (mt0 + i) * 16 + g;
+#pragma unroll
+          for (int n = 0; n < 2; ++n) {
+            const float2 bb = n == 0 ? bia0 : bia1;
+            const int col = npair * 16 + n * 8 + 2 * t;
+            if (r0 < row_lim) *reinterpret_cast<uint32_t*>(dstm + r0 * PQ + col) = pack2(acc[i][n][0] + bb.x, acc[i][n][1] + bb.y);
+            if (r0 + 8 < row_lim)
+              *reinterpret_cast<uint32_t*>(dstm + (r0 + 8) * PQ + col) = pack2(acc[i][n][2] + bb.x, acc[i][n][3] + bb.y);
+          }
+        }
+      }
+    }
+    if (which + NW < 3) {
+      __syncthreads();  // every warp is done reading buffer which % NW
+      load_w_slice(which + NW, which % NW);
+    }
+  }
+  __syncthreads();  // q, k, v complete; the token / weight region is free
+
+  // ---- bias table (+ projection weights) -> smem ------------------------------------------------------------
+  {
+    const float* src = p.tbl + (size_t)hg * HG * tbl_ld;
+    const int n16 = HG * tbl_ld / 4;  // 16-byte chunks (HG * D * 169 floats; multiple of 4 because HG is)
+    for (int i = tid; i < n16; i += kThreadsF) cpa16(sb + Cfg::OFF_TBL + (uint32_t)(i * 16), src + i * 4);
+    if (C == 64) {
+      for (int i = tid; i < 64 * (C / 8); i += kThreadsF) {
+        const int r = i / (C / 8), ch = i - r * (C / 8);
+        cpa16(sb + Cfg::OFF_WP + (uint32_t)((r * PX + ch * 8) * 2), p.wproj + (size_t)r * C + ch * 8);
+      }
+    }
+    cpa_commit();
+    cpa_wait<0>();
+    __syncthreads();
+  }
+
+  // ---- attention: unit = (head of the group, 16-row query tile); scores stay in registers ----------------------
+  const uint32_t vs_u32 = sb + Cfg::OFF_V;
+  __nv_bfloat16* os = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_OS);  // C == 64 only
+  for (int unit = warp; unit < HG * 4; unit += kThreadsF / 32) {
+    const int hl = unit >> 2, mt = unit & 3;
+    const int row0 = mt * 16 + g, row1 = row0 + 8;
+    const float* tb = tbl_s + hl * tbl_ld;
+    const int r0o = roff[row0], r1o = roff[row1];
+    uint32_t qa[4] = {0u, 0u, 0u, 0u};
+    {
+      const __nv_bfloat16* q0 = qs + row0 * PQ + hl * HD;
+      const __nv_bfloat16* q1 = qs + row1 * PQ + hl * HD;
+      if (2 * t < HD) {
+        qa[0] = *reinterpret_cast<const uint32_t*>(q0 + 2 * t);
+        qa[1] = *reinterpret_cast<const uint32_t*>(q1 + 2 * t);
+      }
+      if (2 * t + 8 < HD) {
+        qa[2] = *reinterpret_cast<const uint32_t*>(q0 + 2 * t + 8);
+        qa[3] = *reinterpret_cast<const uint32_t*>(q1 + 2 * t + 8);
+      }
+    }
+    float s[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const uint32_t cp = *reinterpret_cast<const uint32_t*>(coff + j * 8 + 2 * t);
+      const int c0 = (int)(short)(cp & 0xffffu), c1 = (int)(short)(cp >> 16);
+      if (j == NT - 1) {  // only the last key tile can hold padding keys
+        s[j][0] = c0 >= 0 ? tb[r0o + c0] : -1e30f;
+        s[j][1] = c1 >= 0 ? tb[r0o + c1] : -1e30f;
+        s[j][2] = c0 >= 0 ? tb[r1o + c0] : -1e30f;
+        s[j][3] = c1 >= 0 ? tb[r1o + c1] : -1e30f;
+      } else {
+        s[j][0] = tb[r0o + c0]; s[j][1] = tb[r0o + c1];
+        s[j][2] = tb[r1o + c0]; s[j][3] = tb[r1o + c1];
+      }
+      const __nv_bfloat16* kr = ks + (j * 8 + g) * PQ + hl * HD;
+      uint32_t kb0 = 0u, kb1 = 0u;
+      if (2 * t < HD) kb0 = *reinterpret_cast<const uint32_t*>(kr + 2 * t);
+      if (2 * t + 8 < HD) kb1 = *reinterpret_cast<const uint32_t*>(kr + 2 * t + 8);
+      mma16816(s[j], qa, kb0, kb1);
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float m0s = mx0 * kLog2e, m1s = mx1 * kLog2e;
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      s[j][0] = ex2(fmaf(s[j][0], kLog2e, -m0s));
+      s[j][1] = ex2(fmaf(s[j][1], kLog2e, -m0s));
+      s[j][2] = ex2(fmaf(s[j][2], kLog2e, -m1s));
+      s[j][3] = ex2(fmaf(s[j][3], kLog2e, -m1s));
+      l0 += s[j][0] + s[j][1];
+      l1 += s[j][2] + s[j][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+
+    // O = P V: HD >= 8: channel tile v covers channels hl*HD + 8v..; HD == 4: one 8-wide tile shared by a head pair
+    constexpr int NV = (HD + 7) / 8;
+    float o[NV][4];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) o[v][0] = o[v][1] = o[v][2] = o[v][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KSTEPS; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack2(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
+      if (2 * kk + 1 < NT) {
+        pa[2] = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+        pa[3] = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      } else {
+        pa[2] = 0u;
+        pa[3] = 0u;
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int ch0 = (HD >= 8) ? hl * HD + 8 * v : (hl >> 1) * 8;
+        uint32_t vb0, vb1;
+        ldsm_x2_trans(vb0, vb1, vs_u32 + (uint32_t)(((kk * 16 + (lane & 15)) * PQ + ch0) * 2));
+        mma16816(o[v], pa, vb0, vb1);
+      }
+    }
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int col = hl * HD + 8 * v + 2 * t;
+      bool mine = true;
+      if (HD == 4) {
+        mine = (t >> 1) == (hl & 1);
+        col = (hl >> 1) * 8 + 2 * t;
+      }
+      if (mine) {
+        const uint32_t v0 = pack2(o[v][0] * inv0, o[v][1] * inv0), v1 = pack2(o[v][2] * inv1, o[v][3] * inv1);
+        if (C == 64) {
+          *reinterpret_cast<uint32_t*>(os + row0 * PQ + col) = v0;
+          *reinterpret_cast<uint32_t*>(os + row1 * PQ + col) = v1;
+        } else {
+          __nv_bfloat16* og = p.o_out + (size_t)w * kTok * C + hg * 64 + col;
+          if (row0 < kTok) *reinterpret_cast<uint32_t*>(og + (size_t)row0 * C) = v0;
+          if (row1 < kTok) *reinterpret_cast<uint32_t*>(og + (size_t)row1 * C) = v1;
+        }
+      }
+    }
+  }
+
+  if (C == 64) {
+    // ---- output projection + window_reverse + shortcut: x[pix] += proj(o) + b (DTransformer.py:204,294-299) ----
+    __syncthreads();
+    float acc[2][2][4];
+    warp_gemm<C, PQ, 2>(acc, 2, sb + Cfg::OFF_OS, [&](int i, int r) { return (mh * 2 + i) * 16 + r; }, sb + Cfg::OFF_WP, npair, lane);
+    // note: os has pitch PQ == PX for C == 64, so the same routine serves both operands
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const int r = (mh * 2 + i) * 16 + g + hrow * 8;
+        const int pix = r < kTok ? pix_s[r] : -1;
+        if (pix >= 0) {
+#pragma unroll
+          for (int n = 0; n < 2; ++n) {
+            const int col = npair * 16 + n * 8 + 2 * t;
+            const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bproj + col));
+            float2* dst = reinterpret_cast<float2*>(p.xs + (size_t)pix * C + col);
+            float2 cur = *dst;
+            cur.x += acc[i][n][hrow * 2 + 0] + bb.x;
+            cur.y += acc[i][n][hrow * 2 + 1] + bb.y;
+            *dst = cur;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int C, int HD, int NT>
+int launch_fused(const FusedAttnParams& p, cudaStream_t s) {
+  using Cfg = FusedCfg<C, HD, NT>;
+  static_assert(C != 64 || Cfg::PQ == Cfg::PX, "C == 64 shares one pitch between token and q/k/v tiles");
+  auto kern = attn_fused_kernel<C, HD, NT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    BDE_REQUIRE(e == cudaSuccess, "bde_window_attention_fused: smem attribute (%d bytes): %s", Cfg::SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<p.n_win * (C / 64), kThreadsF, Cfg::SMEM, s>>>(p);
+  return check_launch("attn_fused_kernel");
+}
+
+}  // namespace
+}  // namespace bde
+
+using namespace bde;
+
+extern "C" int bde_window_attention_fused_supported(int c, int heads, int n_tok, int D) {
+  if (n_tok != kTok || D < 1 || D > 3 || heads <= 0 || c % heads != 0) return 0;
+  const int hd = c / heads;
+  return ((c == 64 && hd == 4) || (c == 256 && hd == 16)) ? 1 : 0;
+}
+
+extern "C" int bde_window_attention_fused(const float* const* frames_host, int D, int q_slot, const int* tok_map, int n_win,
+                                          int c, int heads, const void* wqkv, const float* bqkv, const float* bias_tbl,
+                                          const void* wproj, const float* bproj, float* xs, void* o_out, void* stream) {
+  if (n_win == 0) return 0;
+  BDE_REQUIRE(bde_window_attention_fused_supported(c, heads, kTok, D) == 1,
+              "bde_window_attention_fused: unsupported shape (c=%d heads=%d D=%d)", c, heads, D);
+  BDE_REQUIRE(q_slot >= 0 && q_slot < D && frames_host != nullptr && tok_map != nullptr && wqkv != nullptr && bqkv != nullptr &&
+                  bias_tbl != nullptr,
+              "bde_window_attention_fused: bad arguments");
+  BDE_REQUIRE(c == 64 ? (wproj != nullptr && bproj != nullptr && xs != nullptr) : o_out != nullptr,
+              "bde_window_attention_fused: missing output operands");
+  BDE_REQUIRE((((uintptr_t)wqkv) & 15) == 0 && (((uintptr_t)bias_tbl) & 15) == 0 && (((uintptr_t)wproj) & 15) == 0,
+              "bde_window_attention_fused: operands must be 16-byte aligned");
+  FusedAttnParams p;
+  for (int i = 0; i < 8; ++i) p.frames[i] = i < D ? frames_host[i] : nullptr;
+  p.tok_map = tok_map;
+  p.wqkv = (const __nv_bfloat16*)wqkv;
+  p.bqkv = bqkv;
+  p.tbl = bias_tbl;
+  p.wproj = (const __nv_bfloat16*)wproj;
+  p.bproj = bproj;
+  p.xs = xs;
+  p.o_out = (__nv_bfloat16*)o_out;
+  p.n_win = n_win; p.D = D; p.q_slot = q_slot; p.heads = heads;
+  cudaStream_t s = (cudaStream_t)stream;
+#define BDE_FUSED(C_, HD_)                                       \
+  switch (D) {                                                   \
+    case 1: return launch_fused<C_, HD_, 7>(p, s);               \
+    case 2: return launch_fused<C_, HD_, 13>(p, s);              \
+    default: return launch_fused<C_, HD_, 19>(p, s);             \
+  }
+  if (c == 64) { BDE_FUSED(64, 4) }
+  BDE_FUSED(256, 16)
+#undef BDE_FUSED
+}

@@ -18,6 +18,7 @@ import os
 import torch
 
 from . import ops
+from .synth import relative_position_index
 from .ops import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_RELU6, ENGINE_SIMT, ENGINE_TCGEN05, EPI_LSTM, EPI_SCATTER,
                   EPI_STORE)
 
@@ -115,6 +116,7 @@ class Engine:
         self.heads = cfg["num_heads"]
         self.ws = cfg["window_size"]
         self.depths = cfg["depths"]
+        self.fuse_attn = os.environ.get("BDE2VID_FUSED_ATTN", "1") != "0"
         if self.bins > VOX_CPAD:
             raise NotImplementedError("num_bins > %d" % VOX_CPAD)
         dt = self.dtype
@@ -185,8 +187,19 @@ class Engine:
                             g2, bt2 = blk.norm2.weight.detach().float(), blk.norm2.bias.detach().float()
                             w, ld = _pack_linear(W1 * g2[None, :], dt)
                             fc1_l = _Layer(w, ld, (W1 @ bt2 + b1).contiguous(), 4 * C)
+                        # fully fused attention half (gather + LN + q/k/v + attention [+ proj + scatter]): needs the
+                        # analytic relative-position index so that the bias can be rebuilt from the compact table
+                        tbl = None
+                        if (fused and self.fuse_attn and ops.window_attention_fused_supported(C, self.heads, n_tok, self.D)
+                                and tuple(self.ws) == (7, 7)
+                                and torch.equal(a.relative_position_index.cpu(),
+                                                relative_position_index(self.D, 7, 7))):
+                            rel = 13 * 13
+                            tab = a.relative_position_bias_table.detach().float()
+                            rows = [tab[((self.q_ind - d) + self.D - 1) * rel:((self.q_ind - d) + self.D) * rel] for d in range(self.D)]
+                            tbl = torch.stack(rows, 0).permute(2, 0, 1).contiguous()       # [heads, D, 169]
                         blocks.append(dict(
-                            qkv=qkv_l, fc1_ln=fc1_l,
+                            qkv=qkv_l, fc1_ln=fc1_l, tbl=tbl,
                             bias_mma=ops.pad_bias_for_mma(bias_hmn, self.D * n_tok) if use_mma else None,
                             nq_g=f32(a.norm_q.weight), nq_b=f32(a.norm_q.bias),
                             nkv_g=f32(a.norm_kv.weight), nkv_b=f32(a.norm_kv.bias),
@@ -458,6 +471,20 @@ class _Plan:
                 tm = d["tm"][i & 1]
                 fr = list(frames)
                 fr[eng.q_ind] = xs
+                if blk["tbl"] is not None:
+                    # one kernel for the attention half; C == 64 also projects and scatters into xs
+                    if C == 64:
+                        ops.window_attention_fused(fr, eng.q_ind, tm.view(-1), nwin, C, eng.heads, blk["qkv"].w,
+                                                   blk["qkv"].bias, blk["tbl"], blk["proj"].w, blk["proj"].bias, xs=xs)
+                        self.launches += 3
+                    else:
+                        ops.window_attention_fused(fr, eng.q_ind, tm.view(-1), nwin, C, eng.heads, blk["qkv"].w,
+                                                   blk["qkv"].bias, blk["tbl"], o_out=d["ob"])
+                        eng._gemm(blk["proj"], d["ob"], xs, 1, nwin * ntok, 1, C, epi=EPI_SCATTER, row_map=tm.view(-1))
+                        self.launches += 4
+                    eng._gemm(blk["fc1_ln"], None, d["hid"], 1, P, 1, C, act=ACT_GELU, ln_frames=[xs])
+                    eng._gemm(blk["fc2"], d["hid"], xs, 1, P, 1, 4 * C, out_f32=True, residual=xs)
+                    continue
                 if blk["qkv"] is not None:
                     # fused: [window gather + LayerNorm + q/k/v projection] -> attention -> proj+scatter ->
                     #        [LayerNorm + fc1 + GELU] -> fc2 + residual          (5 launches per block)

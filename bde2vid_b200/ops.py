@@ -170,6 +170,21 @@ def window_attention_mma_qkv(qkv, bias_padded, n_win, n_q, n_kv, q_row0, c, head
     return out
 
 
+def window_attention_fused_supported(c, heads, n_tok, D):
+    return _lib.load().bde_window_attention_fused_supported(c, heads, n_tok, D) == 1
+
+
+def window_attention_fused(frames, q_slot, tok_map, n_win, c, heads, wqkv, bqkv, bias_tbl, wproj=None, bproj=None,
+                           xs=None, o_out=None):
+    """Fused gather + LayerNorm + q/k/v + window attention (+ proj + scatter for c == 64); see include/bde2vid.h."""
+    lib = _lib.require_device()
+    D = len(frames)
+    arr = (C.c_void_p * D)(*[None if f is None else f.data_ptr() for f in frames])
+    check(lib.bde_window_attention_fused(arr, D, q_slot, ptr(tok_map), n_win, c, heads, ptr(wqkv), ptr(bqkv), ptr(bias_tbl),
+                                         ptr(wproj), ptr(bproj), ptr(xs), ptr(o_out), stream_ptr()),
+          "bde_window_attention_fused")
+
+
 def cast(src, dst):
     lib = _lib.require_device()
     check(lib.bde_cast(ptr(src), BDE_DTYPE[src.dtype], ptr(dst), BDE_DTYPE[dst.dtype], src.numel(), stream_ptr()),

@@ -209,6 +209,27 @@ int bde_window_attention_mma(const void* q, const void* kv, const float* bias_pa
 int bde_window_attention_mma_qkv(const void* qkv, const float* bias_padded, int n_win, int n_q, int n_kv,
                                  int q_row0, int c, int heads, void* out, void* stream);
 
+/* Fused attention half of one SwinTransformerBlock3D (DTransformer.py:254-299): window gather through
+ * tok_map (plain or dilated windows, -1 = zero-padding token) + norm_q / norm_kv + q / kv Linear +
+ * softmax(q k^T + relative-position bias) v, all inside one kernel (q, k, v stay in shared memory).
+ *   frames_host : HOST array of D device pointers, float32 [P, c] per buffered frame (NULL = all-zero
+ *                 frame, ...V5.py:160-161); frames_host[q_slot] is the running x of the block
+ *   tok_map     : int32 [n_win * 49]
+ *   wqkv, bqkv  : bf16 [3c, c] / float32 [3c]: rows q | k | v with the LayerNorm affine and the q scale
+ *                 folded in (W diag(gamma), W beta + b), as for bde_gemm's ln_mode
+ *   bias_tbl    : float32 [heads, D, 169]: bias_tbl[h, d, (aq-ak+6)*13 + (bq-bk+6)] =
+ *                 relative_position_bias_table[((q_slot - d) + D - 1)*169 + ..., h]  (DTransformer.py:139-152,195-199)
+ *   c == 64 : wproj bf16 [c, c], bproj float32 [c]; xs float32 [P, c] (= frames_host[q_slot]) receives
+ *             xs[pix] += proj(attn)[token] + bproj for every covered pixel (window_reverse + crop + shortcut)
+ *   c == 256: o_out bf16 [n_win * 49, c] receives the attention output (heads concatenated); the caller
+ *             runs proj as a bde_gemm with BDE_EPI_SCATTER
+ * Supported: 7x7 windows, D <= 3, (c, heads) with c in {64, 256} and head_dim = c / 64 * 4 (4 or 16);
+ * bde_window_attention_fused_supported returns 1 for a supported shape. */
+int bde_window_attention_fused_supported(int c, int heads, int n_tok, int D);
+int bde_window_attention_fused(const float* const* frames_host, int D, int q_slot, const int* tok_map, int n_win,
+                               int c, int heads, const void* wqkv, const float* bqkv, const float* bias_tbl,
+                               const void* wproj, const float* bproj, float* xs, void* o_out, void* stream);
+
 /* float32 -> dtype copy/cast (and back); n elements */
 int bde_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
 

@@ -135,3 +135,28 @@ def test_batched_event_sequences_match_single():
         err = max(float((x - y).abs().max()) for x, y in zip(single[b], batched[b]))
         print("batched vs single", b, err)
         assert err <= 1e-3
+
+
+def test_fused_attention_matches_unfused():
+    """The one-kernel attention half (gather + LN + q/k/v + attention [+ proj + scatter]) against the
+    GEMM + attention-kernel path it replaces, on the default depths (plain and dilated blocks, D = 3)
+    and on a D = 2 configuration."""
+    for name in ("bde2vid_64x96_T6", "bde2vid_56x80_T3_q0"):
+        H, W, T, N, over, wseed, sid = MODEL_CASES[name]
+        vox, _ = voxel_inputs(sid, T, H, W, N)
+        outs = {}
+        for fuse in (True, False):
+            model, cfg, sd = build_model(over, wseed, "bf16")
+            eng = model.generator.engine()
+            if not fuse:
+                eng.fuse_attn = False
+                for blocks in eng.attn:
+                    for blk in blocks:
+                        blk["tbl"] = None
+            else:
+                assert all(blk["tbl"] is not None for blocks in eng.attn for blk in blocks), "fused path not selected"
+            with torch.no_grad():
+                outs[fuse] = torch.cat(model([{"events": v.to(DEV)} for v in vox]), 0)
+        err = float((outs[True] - outs[False]).abs().max())
+        print(name, "fused vs unfused", err)
+        assert err <= 1e-3
