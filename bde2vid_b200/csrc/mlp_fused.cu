@@ -1,0 +1,248 @@
+// Fused transformer MLP half of a SwinTransformerBlock3D (model/BDE2VID/DTransformer.py:279-283,302-304):
+//
+//   x[m, :] += fc2( GELU( fc1( LayerNorm(x[m, :]) ) ) )          x: float32 [P, C], updated in place
+//
+// for C = 64, hidden = 256 (attention level 1 of the assumed cfg; every pixel is a token).  One CTA owns
+// 128 rows.  Both GEMMs run on tcgen05 with fp32 accumulators in TMEM and the [128 x 256] hidden
+// activation never leaves the SM: the GELU epilogue of GEMM 1 writes it as bf16 straight into the
+// 128B-swizzled K-major shared-memory layout that GEMM 2 consumes as its A operand.  (The unfused path
+// wrote the hidden tensor, 4x the size of x, to HBM and read it back.)
+//
+//   warps 0-7  LayerNorm producer (fp32 rows -> normalised bf16 A tile; affine folded into W1 / b1 by the
+//              caller), then epilogue 1 (TMEM -> +b1 -> GELU -> bf16 -> smem) and epilogue 2
+//              (TMEM -> +b2 + residual -> coalesced fp32 store through a smem transpose)
+//   warp 8     one thread: TMA loads of W1 [256 x 64] and W2 [64 x 256] (SWIZZLE_128B), then both MMA chains
+// Shared memory ~100 KB and 256 TMEM columns (accumulator 2 reuses accumulator 1's columns) -> 2 CTAs / SM.
+#include <string.h>
+
+#include "tc_common.cuh"
+
+namespace bde {
+namespace tc {
+
+constexpr int kMlpC = 64, kMlpH = 256;
+constexpr int kMlpThreads = kNumProducerThreads + 32;
+constexpr int kMlpOffW1 = BM * 128;                      // A tile: 128 rows x 128 B
+constexpr int kMlpOffW2 = BM * kMlpH * 2;                // after the 64 KB region shared by (A, W1) and H
+constexpr int kMlpOffBar = kMlpOffW2 + kMlpC * kMlpH * 2;
+constexpr int kMlpOffBias = kMlpOffBar + 128;
+constexpr int kMlpSmem = kMlpOffBias + (kMlpH + kMlpC) * 4 + 1024;
+
+struct MlpParams {
+  float* x;          // [P, 64] in / out
+  const float* b1;   // [256]
+  const float* b2;   // [64]
+  int P;
+};
+
+__global__ void __launch_bounds__(kMlpThreads, 2)
+mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2, const MlpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sb - smem_u32(smem_raw));
+  const uint32_t s_a = sb, s_w1 = sb + kMlpOffW1, s_h = sb, s_w2 = sb + kMlpOffW2;
+  const uint32_t bar_a = sb + kMlpOffBar, bar_w1 = bar_a + 8, bar_w2 = bar_a + 16, bar_acc1 = bar_a + 24, bar_h = bar_a + 32,
+                 bar_acc2 = bar_a + 40, tmem_slot = bar_a + 48;
+  float* b1_s = reinterpret_cast<float*>(sgen + kMlpOffBias);
+  float* b2_s = b1_s + kMlpH;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+
+  for (int i = threadIdx.x; i < kMlpH + kMlpC; i += kMlpThreads) b1_s[i] = i < kMlpH ? __ldg(p.b1 + i) : __ldg(p.b2 + i - kMlpH);
+  if (threadIdx.x == 0) {
+    mbar_init(bar_a, kNumProducerThreads);
+    mbar_init(bar_w1, 1);
+    mbar_init(bar_w2, 1);
+    mbar_init(bar_acc1, 1);
+    mbar_init(bar_h, kNumProducerThreads);
+    mbar_init(bar_acc2, 1);
+    fence_barrier_init();
+  }
+  if (warp == kNumProducerWarps) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t*>(sgen + kMlpOffBar + 48);
+
+  if (warp < kNumProducerWarps) {
+    // ---------------- LayerNorm producer: lane j = lane & 7 owns 8 channels of rows warp*16 + 4i + (lane >> 3) -------
+    const int j = lane & 7, rsub = lane >> 3;
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) {
+      const int row = warp * (4 * kRowsPerThread) + i * 4 + rsub;
+      const int mm = m0 + row;
+      float v[8];
+      if (mm < p.P) {
+        const float4 t0 = *reinterpret_cast<const float4*>(p.x + (size_t)mm * kMlpC + j * 8);
+        const float4 t1 = *reinterpret_cast<const float4*>(p.x + (size_t)mm * kMlpC + j * 8 + 4);
+        v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += v[e];
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      const float mean = sum / (float)kMlpC;
+      float sq = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        v[e] -= mean;
+        sq += v[e] * v[e];
+      }
+      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+      const float rstd = 1.0f / sqrtf(sq / (float)kMlpC + 1e-5f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= rstd;
+      const uint4 pk = pack8_bf16(v);
+      const uint32_t dst = s_a + (uint32_t)row * 128u + (((uint32_t)j ^ (uint32_t)(row & 7)) << 4);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+    }
+    fence_proxy_async_smem();
+    mbar_arrive(bar_a);
+
+    // ---------------- epilogue 1: hidden = GELU(acc1 + b1) -> bf16, swizzled K-major tile for GEMM 2 -----------------
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;  // TMEM lane == tile row
+    const uint32_t lane_taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+    mbar_wait(bar_acc1, 0);
+    tcgen05_fence_after();
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      const int c0 = half * 128 + ch * 32;
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(lane_taddr + (uint32_t)c0, raw);
+      tmem_ld_wait();
+      const uint32_t kb_base = s_h + (uint32_t)(c0 >> 6) * (BM * 128) + (uint32_t)row * 128u;
+      const int j0 = (c0 & 63) >> 3;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fast_gelu(__uint_as_float(raw[jj * 8 + e]) + b1_s[c0 + jj * 8 + e]);
+        const uint4 pk = pack8_bf16(o);
+        const uint32_t dst = kb_base + ((((uint32_t)(j0 + jj)) ^ (uint32_t)(row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+      }
+    }
+    tcgen05_fence_before();   // our TMEM reads are done before GEMM 2 overwrites the columns
+    fence_proxy_async_smem();
+    mbar_arrive(bar_h);
+
+    // ---------------- epilogue 2: x += acc2 + b2, coalesced through a per-warp smem transpose ---------------------------
+    mbar_wait(bar_acc2, 0);
+    tcgen05_fence_after();
+    constexpr int kPitch = 36;
+    float* stg = reinterpret_cast<float*>(sgen) + warp * (32 * kPitch);  // the H region is free once GEMM 2 has completed
+    const int rq = lane >> 3, cq = (lane & 7) * 4;
+    {
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(half * 32), raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int jq = 0; jq < 32; jq += 4)
+        *reinterpret_cast<float4*>(stg + lane * kPitch + jq) =
+            make_float4(__uint_as_float(raw[jq]), __uint_as_float(raw[jq + 1]), __uint_as_float(raw[jq + 2]), __uint_as_float(raw[jq + 3]));
+      __syncwarp();
+      const float4 bb = *reinterpret_cast<const float4*>(b2_s + half * 32 + cq);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int mm = m0 + q * 32 + it * 4 + rq;
+        if (mm < p.P) {
+          const float4 acc = *reinterpret_cast<const float4*>(stg + (it * 4 + rq) * kPitch + cq);
+          float4* dst = reinterpret_cast<float4*>(p.x + (size_t)mm * kMlpC + half * 32 + cq);
+          float4 cur = *dst;
+          cur.x += acc.x + bb.x; cur.y += acc.y + bb.y; cur.z += acc.z + bb.z; cur.w += acc.w + bb.w;
+          *dst = cur;
+        }
+      }
+    }
+    tcgen05_fence_before();
+  } else {
+    // ---------------- TMA + MMA thread ---------------------------------------------------------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_w1, kMlpH * 128);
+      tma_load_2d(s_w1, &tmap_w1, bar_w1, 0, 0);
+      mbar_arrive_expect_tx(bar_w2, kMlpC * kMlpH * 2);
+#pragma unroll
+      for (int kb = 0; kb < kMlpH / BK; ++kb) tma_load_2d(s_w2 + kb * (kMlpC * 128), &tmap_w2, bar_w2, kb * BK, 0);
+      // GEMM 1: [128 x 64] x [64 x 256]
+      mbar_wait(bar_a, 0);
+      mbar_wait(bar_w1, 0);
+      tcgen05_fence_after();
+      {
+        constexpr uint32_t idesc = make_idesc(kMlpH);
+        const uint64_t adesc = make_smem_desc(s_a), bdesc = make_smem_desc(s_w1);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+        umma_commit(bar_acc1);
+      }
+      // GEMM 2: [128 x 256] x [256 x 64], A = the hidden tile written by epilogue 1
+      mbar_wait(bar_h, 0);
+      mbar_wait(bar_w2, 0);
+      tcgen05_fence_after();
+      {
+        constexpr uint32_t idesc = make_idesc(kMlpC);
+#pragma unroll
+        for (int kb = 0; kb < kMlpH / BK; ++kb) {
+          const uint64_t adesc = make_smem_desc(s_h + kb * (BM * 128)), bdesc = make_smem_desc(s_w2 + kb * (kMlpC * 128));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_acc2);
+      }
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == kNumProducerWarps) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_acc, 256);
+  }
+}
+
+}  // namespace tc
+}  // namespace bde
+
+using namespace bde;
+
+extern "C" int bde_mlp_fused_supported(int c, int hidden) { return (c == tc::kMlpC && hidden == tc::kMlpH) ? 1 : 0; }
+
+extern "C" int bde_mlp_fused(float* x, size_t rows, int c, int hidden, const void* w1, const float* b1, const void* w2,
+                             const float* b2, void* stream) {
+  using namespace bde::tc;
+  if (rows == 0) return 0;
+  BDE_REQUIRE(bde_mlp_fused_supported(c, hidden) == 1, "bde_mlp_fused: only c = 64, hidden = 256 is implemented (got %d, %d)", c, hidden);
+  BDE_REQUIRE(x != nullptr && w1 != nullptr && w2 != nullptr && b1 != nullptr && b2 != nullptr, "bde_mlp_fused: null operand");
+  BDE_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)w1) & 127) == 0 && (((uintptr_t)w2) & 127) == 0,
+              "bde_mlp_fused: operands must be 16-byte (weights 128-byte) aligned");
+  BDE_REQUIRE(rows < ((size_t)1 << 31), "bde_mlp_fused: row count overflows int32");
+  CUtensorMap t1, t2;
+  memset(&t1, 0, sizeof(t1));
+  memset(&t2, 0, sizeof(t2));
+  int rc = get_weight_tmap(w1, kMlpH, kMlpC, kMlpH, &t1);   // one box [64 k x 256 n]
+  if (rc != 0) return rc;
+  rc = get_weight_tmap(w2, kMlpC, kMlpH, kMlpC, &t2);       // boxes [64 k x 64 n]
+  if (rc != 0) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmem);
+    BDE_REQUIRE(e == cudaSuccess, "bde_mlp_fused: smem attribute: %s", cudaGetErrorString(e));
+    configured = true;
+  }
+  MlpParams p;
+  p.x = x; p.b1 = b1; p.b2 = b2; p.P = (int)rows;
+  mlp_fused_kernel<<<(unsigned)ceil_div(rows, BM), kMlpThreads, kMlpSmem, (cudaStream_t)stream>>>(t1, t2, p);
+  return check_launch("mlp_fused_kernel");
+}

@@ -117,6 +117,7 @@ class Engine:
         self.ws = cfg["window_size"]
         self.depths = cfg["depths"]
         self.fuse_attn = os.environ.get("BDE2VID_FUSED_ATTN", "1") != "0"
+        self.fuse_mlp = os.environ.get("BDE2VID_FUSED_MLP", "1") != "0"
         if self.bins > VOX_CPAD:
             raise NotImplementedError("num_bins > %d" % VOX_CPAD)
         dt = self.dtype
@@ -448,6 +449,17 @@ class _Plan:
         ops.pred_sigmoid(cur, self.head[s], eng.pred_w, eng.pred_b, eng.bc, n * Hp * Wp, self.img[s])
         self.launches += 1
 
+    def _mlp(self, blk, d, xs, P, C):
+        """xs += fc2(GELU(fc1(LN(xs)))) (DTransformer.py:279-283,302-304): one fused kernel where supported."""
+        eng = self.eng
+        if eng.fuse_mlp and ops.mlp_fused_supported(C, 4 * C):
+            ops.mlp_fused(xs, P, C, 4 * C, blk["fc1_ln"].w, blk["fc1_ln"].bias, blk["fc2"].w, blk["fc2"].bias)
+            self.launches += 1
+        else:
+            eng._gemm(blk["fc1_ln"], None, d["hid"], 1, P, 1, C, act=ACT_GELU, ln_frames=[xs])
+            eng._gemm(blk["fc2"], d["hid"], xs, 1, P, 1, 4 * C, out_f32=True, residual=xs)
+            self.launches += 2
+
     def _attention_level(self, l, on_frame_done=None):
         """In-place sequential multi-frame window attention (...V5.py:151-169; DTransformer.py:254-389)."""
         eng, T, B = self.eng, self.T, self.B
@@ -476,14 +488,13 @@ class _Plan:
                     if C == 64:
                         ops.window_attention_fused(fr, eng.q_ind, tm.view(-1), nwin, C, eng.heads, blk["qkv"].w,
                                                    blk["qkv"].bias, blk["tbl"], blk["proj"].w, blk["proj"].bias, xs=xs)
-                        self.launches += 3
+                        self.launches += 1
                     else:
                         ops.window_attention_fused(fr, eng.q_ind, tm.view(-1), nwin, C, eng.heads, blk["qkv"].w,
                                                    blk["qkv"].bias, blk["tbl"], o_out=d["ob"])
                         eng._gemm(blk["proj"], d["ob"], xs, 1, nwin * ntok, 1, C, epi=EPI_SCATTER, row_map=tm.view(-1))
-                        self.launches += 4
-                    eng._gemm(blk["fc1_ln"], None, d["hid"], 1, P, 1, C, act=ACT_GELU, ln_frames=[xs])
-                    eng._gemm(blk["fc2"], d["hid"], xs, 1, P, 1, 4 * C, out_f32=True, residual=xs)
+                        self.launches += 2
+                    self._mlp(blk, d, xs, P, C)
                     continue
                 if blk["qkv"] is not None:
                     # fused: [window gather + LayerNorm + q/k/v projection] -> attention -> proj+scatter ->
@@ -493,9 +504,8 @@ class _Plan:
                     ops.window_attention_mma_qkv(d["qkv"], blk["bias_mma"], nwin, ntok, D * ntok, eng.q_ind * ntok, C,
                                                  eng.heads, d["ob"])
                     eng._gemm(blk["proj"], d["ob"], xs, 1, nwin * ntok, 1, C, epi=EPI_SCATTER, row_map=tm.view(-1))
-                    eng._gemm(blk["fc1_ln"], None, d["hid"], 1, P, 1, C, act=ACT_GELU, ln_frames=[xs])
-                    eng._gemm(blk["fc2"], d["hid"], xs, 1, P, 1, 4 * C, out_f32=True, residual=xs)
-                    self.launches += 5
+                    self._mlp(blk, d, xs, P, C)
+                    self.launches += 3
                     continue
                 if C in (64, 128, 256):
                     ops.ln_gather_qkv(fr, eng.q_ind, tm, nwin, ntok, C, blk["nkv_g"], blk["nkv_b"], blk["nq_g"],

@@ -185,6 +185,17 @@ def window_attention_fused(frames, q_slot, tok_map, n_win, c, heads, wqkv, bqkv,
           "bde_window_attention_fused")
 
 
+def mlp_fused_supported(c, hidden):
+    return _lib.load().bde_mlp_fused_supported(c, hidden) == 1
+
+
+def mlp_fused(x, rows, c, hidden, w1, b1, w2, b2):
+    """x (float32 [rows, c]) += fc2(GELU(fc1(LayerNorm(x)))) in place; see include/bde2vid.h."""
+    lib = _lib.require_device()
+    assert x.dtype == torch.float32
+    check(lib.bde_mlp_fused(ptr(x), rows, c, hidden, ptr(w1), ptr(b1), ptr(w2), ptr(b2), stream_ptr()), "bde_mlp_fused")
+
+
 def cast(src, dst):
     lib = _lib.require_device()
     check(lib.bde_cast(ptr(src), BDE_DTYPE[src.dtype], ptr(dst), BDE_DTYPE[dst.dtype], src.numel(), stream_ptr()),

@@ -230,6 +230,16 @@ int bde_window_attention_fused(const float* const* frames_host, int D, int q_slo
                                int c, int heads, const void* wqkv, const float* bqkv, const float* bias_tbl,
                                const void* wproj, const float* bproj, float* xs, void* o_out, void* stream);
 
+/* Fused MLP half of a SwinTransformerBlock3D (DTransformer.py:279-283,302-304), in place on the fp32
+ * residual stream:  x[m, :] += fc2(GELU(fc1(LayerNorm(x[m, :]))))   for x float32 [rows, c].
+ *   w1, b1 : bf16 [hidden, c] / float32 [hidden] with norm2's affine folded in (W diag(gamma), W beta + b)
+ *   w2, b2 : bf16 [c, hidden] / float32 [c]
+ * Both GEMMs run on tcgen05; the hidden activation stays in shared memory.  Implemented for c = 64,
+ * hidden = 256 (bde_mlp_fused_supported); other shapes use two bde_gemm calls (ln_mode + GELU, residual). */
+int bde_mlp_fused_supported(int c, int hidden);
+int bde_mlp_fused(float* x, size_t rows, int c, int hidden, const void* w1, const float* b1, const void* w2,
+                  const float* b2, void* stream);
+
 /* float32 -> dtype copy/cast (and back); n elements */
 int bde_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
 

@@ -179,3 +179,29 @@ def test_ln_gather_qkv(dtype, C):
             assert (okv[:, d].float().cpu() - F.layer_norm(tok, (C,), gk, bk, 1e-5)).abs().max() <= tol
             if d == qs:
                 assert (oq.float().cpu() - F.layer_norm(tok, (C,), gq, bq, 1e-5)).abs().max() <= tol
+
+
+@pytest.mark.parametrize("rows", [128, 1000, 23232])
+def test_mlp_fused(rows):
+    """x += fc2(GELU(fc1(LN(x)))) in one tcgen05 kernel vs fp32 torch on bf16-rounded weights (DTransformer.py:279-304)."""
+    from bde2vid_b200 import ops
+    g = torch.Generator().manual_seed(rows)
+    C, Hd = 64, 256
+    x = torch.randn(rows, C, generator=g) * 2 + 0.3
+    gamma, beta = 1 + 0.2 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    W1, b1 = torch.randn(Hd, C, generator=g) / 8, torch.randn(Hd, generator=g) * 0.1
+    W2, b2 = torch.randn(C, Hd, generator=g) / 16, torch.randn(C, generator=g) * 0.1
+    w1f = (W1 * gamma[None, :]).to(torch.bfloat16)
+    b1f = W1 @ beta + b1
+    w2f = W2.to(torch.bfloat16)
+    xn = F.layer_norm(x, (C,), eps=1e-5).to(torch.bfloat16).float()
+    hid = F.gelu(xn @ w1f.float().t() + b1f).to(torch.bfloat16).float()
+    ref = x + hid @ w2f.float().t() + b2
+    xd = x.to(DEV).contiguous()
+    ops.mlp_fused(xd, rows, C, Hd, w1f.to(DEV).contiguous(), b1f.to(DEV), w2f.to(DEV).contiguous(), b2.to(DEV))
+    torch.cuda.synchronize()
+    err = float((xd.cpu() - ref).abs().max())
+    print("mlp_fused", rows, err)
+    assert err <= 2e-2     # bf16 rounding of the hidden activations at values of order 1..8
+    full = x + F.gelu(F.layer_norm(x, (C,), gamma, beta, 1e-5) @ W1.t() + b1) @ W2.t() + b2
+    assert float((xd.cpu() - full).abs().max()) <= 6e-2

@@ -21,7 +21,7 @@ def main(path, top=40):
         name = name.replace("void ", "").replace("bde::<unnamed>::", "").replace("bde::", "")[:60]
         agg[name][0] += 1
         agg[name][1] += v
-        if "gemm" in name or "attention" in name:
+        if "gemm" in name or "attention" in name or "attn" in name or "mlp" in name:
             by_grid[(name, row.get("Grid Size", ""))][0] += 1
             by_grid[(name, row.get("Grid Size", ""))][1] += v
     tot = sum(v[1] for v in agg.values())
