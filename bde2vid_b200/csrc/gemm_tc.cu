@@ -31,8 +31,12 @@ namespace tc {
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
+// two CTAs per SM wherever the tile's shared memory allows it (the register allocation must then fit 640 threads)
+template <int BN, bool kDeep, int kLn>
+constexpr int kMinCtas = TileCfg<BN, kDeep, kLn>::kSmemBytes <= 113 * 1024 ? 2 : 1;
+
 template <int BN, bool kBTma, bool kDeep, int kLn>
-__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
+__global__ void __launch_bounds__(kThreads, kMinCtas<BN, kDeep, kLn>) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_b, const TcParams p) {
   using Cfg = TileCfg<BN, kDeep, kLn>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -265,6 +269,13 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
       m_it[it] = ok ? mm : -1;
       dst_it[it] = (ok && p.epi == BDE_EPI_SCATTER) ? __ldg(p.row_map + mm) : -1;
     }
+    // operands the epilogue READS from global memory (c_prev / residual / scatter destination) for the first column
+    // chunk: in flight while the accumulator is still being computed
+    const bool need_aux = p.epi != BDE_EPI_STORE || p.residual != nullptr;
+    float4 aux[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it)
+      aux[it] = (need_aux && m_it[it] >= 0) ? aux_load(p, m_it[it], n0 + half * 32 + cq, dst_it[it]) : make_float4(0.f, 0.f, 0.f, 0.f);
     mbar_wait(bar_acc, 0);
     tcgen05_fence_after();
     if (threadIdx.x == 0) BDE_DBG(5);
@@ -281,10 +292,18 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
             make_float4(__uint_as_float(raw[jq]), __uint_as_float(raw[jq + 1]), __uint_as_float(raw[jq + 2]),
                         __uint_as_float(raw[jq + 3]));
       __syncwarp();
+      float4 accv[8];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const float4 acc = *reinterpret_cast<const float4*>(stg + (it * 4 + rq) * kPitch + cq);
-        if (m_it[it] >= 0) epilogue_quad(p, m_it[it], n0 + cb + cq, acc, *reinterpret_cast<const float4*>(bias_s + cb + cq), dst_it[it]);
+      for (int it = 0; it < 8; ++it) accv[it] = *reinterpret_cast<const float4*>(stg + (it * 4 + rq) * kPitch + cq);
+      const float4 bq = *reinterpret_cast<const float4*>(bias_s + cb + cq);
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        if (m_it[it] >= 0) epilogue_quad_aux(p, m_it[it], n0 + cb + cq, accv[it], bq, dst_it[it], aux[it]);
+      // next chunk's reads: issued together, after this chunk's stores
+      if (need_aux && cb + 64 < BN) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          if (m_it[it] >= 0) aux[it] = aux_load(p, m_it[it], n0 + cb + 64 + cq, dst_it[it]);
       }
     }
     tcgen05_fence_before();
@@ -492,17 +511,26 @@ int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s) {
   int rc0 = fill_params(d, p, ln);
   if (rc0 != 0) return rc0;
   if (p.M == 0) return 0;
-  const bool deep = p.tiles_x > 0 && env_flag("BDE2VID_TC_DEEP", false);
-  // tile width: widest tile that still gives every SM work
+  // tile width: widest tile that still gives most SMs work (measured on the LSTM / encoder shapes: a 256-wide tile
+  // gathers the A operand half as often and wins as soon as it yields >= ~100 CTAs; tools/tc_phase_probe.py bn)
   int bn = 32;
   if (p.N % 128 == 0) bn = 128;
   else if (p.N % 64 == 0) bn = 64;
-  const size_t m_tiles = ceil_div(p.M, BM);
-  if (p.N % 256 == 0 && m_tiles * (p.N / 256) >= 2 * (size_t)kNumSMs) bn = 256;
+  const size_t m_tiles = p.tiles_x > 0 ? (size_t)p.n_img * p.tiles_x * p.tiles_y : ceil_div(p.M, BM);
+  if (p.N % 256 == 0 && p.K >= 512 && m_tiles * (p.N / 256) >= 100) bn = 256;
+  {
+    // tuning override (tools/tc_phase_probe.py): force the N tile where it divides N
+    const char* e = getenv("BDE2VID_TC_BN");
+    const int f = (e != nullptr && e[0] != 0) ? atoi(e) : 0;
+    if ((f == 32 || f == 64 || f == 128 || f == 256) && p.N % f == 0) bn = f;
+  }
   if (ln) {
     // the LayerNorm is recomputed by every N tile of a row block: prefer the widest tile
     bn = (p.N % 256 == 0) ? 256 : (p.N % 192 == 0) ? 192 : (p.N % 128 == 0) ? 128 : (p.N % 64 == 0) ? 64 : 32;
   }
+  // grids of at most one CTA per SM cannot overlap two CTAs' phases: give the single CTA a deeper pipeline instead
+  const bool small_grid = !ln && m_tiles * (size_t)(p.N / bn) <= (size_t)kNumSMs && p.num_kb >= 8;
+  const bool deep = (p.tiles_x > 0 && env_flag("BDE2VID_TC_DEEP", false)) || (small_grid && env_flag("BDE2VID_TC_DEEP_SMALL", true));
   if (g_dbg != nullptr) {
     const size_t mt = p.tiles_x > 0 ? (size_t)p.n_img * p.tiles_x * p.tiles_y : ceil_div(p.M, BM);
     if (mt * (p.N / bn) <= g_dbg_ctas) p.dbg = g_dbg;

@@ -221,6 +221,14 @@ struct TileCfg {
 // fast transcendental forms for the bf16 path (relative error ~1e-6, far below bf16 resolution)
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+// single-MUFU forms for the ConvLSTM gate math (tanh.approx.f32: max relative error 2^-11, a quarter of the bf16
+// rounding that h undergoes anyway): sigmoid(x) = 0.5 tanh(x / 2) + 0.5.  5 MUFU per cell instead of 10.
+__device__ __forceinline__ float mufu_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_sigmoid(float x) { return fmaf(mufu_tanh(0.5f * x), 0.5f, 0.5f); }
 
 // GELU with erf from Abramowitz & Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution) on the fast
 // exp / reciprocal units: ~16 instructions instead of ~45 for erff.  The fp32 parity engine keeps erff.
@@ -304,6 +312,70 @@ __device__ __forceinline__ void epilogue_quad(const TcParams& p, int m, int nb, 
   }
 }
 
+// ---- epilogue with pre-fetched auxiliary operand --------------------------------------------------------------
+// The global READS of an epilogue (LSTM: c_prev; STORE: fp32 or pre-activation residual; SCATTER: the destination's
+// current value) alias the kernel's own stores as far as the compiler can tell, so inside an unrolled row loop every
+// read would wait for the previous row's store to issue and for its own latency: ~700 cycles x rows.  The callers
+// therefore fetch the operand of all 8 rows of a chunk up front (aux_load, independent loads in flight together) and
+// hand it to the math here.
+__device__ __forceinline__ float4 aux_load(const TcParams& p, int m, int nb, int dst_row) {
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.epi == BDE_EPI_LSTM) {
+    if (p.c_prev != nullptr) a.x = p.c_prev[(size_t)m * (p.N >> 2) + (nb >> 2)];
+  } else if (p.epi == BDE_EPI_STORE) {
+    if (p.residual != nullptr) {
+      const size_t o = (size_t)m * p.N + nb;
+      if (p.res_mode == 1) {
+        const uint2 rr = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + o);
+        const float2 r0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr.x));
+        const float2 r1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr.y));
+        a = make_float4(r0.x, r0.y, r1.x, r1.y);
+      } else {
+        a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + o);
+      }
+    }
+  } else if (dst_row >= 0) {
+    a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + (size_t)dst_row * p.N + nb);
+  }
+  return a;
+}
+
+__device__ __forceinline__ void epilogue_quad_aux(const TcParams& p, int m, int nb, float4 acc, float4 b, int dst_row, float4 aux) {
+  float v0 = acc.x + b.x, v1 = acc.y + b.y, v2 = acc.z + b.z, v3 = acc.w + b.w;
+  if (p.epi == BDE_EPI_STORE) {
+    const size_t o = (size_t)m * p.N + nb;
+    if (p.res_mode == 1) { v0 += aux.x; v1 += aux.y; v2 += aux.z; v3 += aux.w; }
+    if (p.act == BDE_ACT_RELU) {
+      v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+    } else if (p.act == BDE_ACT_RELU6) {
+      v0 = fminf(fmaxf(v0, 0.f), 6.f); v1 = fminf(fmaxf(v1, 0.f), 6.f);
+      v2 = fminf(fmaxf(v2, 0.f), 6.f); v3 = fminf(fmaxf(v3, 0.f), 6.f);
+    } else if (p.act == BDE_ACT_GELU) {
+      v0 = fast_gelu(v0); v1 = fast_gelu(v1); v2 = fast_gelu(v2); v3 = fast_gelu(v3);
+    } else if (p.act != BDE_ACT_NONE) {
+      v0 = apply_act(v0, p.act); v1 = apply_act(v1, p.act); v2 = apply_act(v2, p.act); v3 = apply_act(v3, p.act);
+    }
+    if (p.res_mode == 0) { v0 += aux.x; v1 += aux.y; v2 += aux.z; v3 += aux.w; }   // aux is zero without a residual
+    if (p.out_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) = make_float4(v0, v1, v2, v3);
+    __nv_bfloat16* dstb = p.out_f32 ? reinterpret_cast<__nv_bfloat16*>(p.out2) : reinterpret_cast<__nv_bfloat16*>(p.out);
+    if (dstb != nullptr) {
+      const __nv_bfloat162 t0 = __floats2bfloat162_rn(v0, v1), t1 = __floats2bfloat162_rn(v2, v3);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&t0);
+      pk.y = *reinterpret_cast<const uint32_t*>(&t1);
+      *reinterpret_cast<uint2*>(dstb + o) = pk;
+    }
+  } else if (p.epi == BDE_EPI_LSTM) {
+    const size_t o = (size_t)m * (p.N >> 2) + (nb >> 2);
+    const float c = fmaf(mufu_sigmoid(v1), aux.x, mufu_sigmoid(v0) * mufu_tanh(v3));
+    const float h = mufu_sigmoid(v2) * mufu_tanh(c);
+    p.c_out[o] = c;
+    reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(h);
+  } else if (dst_row >= 0) {  // BDE_EPI_SCATTER
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)dst_row * p.N + nb) =
+        make_float4(aux.x + v0, aux.y + v1, aux.z + v2, aux.w + v3);
+  }
+}
 
 // host helpers implemented in gemm_tc.cu
 int get_weight_tmap(const void* w, int n, int w_ld, int bn, CUtensorMap* out);

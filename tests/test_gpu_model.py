@@ -160,3 +160,21 @@ def test_fused_attention_matches_unfused():
         err = float((outs[True] - outs[False]).abs().max())
         print(name, "fused vs unfused", err)
         assert err <= 1e-3
+
+
+def test_long_recurrence_bf16_vs_oracle():
+    """The north-star frame gate after a long recurrent chain: T = 40 windows, bf16 tcgen05 engine (approximate
+    gate activations, bf16 h state) against the fp32 oracle; max-abs <= 2e-3, MSE / SSIM deltas <= 1e-3."""
+    H, W, T, N = 64, 96, 40, 2500
+    over = dict(depths=[2, 0, 2])
+    model, cfg, sd = build_model(over, 11, "bf16")
+    vox, _ = voxel_inputs(21, T, H, W, N)
+    with torch.no_grad():
+        ref = torch.cat(O.bde2vid_forward(sd, cfg, vox), 0)
+        out = torch.cat(model([{"events": v.to(DEV)} for v in vox]), 0).cpu()
+    err = float((out - ref).abs().max())
+    late = float((out[T // 2:] - ref[T // 2:]).abs().max())
+    print("long recurrence T=%d: max-abs %.3e (second half %.3e) mse %.3e" % (T, err, late, float(((out - ref) ** 2).mean())))
+    assert err <= 2e-3
+    assert float(((out - ref) ** 2).mean()) <= 1e-3
+    assert min(O.ssim_uniform7(out[t], ref[t]) for t in (0, T // 2, T - 1)) >= 1 - 1e-3

@@ -29,7 +29,28 @@ CASES = [
     ("dec1 5x5 128->64", 1, 132, 176, 128, 0, 64, 5, 1, "store"),
     ("enc0 5x5s2 32->64", 4, 264, 352, 32, 0, 64, 5, 2, "store"),
 ]
+CASES_B4 = [
+    ("LSTM L1 B4", 4, 132, 176, 64, 64, 256, 3, 1, "lstm"),
+    ("LSTM L2 B4", 4, 66, 88, 128, 128, 512, 3, 1, "lstm"),
+    ("LSTM L3 B4", 4, 33, 44, 256, 256, 1024, 3, 1, "lstm"),
+    ("dec2 5x5 64->32 x8", 8, 264, 352, 64, 0, 32, 5, 1, "store"),
+    ("dec1 5x5 128->64 x8", 8, 132, 176, 128, 0, 64, 5, 1, "store"),
+    ("dec0 5x5 256->128 x8", 8, 66, 88, 256, 0, 128, 5, 1, "store"),
+    ("enc0 5x5s2 32->64 x24", 24, 264, 352, 32, 0, 64, 5, 2, "store"),
+    ("enc1 5x5s2 64->128 x24", 24, 132, 176, 64, 0, 128, 5, 2, "store"),
+    ("enc2 5x5s2 128->256 x24", 24, 66, 88, 128, 0, 256, 5, 2, "store"),
+    ("head 5x5 8->32 x24", 24, 264, 352, 8, 0, 32, 5, 1, "store"),
+    ("fc1 L3 B4", 1, 5808, 1, 256, 0, 1024, 1, 1, "store"),
+    ("fc2 L3 B4", 1, 5808, 1, 1024, 0, 256, 1, 1, "store"),
+    ("proj L3 B4", 1, 6860, 1, 256, 0, 256, 1, 1, "store"),
+]
 CONFIGS = [("tile2d=1 deep=0", "1", "0"), ("tile2d=0 deep=0", "0", "0"), ("tile2d=1 deep=1", "1", "1")]
+if len(sys.argv) > 1 and sys.argv[1] == "bn":
+    # N-tile sweep on the batch-4 shapes
+    SWEEP = True
+else:
+    SWEEP = False
+
 
 
 def run_case(name, n_img, h, w, c0, c1, n, k, stride, epi):
@@ -75,6 +96,15 @@ def run_case(name, n_img, h, w, c0, c1, n, k, stride, epi):
           "acc-ready %6d epi %5d total %6d" % (name, M, n, kb, len(used), us, flops / us / 1e6, d(0, 1), d(1, 2), d(1, 4),
                                                 d(2, 3), d(0, 5), d(5, 6), d(0, 7)))
 
+
+if SWEEP:
+    for bn in ("0", "128", "256"):
+        os.environ["BDE2VID_TC_BN"] = bn
+        print("=== BN override " + bn)
+        for case in (CASES if len(sys.argv) > 2 and sys.argv[2] == "b1" else CASES_B4):
+            if case[6] % max(int(bn), 1) == 0 and (len(sys.argv) < 4 or sys.argv[3] in case[0]):
+                run_case(*case)
+    sys.exit(0)
 
 for cfg_name, t2d, deep in CONFIGS:
     os.environ["BDE2VID_TC_TILE2D"] = t2d
