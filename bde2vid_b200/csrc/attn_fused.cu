@@ -60,6 +60,16 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -94,9 +104,9 @@ struct FusedCfg {
   static constexpr int OFF_Q = A_BYTES;
   static constexpr int OFF_K = OFF_Q + 64 * PQ * 2;
   static constexpr int OFF_V = OFF_K + NKEY * PQ * 2;
-  static constexpr int OFF_COFF = OFF_V + XROWS * PQ * 2;   // int16 [NKEY]
-  static constexpr int OFF_ROFF = OFF_COFF + ((NKEY * 2 + 15) / 16) * 16;  // int16 [64]
-  static constexpr int OFF_PIX = OFF_ROFF + 128;            // int32 [64]
+  static constexpr int OFF_COFF = OFF_V + XROWS * PQ * 2;   // int32 [NKEY]  byte offsets into a bias-table row block
+  static constexpr int OFF_ROFF = OFF_COFF + NKEY * 4;      // int32 [64]
+  static constexpr int OFF_PIX = OFF_ROFF + 256;            // int32 [64]
   static constexpr int SMEM = OFF_PIX + 256;
 };
 
@@ -140,8 +150,8 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
   __nv_bfloat16* qs = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_Q);
   __nv_bfloat16* ks = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_K);
   __nv_bfloat16* vs = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_V);
-  short* coff = reinterpret_cast<short*>(smem + Cfg::OFF_COFF);
-  short* roff = reinterpret_cast<short*>(smem + Cfg::OFF_ROFF);
+  int* coff = reinterpret_cast<int*>(smem + Cfg::OFF_COFF);
+  int* roff = reinterpret_cast<int*>(smem + Cfg::OFF_ROFF);
   int* pix_s = reinterpret_cast<int*>(smem + Cfg::OFF_PIX);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -166,16 +176,16 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
 
   // ---- index tables -----------------------------------------------------------------------------------
   for (int n = tid; n < NKEY; n += kThreadsF) {
-    int v = -1;
+    int v = 0;  // padding keys read entry 0 and are masked in the last key tile
     if (n < n_kv) {
       const int d = n / kTok, r = n - d * kTok, a = r / 7, b = r - a * 7;
       v = d * kRel + (6 - a) * 13 + (6 - b);
     }
-    coff[n] = (short)v;
+    coff[n] = v * 4;
   }
   if (tid < 64) {
     const int a = tid / 7, b = tid - a * 7;
-    roff[tid] = (short)(tid < kTok ? a * 13 + b : 0);
+    roff[tid] = tid < kTok ? (a * 13 + b) * 4 : 0;
     pix_s[tid] = tid < kTok ? __ldg(p.tok_map + (size_t)w * kTok + tid) : -1;
   }
   __syncthreads();
@@ -321,46 +331,90 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
   }
 
   // ---- attention: unit = (head of the group, 16-row query tile); scores stay in registers ----------------------
+  // head_dim 4: the 49th query row would cost a whole tile per head, so the normal units cover rows 0..47 and one
+  // "special" unit packs row 48 of all 16 heads into a single tile (tile row = head; the query fragment carries only
+  // that head's 4 channels, the key fragment all 64, so each row still sees its own head's dot product).
   const uint32_t vs_u32 = sb + Cfg::OFF_V;
+  const uint32_t ks_u32 = sb + Cfg::OFF_K;
+  const uint32_t tbl_u32 = sb + Cfg::OFF_TBL;
+  const uint32_t coff_u32 = sb + Cfg::OFF_COFF;
   __nv_bfloat16* os = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_OS);  // C == 64 only
-  for (int unit = warp; unit < HG * 4; unit += kThreadsF / 32) {
-    const int hl = unit >> 2, mt = unit & 3;
+  constexpr int MTN = HD == 4 ? 3 : 4;                 // query tiles per head handled by normal units
+  constexpr int NUNITS = HG * MTN + (HD == 4 ? 1 : 0);
+  constexpr uint32_t kOnes = 0x3F803F80u;              // bf16x2 (1, 1)
+  constexpr float kLog2e = 1.4426950408889634f;
+  for (int unit = warp; unit < NUNITS; unit += kThreadsF / 32) {
+    const bool special = HD == 4 && unit == HG * MTN;
+    const int hl = unit / MTN, mt = unit - hl * MTN;
     const int row0 = mt * 16 + g, row1 = row0 + 8;
-    const float* tb = tbl_s + hl * tbl_ld;
-    const int r0o = roff[row0], r1o = roff[row1];
-    uint32_t qa[4] = {0u, 0u, 0u, 0u};
-    {
-      const __nv_bfloat16* q0 = qs + row0 * PQ + hl * HD;
-      const __nv_bfloat16* q1 = qs + row1 * PQ + hl * HD;
-      if (2 * t < HD) {
-        qa[0] = *reinterpret_cast<const uint32_t*>(q0 + 2 * t);
-        qa[1] = *reinterpret_cast<const uint32_t*>(q1 + 2 * t);
-      }
-      if (2 * t + 8 < HD) {
-        qa[2] = *reinterpret_cast<const uint32_t*>(q0 + 2 * t + 8);
-        qa[3] = *reinterpret_cast<const uint32_t*>(q1 + 2 * t + 8);
-      }
-    }
     float s[NT][4];
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      const uint32_t cp = *reinterpret_cast<const uint32_t*>(coff + j * 8 + 2 * t);
-      const int c0 = (int)(short)(cp & 0xffffu), c1 = (int)(short)(cp >> 16);
-      if (j == NT - 1) {  // only the last key tile can hold padding keys
-        s[j][0] = c0 >= 0 ? tb[r0o + c0] : -1e30f;
-        s[j][1] = c1 >= 0 ? tb[r0o + c1] : -1e30f;
-        s[j][2] = c0 >= 0 ? tb[r1o + c0] : -1e30f;
-        s[j][3] = c1 >= 0 ? tb[r1o + c1] : -1e30f;
-      } else {
-        s[j][0] = tb[r0o + c0]; s[j][1] = tb[r0o + c1];
-        s[j][2] = tb[r1o + c0]; s[j][3] = tb[r1o + c1];
+    if (!special) {
+      const uint32_t r0a = tbl_u32 + (uint32_t)(hl * tbl_ld * 4 + roff[row0]);
+      const uint32_t r1a = tbl_u32 + (uint32_t)(hl * tbl_ld * 4 + roff[row1]);
+      uint32_t qa[4] = {0u, 0u, 0u, 0u};
+      {
+        const __nv_bfloat16* q0 = qs + row0 * PQ + hl * HD;
+        const __nv_bfloat16* q1 = qs + row1 * PQ + hl * HD;
+        if (2 * t < HD) {
+          qa[0] = *reinterpret_cast<const uint32_t*>(q0 + 2 * t);
+          qa[1] = *reinterpret_cast<const uint32_t*>(q1 + 2 * t);
+        }
+        if (2 * t + 8 < HD) {
+          qa[2] = *reinterpret_cast<const uint32_t*>(q0 + 2 * t + 8);
+          qa[3] = *reinterpret_cast<const uint32_t*>(q1 + 2 * t + 8);
+        }
       }
-      const __nv_bfloat16* kr = ks + (j * 8 + g) * PQ + hl * HD;
-      uint32_t kb0 = 0u, kb1 = 0u;
-      if (2 * t < HD) kb0 = *reinterpret_cast<const uint32_t*>(kr + 2 * t);
-      if (2 * t + 8 < HD) kb1 = *reinterpret_cast<const uint32_t*>(kr + 2 * t + 8);
-      mma16816(s[j], qa, kb0, kb1);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const uint2 cp = lds_u64(coff_u32 + (uint32_t)((j * 8 + 2 * t) * 4));
+        s[j][0] = lds_f32(r0a + cp.x); s[j][1] = lds_f32(r0a + cp.y);
+        s[j][2] = lds_f32(r1a + cp.x); s[j][3] = lds_f32(r1a + cp.y);
+        if (j == NT - 1) {  // only the last key tile can hold padding keys
+          if (j * 8 + 2 * t >= n_kv) s[j][0] = s[j][2] = -1e30f;
+          if (j * 8 + 2 * t + 1 >= n_kv) s[j][1] = s[j][3] = -1e30f;
+        }
+        const __nv_bfloat16* kr = ks + (j * 8 + g) * PQ + hl * HD;
+        uint32_t kb0 = 0u, kb1 = 0u;
+        if (2 * t < HD) kb0 = *reinterpret_cast<const uint32_t*>(kr + 2 * t);
+        if (2 * t + 8 < HD) kb1 = *reinterpret_cast<const uint32_t*>(kr + 2 * t + 8);
+        mma16816(s[j], qa, kb0, kb1);
+      }
+    } else {
+      // tile row g <-> head g, row g + 8 <-> head g + 8; query token 48
+      const uint32_t r0a = tbl_u32 + (uint32_t)(g * tbl_ld * 4 + roff[48]);
+      const uint32_t r1a = tbl_u32 + (uint32_t)((g + 8) * tbl_ld * 4 + roff[48]);
+      uint32_t qa4[4][4];
+#pragma unroll
+      for (int kq = 0; kq < 4; ++kq) {
+        const int ch0 = 16 * kq + 2 * t, ch1 = ch0 + 8;
+        const uint32_t v0 = *reinterpret_cast<const uint32_t*>(qs + 48 * PQ + ch0);
+        const uint32_t v1 = *reinterpret_cast<const uint32_t*>(qs + 48 * PQ + ch1);
+        qa4[kq][0] = (ch0 >> 2) == g ? v0 : 0u;
+        qa4[kq][1] = (ch0 >> 2) == g + 8 ? v0 : 0u;
+        qa4[kq][2] = (ch1 >> 2) == g ? v1 : 0u;
+        qa4[kq][3] = (ch1 >> 2) == g + 8 ? v1 : 0u;
+      }
+      // ldmatrix.x4 of an 8-key x 32-channel block: b0 / b1 of two consecutive k16 steps
+      const uint32_t kaddr0 = ks_u32 + (uint32_t)(((lane & 7) * PQ + (lane >> 3) * 8) * 2);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const uint2 cp = lds_u64(coff_u32 + (uint32_t)((j * 8 + 2 * t) * 4));
+        s[j][0] = lds_f32(r0a + cp.x); s[j][1] = lds_f32(r0a + cp.y);
+        s[j][2] = lds_f32(r1a + cp.x); s[j][3] = lds_f32(r1a + cp.y);
+        if (j == NT - 1) {
+          if (j * 8 + 2 * t >= n_kv) s[j][0] = s[j][2] = -1e30f;
+          if (j * 8 + 2 * t + 1 >= n_kv) s[j][1] = s[j][3] = -1e30f;
+        }
+        uint32_t kb[4];
+        ldsm_x4(kb, kaddr0 + (uint32_t)(j * 8 * PQ * 2));
+        mma16816(s[j], qa4[0], kb[0], kb[1]);
+        mma16816(s[j], qa4[1], kb[2], kb[3]);
+        ldsm_x4(kb, kaddr0 + (uint32_t)(j * 8 * PQ * 2 + 64));
+        mma16816(s[j], qa4[2], kb[0], kb[1]);
+        mma16816(s[j], qa4[3], kb[2], kb[3]);
+      }
     }
+    // ---- softmax numerators (the row sums come out of the P.V product through a column of ones) -------------------
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
@@ -371,66 +425,106 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    constexpr float kLog2e = 1.4426950408889634f;
     const float m0s = mx0 * kLog2e, m1s = mx1 * kLog2e;
-    float l0 = 0.f, l1 = 0.f;
+    uint32_t pp[NT][2];   // P as bf16 pairs: [j][0] = row0 (cols 2t, 2t+1), [j][1] = row1
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      s[j][0] = ex2(fmaf(s[j][0], kLog2e, -m0s));
-      s[j][1] = ex2(fmaf(s[j][1], kLog2e, -m0s));
-      s[j][2] = ex2(fmaf(s[j][2], kLog2e, -m1s));
-      s[j][3] = ex2(fmaf(s[j][3], kLog2e, -m1s));
-      l0 += s[j][0] + s[j][1];
-      l1 += s[j][2] + s[j][3];
+      pp[j][0] = pack2(ex2(fmaf(s[j][0], kLog2e, -m0s)), ex2(fmaf(s[j][1], kLog2e, -m0s)));
+      pp[j][1] = pack2(ex2(fmaf(s[j][2], kLog2e, -m1s)), ex2(fmaf(s[j][3], kLog2e, -m1s)));
     }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-
-    // O = P V: HD >= 8: channel tile v covers channels hl*HD + 8v..; HD == 4: one 8-wide tile shared by a head pair
-    constexpr int NV = (HD + 7) / 8;
-    float o[NV][4];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) o[v][0] = o[v][1] = o[v][2] = o[v][3] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < KSTEPS; ++kk) {
-      uint32_t pa[4];
-      pa[0] = pack2(s[2 * kk][0], s[2 * kk][1]);
-      pa[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
-      if (2 * kk + 1 < NT) {
-        pa[2] = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-        pa[3] = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-      } else {
-        pa[2] = 0u;
-        pa[3] = 0u;
-      }
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int ch0 = (HD >= 8) ? hl * HD + 8 * v : (hl >> 1) * 8;
-        uint32_t vb0, vb1;
-        ldsm_x2_trans(vb0, vb1, vs_u32 + (uint32_t)(((kk * 16 + (lane & 15)) * PQ + ch0) * 2));
-        mma16816(o[v], pa, vb0, vb1);
-      }
-    }
-    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      int col = hl * HD + 8 * v + 2 * t;
-      bool mine = true;
+    auto p_frag = [&](int kk, uint32_t (&pa)[4]) {
+      pa[0] = pp[2 * kk][0];
+      pa[1] = pp[2 * kk][1];
+      pa[2] = 2 * kk + 1 < NT ? pp[2 * kk + 1][0] : 0u;
+      pa[3] = 2 * kk + 1 < NT ? pp[2 * kk + 1][1] : 0u;
+    };
+    if (!special) {
       if (HD == 4) {
-        mine = (t >> 1) == (hl & 1);
-        col = (hl >> 1) * 8 + 2 * t;
+        // one 8-channel V tile holds a head pair; the other head's columns are replaced by ones -> row sums
+        const bool ones_lane = (g >> 2) != (hl & 1);
+        float oa[4] = {0.f, 0.f, 0.f, 0.f}, ob[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t vaddr = vs_u32 + (uint32_t)(((lane & 15) * PQ + (hl >> 1) * 8) * 2);
+#pragma unroll
+        for (int kk = 0; kk < KSTEPS; ++kk) {
+          uint32_t pa[4];
+          p_frag(kk, pa);
+          uint32_t vb0, vb1;
+          ldsm_x2_trans(vb0, vb1, vaddr + (uint32_t)(kk * 16 * PQ * 2));
+          if (ones_lane) { vb0 = kOnes; vb1 = kOnes; }
+          if (kk & 1) mma16816(ob, pa, vb0, vb1); else mma16816(oa, pa, vb0, vb1);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oa[e] += ob[e];
+        const float l0 = __shfl_xor_sync(0xffffffffu, oa[0], 2), l1 = __shfl_xor_sync(0xffffffffu, oa[2], 2);
+        if ((t >> 1) == (hl & 1)) {
+          const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+          const int col = (hl >> 1) * 8 + 2 * t;
+          *reinterpret_cast<uint32_t*>(os + row0 * PQ + col) = pack2(oa[0] * inv0, oa[1] * inv0);
+          *reinterpret_cast<uint32_t*>(os + row1 * PQ + col) = pack2(oa[2] * inv1, oa[3] * inv1);
+        }
+      } else {
+        constexpr int NV = HD >= 8 ? HD / 8 : 1;
+        float o[NV][4], ol[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int v = 0; v < NV; ++v) o[v][0] = o[v][1] = o[v][2] = o[v][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KSTEPS; ++kk) {
+          uint32_t pa[4];
+          p_frag(kk, pa);
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            uint32_t vb0, vb1;
+            ldsm_x2_trans(vb0, vb1, vs_u32 + (uint32_t)(((kk * 16 + (lane & 15)) * PQ + hl * HD + 8 * v) * 2));
+            mma16816(o[v], pa, vb0, vb1);
+          }
+          mma16816(ol, pa, kOnes, kOnes);   // row sums
+        }
+        const float inv0 = 1.0f / ol[0], inv1 = 1.0f / ol[2];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int col = hl * HD + 8 * v + 2 * t;
+          const uint32_t v0 = pack2(o[v][0] * inv0, o[v][1] * inv0), v1 = pack2(o[v][2] * inv1, o[v][3] * inv1);
+          if (C == 64) {
+            *reinterpret_cast<uint32_t*>(os + row0 * PQ + col) = v0;
+            *reinterpret_cast<uint32_t*>(os + row1 * PQ + col) = v1;
+          } else {
+            __nv_bfloat16* og = p.o_out + (size_t)w * kTok * C + hg * 64 + col;
+            if (row0 < kTok) *reinterpret_cast<uint32_t*>(og + (size_t)row0 * C) = v0;
+            if (row1 < kTok) *reinterpret_cast<uint32_t*>(og + (size_t)row1 * C) = v1;
+          }
+        }
       }
-      if (mine) {
-        const uint32_t v0 = pack2(o[v][0] * inv0, o[v][1] * inv0), v1 = pack2(o[v][2] * inv1, o[v][3] * inv1);
-        if (C == 64) {
-          *reinterpret_cast<uint32_t*>(os + row0 * PQ + col) = v0;
-          *reinterpret_cast<uint32_t*>(os + row1 * PQ + col) = v1;
-        } else {
-          __nv_bfloat16* og = p.o_out + (size_t)w * kTok * C + hg * 64 + col;
-          if (row0 < kTok) *reinterpret_cast<uint32_t*>(og + (size_t)row0 * C) = v0;
-          if (row1 < kTok) *reinterpret_cast<uint32_t*>(og + (size_t)row1 * C) = v1;
+    } else {
+      // special unit: P [16 heads x keys] . V [keys x 64 channels]; row g keeps the 4 channels of head g.
+      // Two passes of four channel tiles keep the register footprint under the 2-CTA budget.
+      float ol[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        float o[4][4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) o[v][0] = o[v][1] = o[v][2] = o[v][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < KSTEPS; ++kk) {
+          uint32_t pa[4];
+          p_frag(kk, pa);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            uint32_t vb0, vb1;
+            ldsm_x2_trans(vb0, vb1, vs_u32 + (uint32_t)(((kk * 16 + (lane & 15)) * PQ + (pass * 4 + v) * 8) * 2));
+            mma16816(o[v], pa, vb0, vb1);
+          }
+          if (pass == 0) mma16816(ol, pa, kOnes, kOnes);
+        }
+        const float inv0 = 1.0f / ol[0], inv1 = 1.0f / ol[2];
+        // channel tile pass*4 + v holds heads 2(pass*4 + v), +1: pass 0 -> heads 0..7 = tile rows g, pass 1 -> rows g + 8
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          if ((g >> 1) == v && (t >> 1) == (g & 1)) {
+            const int head = pass * 8 + g;
+            const float a = pass == 0 ? o[v][0] * inv0 : o[v][2] * inv1;
+            const float b = pass == 0 ? o[v][1] * inv0 : o[v][3] * inv1;
+            *reinterpret_cast<uint32_t*>(os + 48 * PQ + head * 4 + 2 * (t & 1)) = pack2(a, b);
+          }
         }
       }
     }
