@@ -191,79 +191,94 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
   __syncthreads();
 
   // ---- gather + LayerNorm: 8 lanes per token, 4 tokens per warp pass ----------------------------------
+  // The loads of NB passes are issued together (independent global reads in flight) before any of them is reduced.
   {
     constexpr int NCH = C / 64;
+    constexpr int NPASS = XROWS / 32;             // passes per warp (XROWS = 64, 112 or 160 -> 2, 3.5, 5)
+    constexpr int NB = C == 64 ? 5 : 2;           // passes batched (register budget: NB * NCH * 8 floats)
     const int j = lane & 7, sub = lane >> 3;
-    for (int n0 = warp * 4; n0 < XROWS; n0 += 32) {
-      const int n = n0 + sub;
-      const float* src = nullptr;
-      if (n < n_kv) {
-        const int d = n / kTok, tok = n - d * kTok;
-        const int pix = pix_s[tok];
-        const float* fr = p.frames[0];
+    for (int pb = 0; pb * 32 * NB < XROWS; ++pb) {
+      float v[NB][NCH][8];
+      int nn[NB];
 #pragma unroll
-        for (int q = 1; q < 8; ++q) fr = (d == q) ? p.frames[q] : fr;
-        if (fr != nullptr && pix >= 0) src = fr + (size_t)pix * C + j * 8;
-      }
-      float v[NCH][8];
-      float sum = 0.f;
+      for (int b = 0; b < NB; ++b) {
+        const int n = (pb * NB + b) * 32 + warp * 4 + sub;
+        nn[b] = n;
+        const float* src = nullptr;
+        if (n < n_kv) {
+          const int d = n / kTok, tok = n - d * kTok;
+          const int pix = pix_s[tok];
+          const float* fr = p.frames[0];
 #pragma unroll
-      for (int kb = 0; kb < NCH; ++kb) {
-        if (src != nullptr) {
-          const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + kb * 64));
-          const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + kb * 64 + 4));
-          v[kb][0] = t0.x; v[kb][1] = t0.y; v[kb][2] = t0.z; v[kb][3] = t0.w;
-          v[kb][4] = t1.x; v[kb][5] = t1.y; v[kb][6] = t1.z; v[kb][7] = t1.w;
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[kb][e] = 0.f;
+          for (int q = 1; q < 8; ++q) fr = (d == q) ? p.frames[q] : fr;
+          if (fr != nullptr && pix >= 0) src = fr + (size_t)pix * C + j * 8;
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) sum += v[kb][e];
-      }
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-      const float mean = sum / (float)C;
-      float sq = 0.f;
+        for (int kb = 0; kb < NCH; ++kb) {
+          if (src != nullptr) {
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + kb * 64));
+            const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + kb * 64 + 4));
+            v[b][kb][0] = t0.x; v[b][kb][1] = t0.y; v[b][kb][2] = t0.z; v[b][kb][3] = t0.w;
+            v[b][kb][4] = t1.x; v[b][kb][5] = t1.y; v[b][kb][6] = t1.z; v[b][kb][7] = t1.w;
+          } else {
 #pragma unroll
-      for (int kb = 0; kb < NCH; ++kb)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float dlt = v[kb][e] - mean;
-          v[kb][e] = dlt;
-          sq += dlt * dlt;
+            for (int e = 0; e < 8; ++e) v[b][kb][e] = 0.f;
+          }
         }
-      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-      sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-      sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-      const float rstd = 1.0f / sqrtf(sq / (float)C + 1e-5f);
+      }
 #pragma unroll
-      for (int kb = 0; kb < NCH; ++kb) {
-        uint4 pk;
-        pk.x = pack2(v[kb][0] * rstd, v[kb][1] * rstd);
-        pk.y = pack2(v[kb][2] * rstd, v[kb][3] * rstd);
-        pk.z = pack2(v[kb][4] * rstd, v[kb][5] * rstd);
-        pk.w = pack2(v[kb][6] * rstd, v[kb][7] * rstd);
-        *reinterpret_cast<uint4*>(xn + (size_t)n * PX + kb * 64 + j * 8) = pk;
+      for (int b = 0; b < NB; ++b) {
+        if (nn[b] >= XROWS) continue;   // warp-uniform up to the 4-token granularity of XROWS (a multiple of 16)
+        float sum = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < NCH; ++kb)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sum += v[b][kb][e];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        const float mean = sum / (float)C;
+        float sq = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < NCH; ++kb)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float dlt = v[b][kb][e] - mean;
+            v[b][kb][e] = dlt;
+            sq += dlt * dlt;
+          }
+        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+        const float rstd = 1.0f / sqrtf(sq / (float)C + 1e-5f);
+#pragma unroll
+        for (int kb = 0; kb < NCH; ++kb) {
+          uint4 pk;
+          pk.x = pack2(v[b][kb][0] * rstd, v[b][kb][1] * rstd);
+          pk.y = pack2(v[b][kb][2] * rstd, v[b][kb][3] * rstd);
+          pk.z = pack2(v[b][kb][4] * rstd, v[b][kb][5] * rstd);
+          pk.w = pack2(v[b][kb][6] * rstd, v[b][kb][7] * rstd);
+          *reinterpret_cast<uint4*>(xn + (size_t)nn[b] * PX + kb * 64 + j * 8) = pk;
+        }
       }
     }
+    (void)NPASS;
   }
 
   // ---- q, k, v projections (mma.sync): warp = (n-tile pair, m half) --------------------------------------
   const int npair = warp & 3, mh = warp >> 2;
   const uint32_t xn_u32 = sb + Cfg::OFF_XN;
   constexpr int MTK = (KSTEPS + 1) / 2;  // k / v m-tiles per warp
+  if (NW == 3) {  // all three weight slices were loaded up front: one barrier covers them and the LayerNorm'ed tokens
+    cpa_wait<0>();
+    __syncthreads();
+  }
   for (int which = 0; which < 3; ++which) {
-    // slices were committed in order: wait until slice `which` has landed
-    if (which == 0) {
-      if (NW == 3) cpa_wait<2>(); else cpa_wait<1>();
-    } else if (which == 1) {
-      if (NW == 3) cpa_wait<1>(); else cpa_wait<1>();
-    } else {
-      cpa_wait<0>();
+    if (NW != 3) {
+      // slices were committed in order: wait until slice `which` has landed
+      if (which == 2) cpa_wait<0>(); else cpa_wait<1>();
+      __syncthreads();  // slice + (first pass) the LayerNorm'ed tokens visible to every warp
     }
-    __syncthreads();  // slice + (first pass) the LayerNorm'ed tokens visible to every warp
     const uint32_t w_base = sb + Cfg::OFF_W + (uint32_t)((which % NW) * 64 * PX * 2);
     const float* bsrc = p.bqkv + which * C + hg * 64 + npair * 16 + 2 * t;
     const float2 bia0 = __ldg(reinterpret_cast<const float2*>(bsrc));
