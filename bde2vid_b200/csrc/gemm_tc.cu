@@ -499,6 +499,10 @@ int fill_params(const bde_gemm_desc* d, TcParams& p, bool& ln) {
 }  // namespace tc
 
 int gemm_tcgen05_persistent(const bde_gemm_desc* d, cudaStream_t s);
+namespace tc {
+bool conv_tma_eligible(const TcParams& p, bool ln);
+int conv_tma_launch(const bde_gemm_desc* d, const TcParams& p, cudaStream_t s);
+}  // namespace tc
 
 int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s) {
   using namespace tc;
@@ -511,6 +515,8 @@ int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s) {
   int rc0 = fill_params(d, p, ln);
   if (rc0 != 0) return rc0;
   if (p.M == 0) return 0;
+  // convolutions over 64-channel slabs: persistent kernel with both operands fed by the TMA (gemm_tc_conv.cu)
+  if (conv_tma_eligible(p, ln)) return conv_tma_launch(d, p, s);
   // tile width: widest tile that still gives most SMs work (measured on the LSTM / encoder shapes: a 256-wide tile
   // gathers the A operand half as often and wins as soon as it yields >= ~100 CTAs; tools/tc_phase_probe.py bn)
   int bn = 32;
