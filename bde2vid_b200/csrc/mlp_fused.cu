@@ -212,18 +212,302 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
   }
 }
 
+
+// =====================================================================================================================
+// C = 256, hidden = 1024 (attention level 3 of the assumed cfg).  Same contract, different schedule: the hidden
+// activation is produced and consumed in 8 chunks of 128 columns so that it never exceeds 2 x 32 KB of shared memory:
+//
+//   acc1[a] (128 TMEM cols, double buffered) = LN(x) [128 x 256] . W1[chunk j]^T          (fc1, N = 128, K = 256)
+//   H[a]    (bf16, swizzled K-major, double buffered) = GELU(acc1[a] + b1[chunk j])        (epilogue warps)
+//   acc2    (256 TMEM cols) += H[a] [128 x 128] . W2[:, chunk j]^T                         (fc2, N = 256, K = 128)
+//
+// so the tensor core works on chunk j + 1 / j - 1 while the eight epilogue warps run the GELU of chunk j.
+//   warps 0-7  LayerNorm producer, GELU epilogues, final residual epilogue      warp 8  TMA (weights, 32 KB ring stages)
+//   warp 9     MMA issuer (owns the 512 TMEM columns)
+// One CTA per 128 rows (46 CTAs for four 33 x 44 maps); replaces two GEMM launches whose 276 CTAs each re-derived the
+// LayerNorm or round-tripped the [rows x 1024] hidden tensor through HBM.
+constexpr int kM3C = 256, kM3H = 1024, kM3Chunk = 128, kM3NChunks = kM3H / kM3Chunk;
+constexpr int kM3Threads = kNumProducerThreads + 64;
+constexpr int kM3Stage = 32768, kM3Stages = 3;
+constexpr int kM3OffXn = 0;                                  // 4 slabs x 16 KB
+constexpr int kM3OffH = 65536;                               // 2 buffers x (2 slabs x 16 KB)
+constexpr int kM3OffW = 131072;                              // ring
+constexpr int kM3OffBar = kM3OffW + kM3Stages * kM3Stage;
+constexpr int kM3Smem = kM3OffBar + 256 + 1024;
+
+struct Mlp3Params {
+  float* x;          // [P, 256] in / out
+  const float* b1;   // [1024]
+  const float* b2;   // [256]
+  int P;
+};
+
+__global__ void __launch_bounds__(kM3Threads, 1)
+mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2, const Mlp3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sb - smem_u32(smem_raw));
+  const uint32_t s_xn = sb + kM3OffXn, s_h = sb + kM3OffH, s_w = sb + kM3OffW;
+  const uint32_t bar0 = sb + kM3OffBar;
+  const uint32_t bar_xn = bar0;                    // 8
+  const uint32_t bar_wfull = bar0 + 8;             // 3 x 8
+  const uint32_t bar_wempty = bar0 + 32;           // 3 x 8
+  const uint32_t bar_a1full = bar0 + 56;           // 2 x 8
+  const uint32_t bar_a1empty = bar0 + 72;          // 2 x 8
+  const uint32_t bar_hfull = bar0 + 88;            // 2 x 8
+  const uint32_t bar_hempty = bar0 + 104;          // 2 x 8
+  const uint32_t bar_a2full = bar0 + 120;          // 8
+  const uint32_t tmem_slot = bar0 + 128;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar_xn, kNumProducerThreads);
+    for (int s = 0; s < kM3Stages; ++s) {
+      mbar_init(bar_wfull + 8 * s, 1);
+      mbar_init(bar_wempty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_a1full + 8 * a, 1);
+      mbar_init(bar_a1empty + 8 * a, kNumProducerWarps);
+      mbar_init(bar_hfull + 8 * a, kNumProducerThreads);
+      mbar_init(bar_hempty + 8 * a, 1);
+    }
+    mbar_init(bar_a2full, 1);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + kM3OffBar + 128);
+  const uint32_t acc2 = tmem_base + 256;   // acc1[a] = tmem_base + 128 a
+
+  if (warp < kNumProducerWarps) {
+    // ---------------- LayerNorm producer (affine folded into W1 / b1 by the caller) ------------------------------------
+    {
+      const int j = lane & 7, rsub = lane >> 3;
+#pragma unroll 2
+      for (int i = 0; i < kRowsPerThread; ++i) {
+        const int row = warp * (4 * kRowsPerThread) + i * 4 + rsub;
+        const int mm = m0 + row;
+        float v[4][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          if (mm < p.P) {
+            const float* src = p.x + (size_t)mm * kM3C + kb * 64 + j * 8;
+            const float4 t0 = *reinterpret_cast<const float4*>(src), t1 = *reinterpret_cast<const float4*>(src + 4);
+            v[kb][0] = t0.x; v[kb][1] = t0.y; v[kb][2] = t0.z; v[kb][3] = t0.w;
+            v[kb][4] = t1.x; v[kb][5] = t1.y; v[kb][6] = t1.z; v[kb][7] = t1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[kb][e] = 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sum += v[kb][e];
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        const float mean = sum / (float)kM3C;
+        float sq = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            v[kb][e] -= mean;
+            sq += v[kb][e] * v[kb][e];
+          }
+        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+        const float rstd = 1.0f / sqrtf(sq / (float)kM3C + 1e-5f);
+        const uint32_t dst = s_xn + (uint32_t)row * 128u + (((uint32_t)j ^ (uint32_t)(row & 7)) << 4);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = v[kb][e] * rstd;
+          const uint4 pk = pack8_bf16(o);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kb * (BM * 128)), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w)
+                       : "memory");
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_xn);
+    }
+    // ---------------- GELU epilogues: thread = tile row, 64 hidden columns of the chunk per warp half ------------------
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+#pragma unroll 1
+    for (int jc = 0; jc < kM3NChunks; ++jc) {
+      const uint32_t a = jc & 1, ph = (jc >> 1) & 1;
+      mbar_wait(bar_a1full + 8 * a, ph);
+      tcgen05_fence_after();
+      uint32_t raw0[32], raw1[32];
+      tmem_ld_32x32b_x32(tmem_base + a * 128 + lane_off + (uint32_t)(half * 64), raw0);
+      tmem_ld_32x32b_x32(tmem_base + a * 128 + lane_off + (uint32_t)(half * 64 + 32), raw1);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a1empty + 8 * a);   // fc1 of chunk jc + 2 may overwrite the accumulator
+      mbar_wait(bar_hempty + 8 * a, ph ^ 1u);            // fc2 of chunk jc - 2 has finished reading H[a]
+      const float* b1p = p.b1 + jc * kM3Chunk + half * 64;
+      const uint32_t hrow = s_h + a * 32768 + (uint32_t)half * (BM * 128) + (uint32_t)row * 128u;   // slab `half` of H[a]
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float4 bA = __ldg(reinterpret_cast<const float4*>(b1p + jj * 8)), bB = __ldg(reinterpret_cast<const float4*>(b1p + jj * 8 + 4));
+        const uint32_t* r = jj < 4 ? raw0 + jj * 8 : raw1 + (jj - 4) * 8;
+        float o[8];
+        o[0] = fast_gelu(__uint_as_float(r[0]) + bA.x); o[1] = fast_gelu(__uint_as_float(r[1]) + bA.y);
+        o[2] = fast_gelu(__uint_as_float(r[2]) + bA.z); o[3] = fast_gelu(__uint_as_float(r[3]) + bA.w);
+        o[4] = fast_gelu(__uint_as_float(r[4]) + bB.x); o[5] = fast_gelu(__uint_as_float(r[5]) + bB.y);
+        o[6] = fast_gelu(__uint_as_float(r[6]) + bB.z); o[7] = fast_gelu(__uint_as_float(r[7]) + bB.w);
+        const uint4 pk = pack8_bf16(o);
+        const uint32_t dst = hrow + ((((uint32_t)jj) ^ (uint32_t)(row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(bar_hfull + 8 * a);
+    }
+    // ---------------- final epilogue: x += acc2 + b2, coalesced through a per-warp smem transpose (XN region is free) ---
+    mbar_wait(bar_a2full, 0);
+    tcgen05_fence_after();
+    float* stg = reinterpret_cast<float*>(sgen + kM3OffXn) + warp * 1024;
+    const int rq = lane >> 3, cq4 = lane & 7;
+#pragma unroll 1
+    for (int cb = half * 32; cb < kM3C; cb += 64) {
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(acc2 + lane_off + (uint32_t)cb, raw);
+      tmem_ld_wait();
+      __syncwarp();
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
+            make_float4(__uint_as_float(raw[4 * j4]), __uint_as_float(raw[4 * j4 + 1]), __uint_as_float(raw[4 * j4 + 2]),
+                        __uint_as_float(raw[4 * j4 + 3]));
+      __syncwarp();
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + cb + cq4 * 4));
+      float4 cur[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int mm = m0 + q * 32 + it * 4 + rq;
+        cur[it] = mm < p.P ? *reinterpret_cast<const float4*>(p.x + (size_t)mm * kM3C + cb + cq4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + rq;
+        const int mm = m0 + q * 32 + r;
+        const float4 acc = *reinterpret_cast<const float4*>(stg + r * 32 + ((cq4 ^ (r & 7)) << 2));
+        if (mm < p.P)
+          *reinterpret_cast<float4*>(p.x + (size_t)mm * kM3C + cb + cq4 * 4) =
+              make_float4(cur[it].x + acc.x + bb.x, cur[it].y + acc.y + bb.y, cur[it].z + acc.z + bb.z, cur[it].w + acc.w + bb.w);
+      }
+    }
+    tcgen05_fence_before();
+  } else if (warp == kTmaWarp) {
+    // ---------------- weight loads, in the order the MMA warp consumes them ----------------------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      auto load_w1 = [&](int chunk, int i) {   // item i of fc1(chunk): k slabs 2i, 2i + 1 of W1 rows [128 chunk, +128)
+        const uint32_t s = it % kM3Stages;
+        mbar_wait(bar_wempty + 8 * s, ((it / kM3Stages) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar_wfull + 8 * s, kM3Stage);
+        tma_load_2d(s_w + s * kM3Stage, &tmap_w1, bar_wfull + 8 * s, (2 * i) * BK, chunk * kM3Chunk);
+        tma_load_2d(s_w + s * kM3Stage + 16384, &tmap_w1, bar_wfull + 8 * s, (2 * i + 1) * BK, chunk * kM3Chunk);
+        ++it;
+      };
+      auto load_w2 = [&](int chunk, int i) {   // item i of fc2(chunk): k slab 2 chunk + i of W2 (all 256 rows)
+        const uint32_t s = it % kM3Stages;
+        mbar_wait(bar_wempty + 8 * s, ((it / kM3Stages) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar_wfull + 8 * s, kM3Stage);
+        tma_load_2d(s_w + s * kM3Stage, &tmap_w2, bar_wfull + 8 * s, (2 * chunk + i) * BK, 0);
+        ++it;
+      };
+      load_w1(0, 0); load_w1(0, 1);
+      load_w1(1, 0); load_w1(1, 1);
+      for (int jc = 0; jc < kM3NChunks; ++jc) {
+        load_w2(jc, 0); load_w2(jc, 1);
+        if (jc + 2 < kM3NChunks) { load_w1(jc + 2, 0); load_w1(jc + 2, 1); }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---------------- MMA issuer --------------------------------------------------------------------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc(kM3Chunk), idesc2 = make_idesc(kM3C);
+      uint32_t it = 0;
+      auto fc1 = [&](int chunk) {
+        const uint32_t a = chunk & 1;
+        mbar_wait(bar_a1empty + 8 * a, ((chunk >> 1) & 1u) ^ 1u);   // the epilogue drained this accumulator (chunk - 2)
+        tcgen05_fence_after();
+        for (int i = 0; i < 2; ++i, ++it) {
+          const uint32_t s = it % kM3Stages;
+          mbar_wait(bar_wfull + 8 * s, (it / kM3Stages) & 1u);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int sl = 0; sl < 2; ++sl) {
+            const uint64_t adesc = make_smem_desc(s_xn + (2 * i + sl) * (BM * 128)), bdesc = make_smem_desc(s_w + s * kM3Stage + sl * 16384);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_base + a * 128, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, (i | sl | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_wempty + 8 * s);
+        }
+        umma_commit(bar_a1full + 8 * a);
+      };
+      mbar_wait(bar_xn, 0);
+      fc1(0);
+      fc1(1);
+      for (int jc = 0; jc < kM3NChunks; ++jc) {
+        const uint32_t a = jc & 1;
+        mbar_wait(bar_hfull + 8 * a, (jc >> 1) & 1u);
+        tcgen05_fence_after();
+        for (int i = 0; i < 2; ++i, ++it) {
+          const uint32_t s = it % kM3Stages;
+          mbar_wait(bar_wfull + 8 * s, (it / kM3Stages) & 1u);
+          tcgen05_fence_after();
+          const uint64_t adesc = make_smem_desc(s_h + a * 32768 + i * (BM * 128)), bdesc = make_smem_desc(s_w + s * kM3Stage);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(acc2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (jc | i | k) != 0 ? 1u : 0u);
+          umma_commit(bar_wempty + 8 * s);
+        }
+        umma_commit(bar_hempty + 8 * a);   // H[a] may be rewritten once these MMAs have read it
+        if (jc + 2 < kM3NChunks) fc1(jc + 2);
+      }
+      umma_commit(bar_a2full);
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace tc
 }  // namespace bde
 
 using namespace bde;
 
-extern "C" int bde_mlp_fused_supported(int c, int hidden) { return (c == tc::kMlpC && hidden == tc::kMlpH) ? 1 : 0; }
+extern "C" int bde_mlp_fused_supported(int c, int hidden) {
+  return ((c == tc::kMlpC && hidden == tc::kMlpH) || (c == tc::kM3C && hidden == tc::kM3H)) ? 1 : 0;
+}
 
 extern "C" int bde_mlp_fused(float* x, size_t rows, int c, int hidden, const void* w1, const float* b1, const void* w2,
                              const float* b2, void* stream) {
   using namespace bde::tc;
   if (rows == 0) return 0;
-  BDE_REQUIRE(bde_mlp_fused_supported(c, hidden) == 1, "bde_mlp_fused: only c = 64, hidden = 256 is implemented (got %d, %d)", c, hidden);
+  BDE_REQUIRE(bde_mlp_fused_supported(c, hidden) == 1, "bde_mlp_fused: (c, hidden) must be (64, 256) or (256, 1024) (got %d, %d)", c, hidden);
   BDE_REQUIRE(x != nullptr && w1 != nullptr && w2 != nullptr && b1 != nullptr && b2 != nullptr, "bde_mlp_fused: null operand");
   BDE_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)w1) & 127) == 0 && (((uintptr_t)w2) & 127) == 0,
               "bde_mlp_fused: operands must be 16-byte (weights 128-byte) aligned");
@@ -231,6 +515,22 @@ extern "C" int bde_mlp_fused(float* x, size_t rows, int c, int hidden, const voi
   CUtensorMap t1, t2;
   memset(&t1, 0, sizeof(t1));
   memset(&t2, 0, sizeof(t2));
+  if (c == kM3C) {
+    int rc3 = get_weight_tmap(w1, kM3H, kM3C, kM3Chunk, &t1);   // boxes [64 k x 128 n]
+    if (rc3 != 0) return rc3;
+    rc3 = get_weight_tmap(w2, kM3C, kM3H, kM3C, &t2);           // boxes [64 k x 256 n]
+    if (rc3 != 0) return rc3;
+    static bool configured3 = false;
+    if (!configured3) {
+      cudaError_t e = cudaFuncSetAttribute(mlp_fused256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kM3Smem);
+      BDE_REQUIRE(e == cudaSuccess, "bde_mlp_fused: smem attribute: %s", cudaGetErrorString(e));
+      configured3 = true;
+    }
+    Mlp3Params p3;
+    p3.x = x; p3.b1 = b1; p3.b2 = b2; p3.P = (int)rows;
+    mlp_fused256_kernel<<<(unsigned)ceil_div(rows, BM), kM3Threads, kM3Smem, (cudaStream_t)stream>>>(t1, t2, p3);
+    return check_launch("mlp_fused256_kernel");
+  }
   int rc = get_weight_tmap(w1, kMlpH, kMlpC, kMlpH, &t1);   // one box [64 k x 256 n]
   if (rc != 0) return rc;
   rc = get_weight_tmap(w2, kMlpC, kMlpH, kMlpC, &t2);       // boxes [64 k x 64 n]

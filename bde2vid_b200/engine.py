@@ -147,6 +147,12 @@ class Engine:
 
         with torch.no_grad():
             self.head = conv_layer(gen.head.conv2d, 1, cin_pad=VOX_CPAD)
+            # dedicated first-layer kernel (planar fp32 voxels -> NHWC bf16, no packing pass): 32 channels, 5x5
+            hw = gen.head.conv2d.weight
+            self.head_direct = None
+            if (tc and hw.shape[0] == 32 and hw.shape[-1] == 5 and hw.shape[1] <= 6
+                    and os.environ.get("BDE2VID_HEAD_CONV", "1") != "0"):
+                self.head_direct = (f32(hw), f32(gen.head.conv2d.bias))
             self.enc = []
             for l in range(self.L):
                 self.enc.append(dict(
@@ -377,10 +383,14 @@ class _Plan:
                 ops.voxelize_seq_into(xs, ys, ts, ps, self.ev_off[b], eng.bins, H, W, pt, pl, Hp, Wp,
                                       self.vox_in[0, b], B * eng.bins * Hp * Wp, oob_count=self.oob)
                 self.launches += 1
-        ops.pack_voxel_nhwc(self.vox_in.view(N, eng.bins, Hp, Wp), VOX_CPAD, eng.dtype, out=self.vox8)
         # A: head conv + ReLU over all frames (...V5.py:116)
-        eng._gemm(eng.head, self.vox8, self.head, N, Hp, Wp, VOX_CPAD, act=ACT_RELU)
-        self.launches += 2
+        if eng.head_direct is not None:
+            ops.head_conv(self.vox_in.view(N, eng.bins, Hp, Wp), eng.head_direct[0], eng.head_direct[1], self.head, act=ACT_RELU)
+            self.launches += 1
+        else:
+            ops.pack_voxel_nhwc(self.vox_in.view(N, eng.bins, Hp, Wp), VOX_CPAD, eng.dtype, out=self.vox8)
+            eng._gemm(eng.head, self.vox8, self.head, N, Hp, Wp, VOX_CPAD, act=ACT_RELU)
+            self.launches += 2
         x, xc, xh, xw = self.head, eng.bc, Hp, Wp
         for l in range(eng.L):
             d, e = self.lv[l], eng.enc[l]

@@ -52,6 +52,17 @@ def pack_voxel_nhwc(vox, c_pad, dtype, out=None):
     return out
 
 
+def head_conv(vox, w, bias, out, act=ACT_RELU):
+    """float32 planar [N, Cin, H, W] voxels x float32 [32, Cin, 5, 5] weights -> bf16 NHWC [N, H, W, 32]."""
+    lib = _lib.require_device()
+    N, cin, H, W = vox.shape
+    cout, _, k, _ = w.shape
+    assert vox.dtype == torch.float32 and w.dtype == torch.float32 and out.dtype == torch.bfloat16
+    assert vox.is_contiguous() and w.is_contiguous() and out.is_contiguous()
+    check(lib.bde_head_conv(ptr(vox), ptr(w), ptr(bias), ptr(out), N, cin, H, W, cout, k, act, stream_ptr()), "bde_head_conv")
+    return out
+
+
 def gemm(a0, w, bias, out, *, n_img, h_in, w_in, c0, n, ksize=1, stride=1, pad=0, a1=None, c1=0, w_ld=0,
          epi=EPI_STORE, act=ACT_NONE, out_f32=False, residual=None, c_prev=None, c_out=None, row_map=None,
          out2=None, engine=ENGINE_SIMT, dtype=None, k_order=0, ln_frames=None, ln_tok_map=None, ln_n_tok=1,

@@ -73,6 +73,15 @@ int bde_voxelize_seq_strided(const float* xs, const float* ys, const float* ts, 
                              int pad_top, int pad_left, int Hp, int Wp,
                              float* out, size_t out_window_stride, int* oob_count, int algo, void* stream);
 
+/* Head convolution straight from the voxeliser's planar grid (model/BDE2VID/bde2vid_cross_scale_propogation_V5.py:116,
+ * ConvLayer model/BDE2VID/submodules.py:85-114):  out = act(conv5x5(vox) + bias)
+ *   vox : float32 [n_img, cin, h, w] planar (cin = num_bins <= 6)    w : float32 [32, cin, 5, 5] (checkpoint layout)
+ *   out : bf16 NHWC [n_img, h, w, 32]                                act: BDE_ACT_NONE / RELU / RELU6
+ * Operands are rounded to bf16, accumulation is fp32 (mma.sync).  Replaces bde_pack_voxel_nhwc + bde_gemm for the
+ * 5-channel first layer, where an im2col gather moves 16 bytes per tap. */
+int bde_head_conv(const float* vox, const float* w, const float* bias, void* out, int n_img, int cin, int h, int w_px,
+                  int cout, int ksize, int act, void* stream);
+
 /* planar voxel grids float32[T, bins, Hp, Wp] -> NHWC with channels padded to c_pad (zeros),
  * element type `dtype`.  Feeds the head convolution (bde2vid_cross_scale_propogation_V5.py:116). */
 int bde_pack_voxel_nhwc(const float* vox, int T, int bins, int Hp, int Wp, int c_pad,

@@ -182,15 +182,17 @@ def test_ln_gather_qkv(dtype, C):
 
 
 @pytest.mark.parametrize("rows", [128, 1000, 23232])
-def test_mlp_fused(rows):
-    """x += fc2(GELU(fc1(LN(x)))) in one tcgen05 kernel vs fp32 torch on bf16-rounded weights (DTransformer.py:279-304)."""
+@pytest.mark.parametrize("C", [64, 256])
+def test_mlp_fused(rows, C):
+    """x += fc2(GELU(fc1(LN(x)))) in one tcgen05 kernel vs fp32 torch on bf16-rounded weights (DTransformer.py:279-304);
+    C = 64 / hidden 256 (level 1) and C = 256 / hidden 1024 (level 3, hidden chunked through shared memory)."""
     from bde2vid_b200 import ops
-    g = torch.Generator().manual_seed(rows)
-    C, Hd = 64, 256
+    g = torch.Generator().manual_seed(rows + C)
+    Hd = 4 * C
     x = torch.randn(rows, C, generator=g) * 2 + 0.3
     gamma, beta = 1 + 0.2 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
-    W1, b1 = torch.randn(Hd, C, generator=g) / 8, torch.randn(Hd, generator=g) * 0.1
-    W2, b2 = torch.randn(C, Hd, generator=g) / 16, torch.randn(C, generator=g) * 0.1
+    W1, b1 = torch.randn(Hd, C, generator=g) / C ** 0.5, torch.randn(Hd, generator=g) * 0.1
+    W2, b2 = torch.randn(C, Hd, generator=g) / Hd ** 0.5, torch.randn(C, generator=g) * 0.1
     w1f = (W1 * gamma[None, :]).to(torch.bfloat16)
     b1f = W1 @ beta + b1
     w2f = W2.to(torch.bfloat16)
@@ -201,7 +203,27 @@ def test_mlp_fused(rows):
     ops.mlp_fused(xd, rows, C, Hd, w1f.to(DEV).contiguous(), b1f.to(DEV), w2f.to(DEV).contiguous(), b2.to(DEV))
     torch.cuda.synchronize()
     err = float((xd.cpu() - ref).abs().max())
-    print("mlp_fused", rows, err)
+    print("mlp_fused", rows, C, err)
     assert err <= 2e-2     # bf16 rounding of the hidden activations at values of order 1..8
     full = x + F.gelu(F.layer_norm(x, (C,), gamma, beta, 1e-5) @ W1.t() + b1) @ W2.t() + b2
     assert float((xd.cpu() - full).abs().max()) <= 6e-2
+
+
+@pytest.mark.parametrize("shape", [(3, 5, 40, 56), (2, 5, 33, 47), (1, 3, 16, 32), (2, 6, 19, 70)])
+def test_head_conv(shape):
+    """5x5 head convolution straight from planar fp32 voxels (mma.sync, bf16 operands) vs torch conv2d on the same
+    bf16-rounded operands (...V5.py:116; ConvLayer submodules.py:85-114)."""
+    from bde2vid_b200 import ops
+    n, cin, h, w = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    vox = torch.randn(n, cin, h, w, generator=g) * (torch.rand(n, cin, h, w, generator=g) < 0.4)   # sparse, signed, like voxels
+    wt = torch.randn(32, cin, 5, 5, generator=g) / (25 * cin) ** 0.5
+    b = torch.randn(32, generator=g) * 0.1
+    ref = F.relu(F.conv2d(vox.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float(), b, padding=2))
+    out = torch.zeros(n, h, w, 32, dtype=torch.bfloat16, device=DEV)
+    ops.head_conv(vox.to(DEV).contiguous(), wt.to(DEV).contiguous(), b.to(DEV), out, act=ops.ACT_RELU)
+    torch.cuda.synchronize()
+    got = out.float().cpu().permute(0, 3, 1, 2)
+    err = float((got - ref).abs().max())
+    print("head_conv", shape, err, float(ref.abs().max()))
+    assert err <= 1e-2 * max(1.0, float(ref.abs().max()))
