@@ -49,6 +49,7 @@ EXPORTS = {
     "bde_pack_voxel_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_void_p]),
     "bde_profile_begin": (C.c_int, [C.c_int]),
     "bde_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "bde_profile_flops": (C.c_int, [C.POINTER(C.c_double)]),
     "bde_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     "bde_add": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                           C.c_void_p]),

@@ -45,6 +45,7 @@ namespace {
 std::vector<cudaEvent_t> g_prof_ev;  // start/stop pairs
 size_t g_prof_used = 0;
 bool g_prof_on = false;
+double g_prof_flops = 0.0;  // 2 M N K of the profiled launches (K without padding)
 }  // namespace
 
 extern "C" int bde_profile_begin(int max_launches) {
@@ -52,6 +53,7 @@ extern "C" int bde_profile_begin(int max_launches) {
   g_prof_ev.clear();
   g_prof_used = 0;
   g_prof_on = false;
+  g_prof_flops = 0.0;
   if (max_launches <= 0) return 0;
   g_prof_ev.resize((size_t)max_launches * 2);
   for (auto& e : g_prof_ev)
@@ -78,6 +80,11 @@ extern "C" int bde_profile_end(double* total_ms, int* n_launches) {
   }
   if (total_ms != nullptr) *total_ms = tot;
   if (n_launches != nullptr) *n_launches = (int)n;
+  return 0;
+}
+
+extern "C" int bde_profile_flops(double* flops) {
+  if (flops != nullptr) *flops = g_prof_flops;
   return 0;
 }
 
@@ -109,6 +116,7 @@ extern "C" int bde_gemm(const bde_gemm_desc* d, void* stream) {
     if (prof) {
       cudaEventRecord(g_prof_ev[g_prof_used + 1], s);
       g_prof_used += 2;
+      g_prof_flops += 2.0 * d->n_img * d->h_out * d->w_out * (double)d->n * d->ksize * d->ksize * (d->c0 + d->c1);
     }
     return rc;
   }

@@ -335,29 +335,32 @@ __global__ void __launch_bounds__(kThreads, kMinCtas<BN, kDeep, kLn>) gemm_tc_ke
     }
   } else {
     // =============================== MMA issuer =========================================
-    if (lane == 0) {
+    // all lanes walk the loop, one elected lane issues (see elect_one_sync in tc_common.cuh)
+    {
       constexpr uint32_t idesc = make_idesc(BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % S;
         const uint32_t ph = (uint32_t)(kb / S) & 1u;
         mbar_wait(bar_full + 8 * s, ph);
-        if (kb == 0) BDE_DBG(4);
+        if (kb == 0 && lane == 0) BDE_DBG(4);
         // operands were written through the generic proxy (cp.async): order them before the
         // tensor core's async-proxy reads
         fence_proxy_async_smem();
         tcgen05_fence_after();
-        const uint64_t adesc = make_smem_desc(smem_a + s * Cfg::kABytes);
-        const uint64_t bdesc = make_smem_desc(smem_b + s * Cfg::kBBytes);
+        if (elect_one_sync()) {
+          const uint64_t adesc = make_smem_desc(smem_a + s * Cfg::kABytes);
+          const uint64_t bdesc = make_smem_desc(smem_b + s * Cfg::kBBytes);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
-          umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * s);  // frees the smem stage once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(bar_acc);  // accumulator complete
         }
-        umma_commit(bar_empty + 8 * s);  // frees the smem stage once these MMAs have read it
+        __syncwarp();
       }
-      umma_commit(bar_acc);  // accumulator complete
     }
-    __syncwarp();
   }
 
   __syncthreads();

@@ -64,9 +64,13 @@ struct CvParams {
   float act_lo, act_hi;    // kEpiStore: clamp bounds (-inf / 0, 6 / +inf)
 };
 
-template <int BN, bool kHalo, bool kPair>
+// NSUB = 2 ("dual tile", halo mode, narrow N): one CTA works on two neighbouring 8 x 16 tiles at once (one 8 x 32 halo
+// load, two TMEM accumulators) and alternates its MMAs between them.  With N <= 128 a tcgen05.mma takes ~105 cycles
+// however small N is -- consecutive MMAs into ONE accumulator are a dependent chain -- so two independent chains
+// nearly double the issue rate, and every weight tile is fetched once for 256 pixels instead of 128.
+template <int BN, bool kHalo, bool kPair, int NSUB = 1>
 struct CvCfg {
-  static constexpr int kABytes = kHalo ? kCvMaxHaloCols * kCvHaloPitch * 128 : BM * 128;
+  static constexpr int kABytes = kHalo ? (NSUB * kCvD2 + 4) * kCvHaloPitch * 128 : BM * 128;
   static constexpr int kBBytes = (kPair ? BN / 2 : BN) * 128;   // per CTA
   static constexpr int kEpiBytes = kCvEpiWarps * 4096;
   static constexpr int kBudget = 232448 - 1024 - 512 - kEpiBytes;
@@ -76,7 +80,8 @@ struct CvCfg {
   static constexpr int kSB = kSBraw < 8 ? kSBraw : 8;
   static constexpr int kSmemBytes = kSA * kABytes + kSB * kBBytes + kEpiBytes + 1024 + 512;
   static constexpr int kAccCols = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-  static constexpr int kTmemCols = 2 * kAccCols;
+  static constexpr int kTmemCols = 2 * NSUB * kAccCols;
+  static_assert(kTmemCols <= 512, "TMEM budget");
   static_assert(kSA >= 2 && kSB >= 2, "pipeline too shallow");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -167,7 +172,7 @@ struct CvTile {
   int img, u0, v0, n0;
   // group g: N tile g / groups_per_n, M tile (g % groups_per_n) * cs + rank (past the end: an all-zero dummy tile --
   // image index n_img is outside the tensor map, so the TMA fills zeros -- whose rows are never stored)
-  __device__ __forceinline__ void init(const CvParams& cp, int group, int rank, int cs, int bn) {
+  __device__ __forceinline__ void init(const CvParams& cp, int group, int rank, int cs, int bn, int nsub = 1) {
     const int gn = group / cp.groups_per_n;
     const int m_tile = (group - gn * cp.groups_per_n) * cs + rank;
     n0 = gn * bn;
@@ -176,23 +181,24 @@ struct CvTile {
     const int t = m_tile - img * per_img;
     const int t2 = t / cp.t1_tiles;
     u0 = (t - t2 * cp.t1_tiles) * kCvD1;
-    v0 = t2 * kCvD2;
+    v0 = t2 * kCvD2 * nsub;
   }
   // tile row r (TMEM lane) -> linear output pixel index, -1 outside the image
-  __device__ __forceinline__ int row_m(const CvParams& cp, int r) const {
-    const int u = u0 + (r & 7), v = v0 + (r >> 3);
+  __device__ __forceinline__ int row_m(const CvParams& cp, int r, int sub = 0) const {
+    const int u = u0 + (r & 7), v = v0 + sub * kCvD2 + (r >> 3);
     const int y = cp.swap ? u : v, x = cp.swap ? v : u;
     return (y < cp.p.h_out && x < cp.p.w_out && img < cp.p.n_img) ? (img * cp.p.h_out + y) * cp.p.w_out + x : -1;
   }
 };
 
-template <int BN, bool kHalo, int EPI, bool kPair>
+template <int BN, bool kHalo, int EPI, bool kPair, int NSUB>
 __global__ void __launch_bounds__(kCvThreads, 1)
 conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_a1,
                 const __grid_constant__ CUtensorMap tmap_b, const CvParams cp) {
-  using Cfg = CvCfg<BN, kHalo, kPair>;
+  using Cfg = CvCfg<BN, kHalo, kPair, NSUB>;
   constexpr int SA = Cfg::kSA, SB = Cfg::kSB;
   constexpr int CS = kPair ? 2 : 1;
+  static_assert(NSUB == 1 || (kHalo && !kPair), "dual tiles need the halo form");
   const TcParams& p = cp.p;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -248,8 +254,8 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
 
   const int ks = p.ksize;
   if (warp == 0) {
-    // =============================== TMA producer ========================================
-    if (lane == 0) {
+    // =============================== TMA producer (all lanes wait, one elected lane issues) ===
+    {
       uint32_t ia = 0, ib = 0;  // A / B stages issued so far
       // pair mode: "full" barriers live in the leader; its expect_tx covers the bytes of both CTAs
       const uint32_t afull0 = kPair ? mapa_cluster(bar_afull, 0) : bar_afull;
@@ -257,7 +263,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
       const uint32_t a_tx = (uint32_t)(kHalo ? cp.halo_bytes : BM * 128) * CS;
       for (int grp = group0; grp < cp.num_groups; grp += group_step) {
         CvTile tl;
-        tl.init(cp, grp, rank, CS, BN);
+        tl.init(cp, grp, rank, CS, BN, NSUB);
         const int o1 = tl.u0 * p.stride - p.pad, o2 = tl.v0 * p.stride - p.pad;  // input coordinate of tap (0, 0)
         const int nrow0 = tl.n0 + (kPair ? rank * (BN / 2) : 0);
         int kb = 0;
@@ -268,11 +274,14 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
           if (kHalo) {
             const uint32_t s = ia % SA;
             mbar_wait(bar_aempty + 8 * s, ((ia / SA) & 1u) ^ 1u);
-            if (!kPair || rank == 0) mbar_arrive_expect_tx(bar_afull + 8 * s, a_tx);
-            if (kPair)
-              tma_load_4d_pair(smem_a + s * Cfg::kABytes, am, afull0 + 8 * s, coff, o1, o2, tl.img);
-            else
-              tma_load_4d(smem_a + s * Cfg::kABytes, am, bar_afull + 8 * s, coff, o1, o2, tl.img);
+            if (elect_one_sync()) {
+              if (!kPair || rank == 0) mbar_arrive_expect_tx(bar_afull + 8 * s, a_tx);
+              if (kPair)
+                tma_load_4d_pair(smem_a + s * Cfg::kABytes, am, afull0 + 8 * s, coff, o1, o2, tl.img);
+              else
+                tma_load_4d(smem_a + s * Cfg::kABytes, am, bar_afull + 8 * s, coff, o1, o2, tl.img);
+            }
+            __syncwarp();
             ++ia;
           }
           for (int ky = 0; ky < ks; ++ky)
@@ -281,22 +290,28 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
                 const int k1 = cp.swap ? ky : kx, k2 = cp.swap ? kx : ky;
                 const uint32_t s = ia % SA;
                 mbar_wait(bar_aempty + 8 * s, ((ia / SA) & 1u) ^ 1u);
-                if (!kPair || rank == 0) mbar_arrive_expect_tx(bar_afull + 8 * s, a_tx);
-                if (kPair)
-                  tma_load_4d_pair(smem_a + s * Cfg::kABytes, am, afull0 + 8 * s, coff, o1 + k1, o2 + k2, tl.img);
-                else
-                  tma_load_4d(smem_a + s * Cfg::kABytes, am, bar_afull + 8 * s, coff, o1 + k1, o2 + k2, tl.img);
+                if (elect_one_sync()) {
+                  if (!kPair || rank == 0) mbar_arrive_expect_tx(bar_afull + 8 * s, a_tx);
+                  if (kPair)
+                    tma_load_4d_pair(smem_a + s * Cfg::kABytes, am, afull0 + 8 * s, coff, o1 + k1, o2 + k2, tl.img);
+                  else
+                    tma_load_4d(smem_a + s * Cfg::kABytes, am, bar_afull + 8 * s, coff, o1 + k1, o2 + k2, tl.img);
+                }
+                __syncwarp();
                 ++ia;
               }
               const uint32_t s = ib % SB;
               const long long w0 = dbg ? clock64() : 0;
               mbar_wait(bar_bempty + 8 * s, ((ib / SB) & 1u) ^ 1u);
               if (dbg) dbg_prod_wait += clock64() - w0;
-              if (!kPair || rank == 0) mbar_arrive_expect_tx(bar_bfull + 8 * s, (uint32_t)Cfg::kBBytes * CS);
-              if (kPair)
-                tma_load_2d_pair(smem_b + s * Cfg::kBBytes, &tmap_b, bfull0 + 8 * s, kb * BK, nrow0);
-              else
-                tma_load_2d(smem_b + s * Cfg::kBBytes, &tmap_b, bar_bfull + 8 * s, kb * BK, nrow0);
+              if (elect_one_sync()) {
+                if (!kPair || rank == 0) mbar_arrive_expect_tx(bar_bfull + 8 * s, (uint32_t)Cfg::kBBytes * CS);
+                if (kPair)
+                  tma_load_2d_pair(smem_b + s * Cfg::kBBytes, &tmap_b, bfull0 + 8 * s, kb * BK, nrow0);
+                else
+                  tma_load_2d(smem_b + s * Cfg::kBBytes, &tmap_b, bar_bfull + 8 * s, kb * BK, nrow0);
+              }
+              __syncwarp();
               ++ib;
             }
         }
@@ -305,7 +320,11 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // =============================== MMA issuer (pair mode: leader only) ================
-    if (lane == 0 && rank == 0) {
+    // The whole warp walks the loops (all lanes poll the barriers) and ONE elected lane issues the tcgen05
+    // instructions: with a guard that comes from elect.sync ptxas emits plain UTCHMMA / UTCBAR, whereas under
+    // `if (lane == 0)` it wraps every one of them in an ELECT ... BRA.U.ANY waterfall (~40 issue cycles per MMA, which
+    // is what capped narrow-N tiles at ~105 cycles per instruction).
+    if (rank == 0) {
       constexpr uint32_t idesc = make_idesc_mn(kPair ? 256 : 128, BN);
       uint32_t ia = 0, ib = 0, lt = 0;
       for (int grp = group0; grp < cp.num_groups; grp += group_step, ++lt) {
@@ -314,7 +333,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
         mbar_wait(bar_tempty + 8 * a, aph ^ 1u);  // the epilogue(s) drained this accumulator slot
         if (dbg) dbg_wait_acc += clock64() - w0;
         tcgen05_fence_after();
-        const uint32_t acc = tmem_acc + a * Cfg::kAccCols;
+        const uint32_t acc = tmem_acc + a * (NSUB * Cfg::kAccCols);
         uint32_t first = 1u;
         for (int ch = 0; ch < cp.nchunks; ++ch) {
           uint32_t sa = 0;
@@ -327,16 +346,15 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
           }
           for (int ky = 0; ky < ks; ++ky)
             for (int kx = 0; kx < ks; ++kx) {
-              uint64_t adesc;
+              uint32_t a_start;
               if (kHalo) {
                 const int k1 = cp.swap ? ky : kx, k2 = cp.swap ? kx : ky;
-                const uint32_t start = smem_a + sa * Cfg::kABytes + (uint32_t)(k2 * kCvHaloPitch + k1) * 128u;
-                adesc = make_smem_desc_sbo(start, kCvHaloPitch * 128u);
+                a_start = smem_a + sa * Cfg::kABytes + (uint32_t)(k2 * kCvHaloPitch + k1) * 128u;
               } else {
                 sa = ia % SA;
                 mbar_wait(bar_afull + 8 * sa, (ia / SA) & 1u);
                 ++ia;
-                adesc = make_smem_desc_sbo(smem_a + sa * Cfg::kABytes, 1024u);
+                a_start = smem_a + sa * Cfg::kABytes;
               }
               const uint32_t sb = ib % SB;
               const long long w2 = dbg ? clock64() : 0;
@@ -344,28 +362,36 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
               if (dbg) dbg_wait_ops += clock64() - w2;
               ++ib;
               tcgen05_fence_after();
-              const uint64_t bdesc = make_smem_desc(smem_b + sb * Cfg::kBBytes);
+              const bool last_tap = ky == ks - 1 && kx == ks - 1;
+              const bool last_kb = last_tap && ch == cp.nchunks - 1;
+              if (elect_one_sync()) {
+                const uint64_t adesc = make_smem_desc_sbo(a_start, kHalo ? kCvHaloPitch * 128u : 1024u);
+                const uint64_t bdesc = make_smem_desc(smem_b + sb * Cfg::kBBytes);
 #pragma unroll
-              for (int k = 0; k < BK / 16; ++k) {
-                if (kPair)
-                  umma_bf16_pair(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
-                else
-                  umma_bf16(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first ? 0u : 1u);
-                first = 0u;
+                for (int k = 0; k < BK / 16; ++k) {
+                  if (kPair) {
+                    umma_bf16_pair(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+                  } else {
+#pragma unroll
+                    for (int sub = 0; sub < NSUB; ++sub)   // sub-tile `sub`: 16 halo columns further, its own accumulator
+                      umma_bf16(acc + sub * Cfg::kAccCols, adesc + (uint64_t)(2 * k) + (uint64_t)(sub * ((kCvD2 * kCvHaloPitch * 128) >> 4)),
+                                bdesc + (uint64_t)(2 * k), idesc, (first && k == 0) ? 0u : 1u);
+                  }
+                }
+                if (kPair) {
+                  umma_commit_pair(bar_bempty + 8 * sb);
+                  if (!kHalo || last_tap) umma_commit_pair(bar_aempty + 8 * sa);
+                  if (last_kb) umma_commit_pair(bar_tfull + 8 * a);
+                } else {
+                  umma_commit(bar_bempty + 8 * sb);
+                  if (!kHalo || last_tap) umma_commit(bar_aempty + 8 * sa);
+                  if (last_kb) umma_commit(bar_tfull + 8 * a);
+                }
               }
-              if (kPair) {
-                umma_commit_pair(bar_bempty + 8 * sb);
-                if (!kHalo) umma_commit_pair(bar_aempty + 8 * sa);
-              } else {
-                umma_commit(bar_bempty + 8 * sb);
-                if (!kHalo) umma_commit(bar_aempty + 8 * sa);
-              }
+              __syncwarp();
+              first = 0u;
             }
-          if (kHalo) {
-            if (kPair) umma_commit_pair(bar_aempty + 8 * sa); else umma_commit(bar_aempty + 8 * sa);
-          }
         }
-        if (kPair) umma_commit_pair(bar_tfull + 8 * a); else umma_commit(bar_tfull + 8 * a);
       }
     }
     __syncwarp();
@@ -382,31 +408,34 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
       for (int grp = group0; grp < cp.num_groups; grp += group_step, ++lt) {
         const uint32_t a = lt & 1u, aph = (lt >> 1) & 1u;
         CvTile tl;
-        tl.init(cp, grp, rank, CS, BN);
-        const uint32_t lane_taddr = tmem_acc + a * Cfg::kAccCols + ((uint32_t)(q * 32) << 16);
+        tl.init(cp, grp, rank, CS, BN, NSUB);
         long long w1 = 0;
-
+#pragma unroll 1
+        for (int sub = 0; sub < NSUB; ++sub) {
+        const uint32_t lane_taddr = tmem_acc + (a * NSUB + sub) * Cfg::kAccCols + ((uint32_t)(q * 32) << 16);
         if (EPI == kEpiGeneric) {
           const int rq = lane >> 3, cq4 = lane & 7, cq = cq4 * 4;
           const bool need_aux = p.epi != BDE_EPI_STORE || p.residual != nullptr;
           int m_it[8];
 #pragma unroll
-          for (int it = 0; it < 8; ++it) m_it[it] = tl.row_m(cp, q * 32 + it * 4 + rq);
+          for (int it = 0; it < 8; ++it) m_it[it] = tl.row_m(cp, q * 32 + it * 4 + rq, sub);
           float4 aux[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it)
             aux[it] = (need_aux && m_it[it] >= 0) ? aux_load(p, m_it[it], tl.n0 + half * 32 + cq, -1) : make_float4(0.f, 0.f, 0.f, 0.f);
           const long long w0 = dbg ? clock64() : 0;
           mbar_wait(bar_tfull + 8 * a, aph);
-          w1 = dbg ? clock64() : 0;
-          dbg_epi_wait += w1 - w0;
+          if (sub == 0) {
+            w1 = dbg ? clock64() : 0;
+            dbg_epi_wait += w1 - w0;
+          }
           tcgen05_fence_after();
 #pragma unroll 1
           for (int cb = half * 32; cb < BN; cb += 64) {
             uint32_t raw[32];
             tmem_ld_32x32b_x32(lane_taddr + (uint32_t)cb, raw);
             tmem_ld_wait();
-            if (cb + 64 >= BN) {
+            if (cb + 64 >= BN && sub == NSUB - 1) {
               // last TMEM read of this tile by this warp: hand the accumulator slot back to the MMA warp
               tcgen05_fence_before();
               __syncwarp();
@@ -444,7 +473,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
           const int hf = lane & 1;
           int m_ps[2];
 #pragma unroll
-          for (int ps = 0; ps < 2; ++ps) m_ps[ps] = tl.row_m(cp, q * 32 + ps * 16 + (lane >> 1));
+          for (int ps = 0; ps < 2; ++ps) m_ps[ps] = tl.row_m(cp, q * 32 + ps * 16 + (lane >> 1), sub);
           const int hid = p.N >> 2;
           // LSTM: c_prev of every chunk of this warp, in flight while the accumulator is still being computed
           float4 cpv[NCH][2];
@@ -461,8 +490,10 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
           }
           const long long w0 = dbg ? clock64() : 0;
           mbar_wait(bar_tfull + 8 * a, aph);
-          w1 = dbg ? clock64() : 0;
-          dbg_epi_wait += w1 - w0;
+          if (sub == 0) {
+            w1 = dbg ? clock64() : 0;
+            dbg_epi_wait += w1 - w0;
+          }
           tcgen05_fence_after();
 #pragma unroll
           for (int c = 0; c < NCH; ++c) {
@@ -477,7 +508,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
                 bv[k] = p.bias != nullptr ? __ldg(reinterpret_cast<const float4*>(p.bias + tl.n0 + cb + hf * 16 + 4 * k))
                                           : make_float4(0.f, 0.f, 0.f, 0.f);
               tmem_ld_wait();
-              if (cb + 64 >= BN) {
+              if (cb + 64 >= BN && sub == NSUB - 1) {
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -538,6 +569,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
             }
           }
         }
+        }  // sub
         if (dbg) dbg_epi_busy += clock64() - w1;
       }
     }
@@ -593,11 +625,11 @@ static int get_act_tmap(const void* base, int C, int H, int W, int N, int swap, 
   return 0;
 }
 
-template <int BN, bool kHalo, int EPI, bool kPair>
+template <int BN, bool kHalo, int EPI, bool kPair, int NSUB = 1>
 static int launch_conv(const CUtensorMap& ta0, const CUtensorMap& ta1, const CUtensorMap& tb, const CvParams& cp, cudaStream_t s) {
-  using Cfg = CvCfg<BN, kHalo, kPair>;
+  using Cfg = CvCfg<BN, kHalo, kPair, NSUB>;
   constexpr int CS = kPair ? 2 : 1;
-  auto kern = conv_tma_kernel<BN, kHalo, EPI, kPair>;
+  auto kern = conv_tma_kernel<BN, kHalo, EPI, kPair, NSUB>;
   static int max_clusters = 0;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -649,19 +681,27 @@ bool conv_tma_eligible(const TcParams& p, bool ln) {
   return p.N % 32 == 0;
 }
 
-template <int BN, bool kHalo, bool kPair>
+template <int BN, bool kHalo, bool kPair, int NSUB>
 static int launch_conv_epi(int epi, const CUtensorMap& ta0, const CUtensorMap& ta1, const CUtensorMap& tb, const CvParams& cp,
                            cudaStream_t s) {
-  if (epi == kEpiLstm) return launch_conv<BN, kHalo, kEpiLstm, kPair>(ta0, ta1, tb, cp, s);
-  if (epi == kEpiStore) return launch_conv<BN, kHalo, kEpiStore, kPair>(ta0, ta1, tb, cp, s);
-  return launch_conv<BN, kHalo, kEpiGeneric, kPair>(ta0, ta1, tb, cp, s);
+  if (epi == kEpiLstm) return launch_conv<BN, kHalo, kEpiLstm, kPair, NSUB>(ta0, ta1, tb, cp, s);
+  if (epi == kEpiStore) return launch_conv<BN, kHalo, kEpiStore, kPair, NSUB>(ta0, ta1, tb, cp, s);
+  return launch_conv<BN, kHalo, kEpiGeneric, kPair, NSUB>(ta0, ta1, tb, cp, s);
 }
 
 template <int BN>
-static int launch_conv_bn(bool halo, bool pair, int epi, const CUtensorMap& ta0, const CUtensorMap& ta1, const CUtensorMap& tb,
+static int launch_conv_bn(bool halo, bool pair, int nsub, int epi, const CUtensorMap& ta0, const CUtensorMap& ta1, const CUtensorMap& tb,
                           const CvParams& cp, cudaStream_t s) {
-  if (halo) return pair ? launch_conv_epi<BN, true, true>(epi, ta0, ta1, tb, cp, s) : launch_conv_epi<BN, true, false>(epi, ta0, ta1, tb, cp, s);
-  return pair ? launch_conv_epi<BN, false, true>(epi, ta0, ta1, tb, cp, s) : launch_conv_epi<BN, false, false>(epi, ta0, ta1, tb, cp, s);
+  if (halo) {
+    // the pair form (cta_group::2) is kept for the widest tile only, the dual-tile form for N tiles up to 128
+    if constexpr (BN == 256) {
+      if (pair) return launch_conv_epi<BN, true, true, 1>(epi, ta0, ta1, tb, cp, s);
+    } else {
+      if (nsub == 2) return launch_conv_epi<BN, true, false, 2>(epi, ta0, ta1, tb, cp, s);
+    }
+    return launch_conv_epi<BN, true, false, 1>(epi, ta0, ta1, tb, cp, s);
+  }
+  return launch_conv_epi<BN, false, false, 1>(epi, ta0, ta1, tb, cp, s);
 }
 
 int conv_tma_launch(const bde_gemm_desc* d, const TcParams& p0, cudaStream_t s) {
@@ -672,23 +712,31 @@ int conv_tma_launch(const bde_gemm_desc* d, const TcParams& p0, cudaStream_t s) 
   const bool halo = p.stride == 1 && env_flag("BDE2VID_CONV_HALO", true);
   cp.swap = env_int("BDE2VID_CONV_SWAP", 1) ? 1 : 0;
   const int d1_out = cp.swap ? p.h_out : p.w_out, d2_out = cp.swap ? p.w_out : p.h_out;
+  // widest N tile that divides N
+  const int bn_max = (p.N % 256 == 0) ? 256 : (p.N % 128 == 0) ? 128 : (p.N % 64 == 0) ? 64 : 32;
+  // dual tiles (two 8 x 16 tiles per CTA) for narrow N, where single MMAs are latency-bound; needs enough tiles to
+  // keep every SM busy and a map at least two tiles wide
+  int nsub = 1;
+  if (halo && bn_max <= 128 && env_flag("BDE2VID_CONV_DUAL", true) && d2_out > kCvD2 &&
+      (size_t)p.n_img * ceil_div(d1_out, kCvD1) * ceil_div(d2_out, 2 * kCvD2) * (p.N / bn_max) >= (size_t)kNumSMs)
+    nsub = 2;
   cp.t1_tiles = (int)ceil_div(d1_out, kCvD1);
-  cp.t2_tiles = (int)ceil_div(d2_out, kCvD2);
+  cp.t2_tiles = (int)ceil_div(d2_out, kCvD2 * nsub);
   cp.num_m_tiles = p.n_img * cp.t1_tiles * cp.t2_tiles;
   cp.ntaps = p.ksize * p.ksize;
   cp.nchunks = p.ctot / BK;
-  cp.halo_bytes = (kCvD2 + p.ksize - 1) * kCvHaloPitch * 128;
+  cp.halo_bytes = (kCvD2 * nsub + p.ksize - 1) * kCvHaloPitch * 128;
   // CTA pairs (cta_group::2): off by default -- measured on B200 the pair form is 3-8 % SLOWER than one CTA per SM on
   // every shape of the path (the main loop is bound by the tensor pipe at ~700 cycles per 128x256x64 block either way)
-  const bool pair = env_flag("BDE2VID_CONV_PAIR", false) && cp.num_m_tiles >= 2;
+  const bool pair = env_flag("BDE2VID_CONV_PAIR", false) && cp.num_m_tiles >= 2 && halo && bn_max == 256 && nsub == 1;
   const int cs = pair ? 2 : 1;
   const int units = kNumSMs / cs;   // CTAs or CTA pairs that run concurrently
   // tile width: the widest N tile that divides N, narrowed while the grid would leave SMs idle
-  int bn = (p.N % 256 == 0) ? 256 : (p.N % 128 == 0) ? 128 : (p.N % 64 == 0) ? 64 : 32;
-  while (bn > 64 && ceil_div(cp.num_m_tiles, cs) * (size_t)(p.N / bn) < (size_t)units) bn /= 2;
+  int bn = bn_max;
+  while (nsub == 1 && !pair && bn > 64 && ceil_div(cp.num_m_tiles, cs) * (size_t)(p.N / bn) < (size_t)units) bn /= 2;
   {
     const int f = env_int("BDE2VID_CONV_BN", 0);
-    if ((f == 32 || f == 64 || f == 128 || f == 256) && p.N % f == 0) bn = f;
+    if ((f == 32 || f == 64 || f == 128 || f == 256) && p.N % f == 0 && nsub == 1 && !pair) bn = f;
   }
   cp.groups_per_n = (int)ceil_div(cp.num_m_tiles, cs);
   const size_t groups = (size_t)cp.groups_per_n * (p.N / bn);
@@ -709,7 +757,7 @@ int conv_tma_launch(const bde_gemm_desc* d, const TcParams& p0, cudaStream_t s) 
   }
   CUtensorMap ta0, ta1, tb;
   const int box1 = halo ? kCvHaloPitch : (p.stride == 2 ? 2 * kCvD1 : kCvD1);
-  const int box2 = halo ? kCvD2 + p.ksize - 1 : (p.stride == 2 ? 2 * kCvD2 : kCvD2);
+  const int box2 = halo ? kCvD2 * nsub + p.ksize - 1 : (p.stride == 2 ? 2 * kCvD2 : kCvD2);
   int rc = get_act_tmap(d->a0, p.c0, p.h_in, p.w_in, p.n_img, cp.swap, box1, box2, p.stride, &ta0);
   if (rc != 0) return rc;
   if (p.c1 > 0) {
@@ -721,10 +769,10 @@ int conv_tma_launch(const bde_gemm_desc* d, const TcParams& p0, cudaStream_t s) 
   rc = get_weight_tmap(d->w, p.N, p.w_ld, bn / cs, &tb);
   if (rc != 0) return rc;
   switch (bn) {
-    case 32: return launch_conv_bn<32>(halo, pair, epi, ta0, ta1, tb, cp, s);
-    case 64: return launch_conv_bn<64>(halo, pair, epi, ta0, ta1, tb, cp, s);
-    case 128: return launch_conv_bn<128>(halo, pair, epi, ta0, ta1, tb, cp, s);
-    default: return launch_conv_bn<256>(halo, pair, epi, ta0, ta1, tb, cp, s);
+    case 32: return launch_conv_bn<32>(halo, pair, nsub, epi, ta0, ta1, tb, cp, s);
+    case 64: return launch_conv_bn<64>(halo, pair, nsub, epi, ta0, ta1, tb, cp, s);
+    case 128: return launch_conv_bn<128>(halo, pair, nsub, epi, ta0, ta1, tb, cp, s);
+    default: return launch_conv_bn<256>(halo, pair, nsub, epi, ta0, ta1, tb, cp, s);
   }
 }
 

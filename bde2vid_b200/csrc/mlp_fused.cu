@@ -168,39 +168,41 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
     }
     tcgen05_fence_before();
   } else {
-    // ---------------- TMA + MMA thread ---------------------------------------------------------------------------------
-    if (lane == 0) {
+    // ---------------- TMA + MMA warp: all lanes wait, one elected lane issues (elect_one_sync, tc_common.cuh) --------------
+    if (elect_one_sync()) {
       mbar_arrive_expect_tx(bar_w1, kMlpH * 128);
       tma_load_2d(s_w1, &tmap_w1, bar_w1, 0, 0);
       mbar_arrive_expect_tx(bar_w2, kMlpC * kMlpH * 2);
 #pragma unroll
       for (int kb = 0; kb < kMlpH / BK; ++kb) tma_load_2d(s_w2 + kb * (kMlpC * 128), &tmap_w2, bar_w2, kb * BK, 0);
-      // GEMM 1: [128 x 64] x [64 x 256]
-      mbar_wait(bar_a, 0);
-      mbar_wait(bar_w1, 0);
-      tcgen05_fence_after();
-      {
-        constexpr uint32_t idesc = make_idesc(kMlpH);
-        const uint64_t adesc = make_smem_desc(s_a), bdesc = make_smem_desc(s_w1);
+    }
+    __syncwarp();
+    // GEMM 1: [128 x 64] x [64 x 256]
+    mbar_wait(bar_a, 0);
+    mbar_wait(bar_w1, 0);
+    tcgen05_fence_after();
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc(kMlpH);
+      const uint64_t adesc = make_smem_desc(s_a), bdesc = make_smem_desc(s_w1);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
-        umma_commit(bar_acc1);
+      for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+      umma_commit(bar_acc1);
+    }
+    __syncwarp();
+    // GEMM 2: [128 x 256] x [256 x 64], A = the hidden tile written by epilogue 1
+    mbar_wait(bar_h, 0);
+    mbar_wait(bar_w2, 0);
+    tcgen05_fence_after();
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc(kMlpC);
+#pragma unroll
+      for (int kb = 0; kb < kMlpH / BK; ++kb) {
+        const uint64_t adesc = make_smem_desc(s_h + kb * (BM * 128)), bdesc = make_smem_desc(s_w2 + kb * (kMlpC * 128));
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
       }
-      // GEMM 2: [128 x 256] x [256 x 64], A = the hidden tile written by epilogue 1
-      mbar_wait(bar_h, 0);
-      mbar_wait(bar_w2, 0);
-      tcgen05_fence_after();
-      {
-        constexpr uint32_t idesc = make_idesc(kMlpC);
-#pragma unroll
-        for (int kb = 0; kb < kMlpH / BK; ++kb) {
-          const uint64_t adesc = make_smem_desc(s_h + kb * (BM * 128)), bdesc = make_smem_desc(s_w2 + kb * (kMlpC * 128));
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(bar_acc2);
-      }
+      umma_commit(bar_acc2);
     }
     __syncwarp();
   }
@@ -413,21 +415,27 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
     tcgen05_fence_before();
   } else if (warp == kTmaWarp) {
     // ---------------- weight loads, in the order the MMA warp consumes them ----------------------------------------------
-    if (lane == 0) {
+    {
       uint32_t it = 0;
       auto load_w1 = [&](int chunk, int i) {   // item i of fc1(chunk): k slabs 2i, 2i + 1 of W1 rows [128 chunk, +128)
         const uint32_t s = it % kM3Stages;
         mbar_wait(bar_wempty + 8 * s, ((it / kM3Stages) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(bar_wfull + 8 * s, kM3Stage);
-        tma_load_2d(s_w + s * kM3Stage, &tmap_w1, bar_wfull + 8 * s, (2 * i) * BK, chunk * kM3Chunk);
-        tma_load_2d(s_w + s * kM3Stage + 16384, &tmap_w1, bar_wfull + 8 * s, (2 * i + 1) * BK, chunk * kM3Chunk);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(bar_wfull + 8 * s, kM3Stage);
+          tma_load_2d(s_w + s * kM3Stage, &tmap_w1, bar_wfull + 8 * s, (2 * i) * BK, chunk * kM3Chunk);
+          tma_load_2d(s_w + s * kM3Stage + 16384, &tmap_w1, bar_wfull + 8 * s, (2 * i + 1) * BK, chunk * kM3Chunk);
+        }
+        __syncwarp();
         ++it;
       };
       auto load_w2 = [&](int chunk, int i) {   // item i of fc2(chunk): k slab 2 chunk + i of W2 (all 256 rows)
         const uint32_t s = it % kM3Stages;
         mbar_wait(bar_wempty + 8 * s, ((it / kM3Stages) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(bar_wfull + 8 * s, kM3Stage);
-        tma_load_2d(s_w + s * kM3Stage, &tmap_w2, bar_wfull + 8 * s, (2 * chunk + i) * BK, 0);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(bar_wfull + 8 * s, kM3Stage);
+          tma_load_2d(s_w + s * kM3Stage, &tmap_w2, bar_wfull + 8 * s, (2 * chunk + i) * BK, 0);
+        }
+        __syncwarp();
         ++it;
       };
       load_w1(0, 0); load_w1(0, 1);
@@ -439,8 +447,8 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
     }
     __syncwarp();
   } else {
-    // ---------------- MMA issuer --------------------------------------------------------------------------------------------
-    if (lane == 0) {
+    // ---------------- MMA issuer: all lanes walk the schedule, one elected lane issues -------------------------------------
+    {
       constexpr uint32_t idesc1 = make_idesc(kM3Chunk), idesc2 = make_idesc(kM3C);
       uint32_t it = 0;
       auto fc1 = [&](int chunk) {
@@ -451,16 +459,19 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
           const uint32_t s = it % kM3Stages;
           mbar_wait(bar_wfull + 8 * s, (it / kM3Stages) & 1u);
           tcgen05_fence_after();
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int sl = 0; sl < 2; ++sl) {
-            const uint64_t adesc = make_smem_desc(s_xn + (2 * i + sl) * (BM * 128)), bdesc = make_smem_desc(s_w + s * kM3Stage + sl * 16384);
+            for (int sl = 0; sl < 2; ++sl) {
+              const uint64_t adesc = make_smem_desc(s_xn + (2 * i + sl) * (BM * 128)), bdesc = make_smem_desc(s_w + s * kM3Stage + sl * 16384);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(tmem_base + a * 128, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, (i | sl | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16(tmem_base + a * 128, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, (i | sl | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(bar_wempty + 8 * s);
+            if (i == 1) umma_commit(bar_a1full + 8 * a);
           }
-          umma_commit(bar_wempty + 8 * s);
+          __syncwarp();
         }
-        umma_commit(bar_a1full + 8 * a);
       };
       mbar_wait(bar_xn, 0);
       fc1(0);
@@ -473,18 +484,22 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
           const uint32_t s = it % kM3Stages;
           mbar_wait(bar_wfull + 8 * s, (it / kM3Stages) & 1u);
           tcgen05_fence_after();
-          const uint64_t adesc = make_smem_desc(s_h + a * 32768 + i * (BM * 128)), bdesc = make_smem_desc(s_w + s * kM3Stage);
+          if (elect_one_sync()) {
+            const uint64_t adesc = make_smem_desc(s_h + a * 32768 + i * (BM * 128)), bdesc = make_smem_desc(s_w + s * kM3Stage);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(acc2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (jc | i | k) != 0 ? 1u : 0u);
-          umma_commit(bar_wempty + 8 * s);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(acc2, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc2, (jc | i | k) != 0 ? 1u : 0u);
+            umma_commit(bar_wempty + 8 * s);
+            if (i == 1) {
+              umma_commit(bar_hempty + 8 * a);   // H[a] may be rewritten once these MMAs have read it
+              if (jc == kM3NChunks - 1) umma_commit(bar_a2full);
+            }
+          }
+          __syncwarp();
         }
-        umma_commit(bar_hempty + 8 * a);   // H[a] may be rewritten once these MMAs have read it
         if (jc + 2 < kM3NChunks) fc1(jc + 2);
       }
-      umma_commit(bar_a2full);
     }
-    __syncwarp();
   }
 
   __syncthreads();

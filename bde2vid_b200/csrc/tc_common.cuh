@@ -98,6 +98,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// Guard for single-thread tcgen05 / TMA issue.  With a predicate that comes from elect.sync ptxas emits the
+// uniform-datapath instructions (UTCHMMA, UTCBAR, UTMALDG) directly; under `if (lane == 0)` it wraps each of them in an
+// ELECT ... BRA.U.ANY waterfall loop (~40 issue cycles apiece).  True in exactly one (the lowest) lane of the converged warp
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {

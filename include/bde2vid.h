@@ -151,6 +151,8 @@ int bde_gemm(const bde_gemm_desc* desc, void* stream);
  * and the number of launches.  Not for use under stream capture. */
 int bde_profile_begin(int max_launches);
 int bde_profile_end(double* total_ms, int* n_launches);
+/* Algorithmic work of the launches profiled since bde_profile_begin: sum of 2 * M * n * ksize^2 * (c0 + c1). */
+int bde_profile_flops(double* flops);
 
 /* --------------------------------------------------------------------------------------------
  * Element-wise / gather kernels around the GEMMs.

@@ -122,7 +122,8 @@ def time_case(name, n, ci, co, h, w, k, s, lstm=False, iters=20):
 def main():
     cfg = {k: v for k, v in os.environ.items() if k.startswith("BDE2VID_")}
     print("config", cfg, flush=True)
-    cases = [(1, 128, 64, 19, 37, 3, 1, False), (2, 256, 128, 18, 22, 5, 1, False), (3, 64, 32, 40, 56, 5, 1, False),
+    cases = [(8, 128, 64, 40, 70, 5, 1, False), (6, 64, 32, 37, 90, 5, 1, False), (8, 256, 128, 24, 44, 3, 1, False),
+             (1, 128, 64, 19, 37, 3, 1, False), (2, 256, 128, 18, 22, 5, 1, False), (3, 64, 32, 40, 56, 5, 1, False),
              (2, 128, 256, 17, 22, 3, 1, True), (1, 64, 64, 8, 16, 3, 1, False), (2, 512, 1024, 33, 44, 3, 1, True)]
     if os.environ.get("BDE2VID_CONV_S2", "0") == "1":
         cases += [(2, 64, 128, 33, 44, 5, 2, False), (2, 128, 256, 16, 24, 5, 2, False)]
