@@ -10,6 +10,9 @@
 //   for every bin b: w = p * max(0, 1 - |tn - b|);  grid[b, int(y), int(x)] += w
 // Only bins floor(tn) and floor(tn)+1 can receive a non-zero weight, so only those are touched.
 // A NaN tn (dt == 0) poisons every bin of the touched pixel exactly like the reference does.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace bde {
@@ -202,6 +205,122 @@ __global__ void __launch_bounds__(256) voxel_atomic_kernel(
   if (oob_count != nullptr && oob > 0) atomicAdd(oob_count, oob);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Algorithm 3: one thread-block CLUSTER per window; the whole voxel grid lives in the distributed
+// shared memory of the cluster (CTA r owns the sensor rows [r * band, (r + 1) * band) of every bin).
+// Every event is read from HBM exactly once -- CTA r scans the r-th share of the window -- and is
+// added into the owning CTA's tile with a shared::cluster reduction (red.add.f32 over DSMEM); after a
+// cluster barrier each CTA streams its band of the zero-padded output with 16-byte stores.
+// HBM traffic == algorithmic bytes (16 N + 4 B Hp Wp per window) and, unlike the row-band algorithm,
+// no CTA re-scans events that belong to other bands.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t vx_mapa(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void vx_red_add(uint32_t cluster_addr, float v) {
+  asm volatile("red.relaxed.cluster.shared::cluster.add.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void vx_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(512, 1) voxel_cluster_kernel(
+    const float* __restrict__ xs, const float* __restrict__ ys, const float* __restrict__ ts,
+    const float* __restrict__ ps, const int64_t* __restrict__ offsets, int bins, int H, int W,
+    int pad_top, int pad_left, int Hp, int Wp, int band_rows, int nc, int vec_ok, float* __restrict__ out,
+    size_t win_stride, int* oob_count) {
+  extern __shared__ __align__(16) float tile[];  // [bins][band_rows][W] of this CTA's band
+  const int win = blockIdx.x / nc;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int plane = band_rows * W;
+  const int tile_elems = bins * plane;
+  {
+    float4* t4 = reinterpret_cast<float4*>(tile);
+    const int n4 = tile_elems >> 2;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = (n4 << 2) + threadIdx.x; i < tile_elems; i += blockDim.x) tile[i] = 0.f;
+  }
+  vx_cluster_sync();  // every tile of the cluster is zeroed before anyone adds into it
+
+  const int64_t ea = offsets[win], eb = offsets[win + 1];
+  if (eb > ea) {
+    const float t0 = ts[ea];
+    const float dt = __fsub_rn(ts[eb - 1], t0);
+    const float bm1 = (float)(bins - 1);
+    const uint32_t tile_u32 = (uint32_t)__cvta_generic_to_shared(tile);
+    int oob = 0;
+    auto one = [&](float x, float y, float t, float p) {
+      const int xi = (int)x, yi = (int)y;  // truncation == .long() (event_utils.py:371-374)
+      if (xi < 0 || xi >= W || yi < 0 || yi >= H) {
+        oob++;
+        return;
+      }
+      const EventContrib c = contrib(t, p, t0, dt, bm1, bins);
+      const int owner = yi / band_rows;
+      const uint32_t cell = vx_mapa(tile_u32 + (uint32_t)(((yi - owner * band_rows) * W + xi) * 4), (uint32_t)owner);
+      if (c.b0 < 0) {  // NaN event: every bin of the pixel becomes NaN
+        for (int b = 0; b < bins; ++b) vx_red_add(cell + (uint32_t)(b * plane * 4), c.w0);
+        return;
+      }
+      if (c.w0 != 0.0f) vx_red_add(cell + (uint32_t)(c.b0 * plane * 4), c.w0);
+      if (c.b0 + 1 < bins && c.w1 != 0.0f) vx_red_add(cell + (uint32_t)((c.b0 + 1) * plane * 4), c.w1);
+    };
+    // this CTA's share of the window: scalar head / tail around a 16-byte aligned float4 body
+    const int64_t n = eb - ea;
+    const int64_t sa = ea + (n * rank) / nc, sb_ = ea + (n * (rank + 1)) / nc;
+    int64_t body_a = vec_ok ? min(sb_, (sa + 3) & ~(int64_t)3) : sb_;
+    int64_t body_b = vec_ok ? max(body_a, sb_ & ~(int64_t)3) : sb_;
+    const int64_t n_edge = (body_a - sa) + (sb_ - body_b);
+    for (int64_t i = threadIdx.x; i < n_edge; i += blockDim.x) {
+      const int64_t e = i < body_a - sa ? sa + i : body_b + (i - (body_a - sa));
+      one(xs[e], ys[e], ts[e], ps[e]);
+    }
+    const int64_t nvec = (body_b - body_a) >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(xs + body_a);
+    const float4* y4 = reinterpret_cast<const float4*>(ys + body_a);
+    const float4* t4 = reinterpret_cast<const float4*>(ts + body_a);
+    const float4* p4 = reinterpret_cast<const float4*>(ps + body_a);
+    for (int64_t v = threadIdx.x; v < nvec; v += blockDim.x) {
+      const float4 x = __ldg(x4 + v), y = __ldg(y4 + v), t = __ldg(t4 + v), p = __ldg(p4 + v);
+      one(x.x, y.x, t.x, p.x);
+      one(x.y, y.y, t.y, p.y);
+      one(x.z, y.z, t.z, p.z);
+      one(x.w, y.w, t.w, p.w);
+    }
+    if (oob_count != nullptr && oob > 0) atomicAdd(oob_count, oob);
+  }
+  vx_cluster_sync();  // all reductions into this CTA's tile have landed
+
+  // ---- coalesced write of this CTA's rows of the padded grid (first / last CTA add the padding rows) ----
+  float* dst = out + (size_t)win * win_stride;
+  const int y_lo = min(H, (int)rank * band_rows), y_hi = min(H, y_lo + band_rows);   // sensor rows owned
+  const int r_lo = rank == 0 ? 0 : y_lo + pad_top;
+  const int r_hi = (int)rank == nc - 1 ? Hp : y_hi + pad_top;
+  const int nrows = max(0, r_hi - r_lo);
+  const int wq = Wp >> 2;   // Wp % 4 == 0 (checked by the host)
+  for (int b = 0; b < bins; ++b) {
+    const float* tb = tile + b * plane;
+    for (int i = threadIdx.x; i < nrows * wq; i += blockDim.x) {
+      const int rr = i / wq, c4 = (i - rr * wq) << 2;
+      const int r = r_lo + rr, y = r - pad_top;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (y >= y_lo && y < y_hi) {
+        const float* trow = tb + (y - y_lo) * W;
+        const int x = c4 - pad_left;
+        v.x = (x >= 0 && x < W) ? trow[x] : 0.f;
+        v.y = (x + 1 >= 0 && x + 1 < W) ? trow[x + 1] : 0.f;
+        v.z = (x + 2 >= 0 && x + 2 < W) ? trow[x + 2] : 0.f;
+        v.w = (x + 3 >= 0 && x + 3 < W) ? trow[x + 3] : 0.f;
+      }
+      *reinterpret_cast<float4*>(dst + ((size_t)b * Hp + r) * Wp + c4) = v;
+    }
+  }
+}
+
 // planar fp32 [T, bins, Hp, Wp] -> NHWC [T, Hp, Wp, c_pad] (zero-padded channels)
 template <typename T>
 __global__ void pack_voxel_kernel(const float* __restrict__ vox, int bins, size_t plane, int c_pad,
@@ -246,7 +365,52 @@ extern "C" int bde_voxelize_seq_strided(const float* xs, const float* ys, const 
   int band_rows = (int)(smem_budget / ((size_t)num_bins * W * sizeof(float)));
   band_rows = band_rows > Hp ? Hp : band_rows;
   int bands = band_rows > 0 ? (int)ceil_div(Hp, band_rows) : 1 << 30;
-  if (algo == 0) algo = (bands <= 16) ? 1 : 2;
+  // algorithm 3 (cluster / distributed shared memory): the grid of one window must fit the shared memory of at most 8 CTAs
+  const size_t tile_budget = 227 * 1024 - 1024;
+  int nc = 0, crow = 0;
+  for (int c = 1; c <= 8; c *= 2) {
+    const int rows = (int)ceil_div((size_t)H, (size_t)c);
+    if ((size_t)num_bins * rows * W * sizeof(float) <= tile_budget) {
+      nc = c;
+      crow = rows;
+      break;
+    }
+  }
+  const bool cluster_ok = nc > 0 && Wp % 4 == 0 && (((uintptr_t)out) & 15) == 0 && out_window_stride % 4 == 0;
+  if (algo == 0) {
+    const char* e = getenv("BDE2VID_VOXEL_ALGO");
+    if (e != nullptr && e[0] >= '1' && e[0] <= '3') algo = e[0] - '0';
+  }
+  if (algo == 0) algo = cluster_ok ? 3 : ((bands <= 16) ? 1 : 2);
+  if (algo == 3) {
+    BDE_REQUIRE(cluster_ok, "bde_voxelize_seq: the cluster algorithm needs a grid that fits 8 CTAs' shared memory, Wp %% 4 == 0 and a "
+                            "16-byte aligned output");
+    const size_t smem = (size_t)num_bins * crow * W * sizeof(float);
+    static size_t configured = 0;
+    if (smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(voxel_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      BDE_REQUIRE(e == cudaSuccess, "bde_voxelize_seq: smem attr: %s", cudaGetErrorString(e));
+      configured = smem;
+    }
+    const int vec_ok = ((((uintptr_t)xs) | ((uintptr_t)ys) | ((uintptr_t)ts) | ((uintptr_t)ps)) & 15) == 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nc;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)(T * nc));
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, voxel_cluster_kernel, xs, ys, ts, ps, offsets, num_bins, H, W, pad_top, pad_left, Hp, Wp,
+                                       crow, nc, vec_ok, out, out_window_stride, oob_count);
+    BDE_REQUIRE(e == cudaSuccess, "bde_voxelize_seq: cluster launch: %s", cudaGetErrorString(e));
+    return check_launch("voxel_cluster_kernel");
+  }
   if (algo == 1) {
     BDE_REQUIRE(band_rows >= 1, "bde_voxelize_seq: sensor row too wide for the shared-memory algorithm");
     // balance the bands
