@@ -606,6 +606,371 @@ int launch_fused(const FusedAttnParams& p, cudaStream_t s) {
   return check_launch("attn_fused_kernel");
 }
 
+
+// =====================================================================================================================
+// C = 256 (16 heads of 16 channels), whole-window form: ONE 512-thread CTA per window walks the four 64-column head
+// groups, so the gather + LayerNorm of the window's D x 49 tokens is done once (the per-head-group kernel above redoes
+// it in each of its 4 CTAs), sixteen warps instead of eight hide the mma.sync / shared-memory latencies, and the output
+// projection + window_reverse + shortcut (DTransformer.py:204, 294-299) run in the same kernel on the [49 x 256]
+// attention output that never leaves shared memory -- the separate proj GEMM launch and its bf16 round trip are gone.
+// Weights stream through two [64 x 128] half-slice buffers (cp.async ping-pong): 12 q/k/v slices + 4 proj slices.
+// =====================================================================================================================
+constexpr int kThreadsW = 512;
+
+template <int NT>
+struct WinCfg {
+  static constexpr int C = 256, HD = 16, HG = 4, NHG = 4;
+  static constexpr int PX = C + 8;                // LayerNorm'ed tokens / attention-output pitch (bf16 elements)
+  static constexpr int PH = 128 + 8;              // weight half-slice pitch
+  static constexpr int PQ = 72;
+  static constexpr int KSTEPS = (NT + 1) / 2;
+  static constexpr int XROWS = KSTEPS * 16;
+  static constexpr int NKEY = NT * 8;
+  static constexpr int DMAX = NT <= 7 ? 1 : (NT <= 13 ? 2 : 3);
+  static constexpr int OFF_XN = 0;
+  static constexpr int OFF_WB = OFF_XN + XROWS * PX * 2;          // 2 x [64 x PH]
+  static constexpr int OFF_Q = OFF_WB + 2 * 64 * PH * 2;
+  static constexpr int OFF_K = OFF_Q + 64 * PQ * 2;
+  static constexpr int OFF_V = OFF_K + NKEY * PQ * 2;
+  static constexpr int OFF_O = OFF_V + XROWS * PQ * 2;            // [64 x PX] attention output of all heads
+  static constexpr int OFF_TBL = OFF_O + 64 * PX * 2;             // HG x DMAX x 169 floats of the current head group
+  static constexpr int OFF_COFF = OFF_TBL + HG * DMAX * kRel * 4;
+  static constexpr int OFF_ROFF = OFF_COFF + NKEY * 4;
+  static constexpr int OFF_PIX = OFF_ROFF + 256;
+  static constexpr int SMEM = OFF_PIX + 256;
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+// acc[i][n][4] += A[rows, k0 .. k0 + 128) (smem, pitch PX) * Whalf[64, 128]^T (smem, pitch PH)
+template <int PX, int PH, int MT, typename RowFn>
+__device__ __forceinline__ void warp_gemm_half(float (&acc)[MT][2][4], int n_mt, uint32_t a_base, RowFn a_row, int k0, uint32_t w_base,
+                                               int npair, int lane) {
+  const int bm = lane >> 3;
+  const uint32_t b_addr0 = w_base + (uint32_t)(((npair * 16 + (bm >> 1) * 8 + (lane & 7)) * PH + (bm & 1) * 8) * 2);
+#pragma unroll 4
+  for (int kk = 0; kk < 8; ++kk) {
+    uint32_t b[4];
+    ldsm_x4(b, b_addr0 + (uint32_t)(kk * 32));
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+      if (i < n_mt) {
+        uint32_t a[4];
+        ldsm_x4(a, a_base + (uint32_t)((a_row(i, lane & 15) * PX + k0 + kk * 16 + (lane >> 4) * 8) * 2));
+        mma16816(acc[i][0], a, b[0], b[1]);
+        mma16816(acc[i][1], a, b[2], b[3]);
+      }
+    }
+  }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAttnParams p) {
+  using Cfg = WinCfg<NT>;
+  constexpr int C = Cfg::C, HD = Cfg::HD, HG = Cfg::HG, PX = Cfg::PX, PH = Cfg::PH, PQ = Cfg::PQ;
+  constexpr int KSTEPS = Cfg::KSTEPS, XROWS = Cfg::XROWS, NKEY = Cfg::NKEY;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
+  __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_XN);
+  __nv_bfloat16* qs = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_Q);
+  __nv_bfloat16* ks = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_K);
+  __nv_bfloat16* vs = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_V);
+  __nv_bfloat16* os = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_O);
+  int* coff = reinterpret_cast<int*>(smem + Cfg::OFF_COFF);
+  int* roff = reinterpret_cast<int*>(smem + Cfg::OFF_ROFF);
+  int* pix_s = reinterpret_cast<int*>(smem + Cfg::OFF_PIX);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int w = blockIdx.x;
+  const int n_kv = p.D * kTok;
+  const int tbl_ld = p.D * kRel;
+
+  // weight half-slice hs (0 .. 31): slice = hs / 2 (q, k, v of head group 0..3, then the 4 proj slices), K half = hs & 1
+  auto load_half = [&](int hs) {
+    const int sl = hs >> 1, half = hs & 1;
+    const __nv_bfloat16* src;
+    if (sl < 12) {
+      const int hg = sl / 3, which = sl - hg * 3;
+      src = p.wqkv + (size_t)(which * C + hg * 64) * C + half * 128;
+    } else {
+      src = p.wproj + (size_t)((sl - 12) * 64) * C + half * 128;
+    }
+    const uint32_t dst = sb + Cfg::OFF_WB + (uint32_t)((hs & 1) * 64 * PH * 2);
+    for (int i = tid; i < 64 * 16; i += kThreadsW) {
+      const int r = i >> 4, ch = i & 15;
+      cpa16(dst + (uint32_t)((r * PH + ch * 8) * 2), src + (size_t)r * C + ch * 8);
+    }
+    cpa_commit();
+  };
+  load_half(0);
+
+  // ---- index tables -----------------------------------------------------------------------------------
+  for (int n = tid; n < NKEY; n += kThreadsW) {
+    int v = 0;
+    if (n < n_kv) {
+      const int d = n / kTok, r = n - d * kTok, a = r / 7, b = r - a * 7;
+      v = d * kRel + (6 - a) * 13 + (6 - b);
+    }
+    coff[n] = v * 4;
+  }
+  if (tid < 64) {
+    const int a = tid / 7, b = tid - a * 7;
+    roff[tid] = tid < kTok ? (a * 13 + b) * 4 : 0;
+    pix_s[tid] = tid < kTok ? __ldg(p.tok_map + (size_t)w * kTok + tid) : -1;
+  }
+  __syncthreads();
+
+  // ---- gather + LayerNorm, once per window: 8 lanes per token, 64 tokens per pass ---------------------
+  {
+    const int j = lane & 7, sub = lane >> 3;
+    for (int pass = 0; pass * 64 < XROWS; ++pass) {
+      const int n = pass * 64 + warp * 4 + sub;
+      if (n >= XROWS) continue;   // uniform per 4-token group; XROWS is a multiple of 16
+      const float* src = nullptr;
+      if (n < n_kv) {
+        const int d = n / kTok, tok = n - d * kTok;
+        const int pix = pix_s[tok];
+        const float* fr = p.frames[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) fr = (d == q) ? p.frames[q] : fr;
+        if (fr != nullptr && pix >= 0) src = fr + (size_t)pix * C + j * 8;
+      }
+      float v[4][8];
+      float sum = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        if (src != nullptr) {
+          const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + kb * 64));
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + kb * 64 + 4));
+          v[kb][0] = t0.x; v[kb][1] = t0.y; v[kb][2] = t0.z; v[kb][3] = t0.w;
+          v[kb][4] = t1.x; v[kb][5] = t1.y; v[kb][6] = t1.z; v[kb][7] = t1.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[kb][e] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += v[kb][e];
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      const float mean = sum / (float)C;
+      float sq = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dlt = v[kb][e] - mean;
+          v[kb][e] = dlt;
+          sq += dlt * dlt;
+        }
+      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+      const float rstd = 1.0f / sqrtf(sq / (float)C + 1e-5f);
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        uint4 pk;
+        pk.x = pack2(v[kb][0] * rstd, v[kb][1] * rstd);
+        pk.y = pack2(v[kb][2] * rstd, v[kb][3] * rstd);
+        pk.z = pack2(v[kb][4] * rstd, v[kb][5] * rstd);
+        pk.w = pack2(v[kb][6] * rstd, v[kb][7] * rstd);
+        *reinterpret_cast<uint4*>(xn + (size_t)n * PX + kb * 64 + j * 8) = pk;
+      }
+    }
+  }
+
+  const int npair = warp & 3, mq = warp >> 2;
+  const uint32_t xn_u32 = sb + Cfg::OFF_XN, os_u32 = sb + Cfg::OFF_O;
+  const uint32_t vs_u32 = sb + Cfg::OFF_V, tbl_u32 = sb + Cfg::OFF_TBL, coff_u32 = sb + Cfg::OFF_COFF;
+  constexpr int MTK = (KSTEPS + 3) / 4;   // k / v m-tiles per warp (4 m groups)
+  constexpr uint32_t kOnes = 0x3C003C00u;
+  constexpr float kLog2e = 1.4426950408889634f;
+  int hs = 0;   // next half-slice to consume (its load has been issued)
+
+  // one weight slice = two half-slices: wait for the half, release the other buffer to the next load, accumulate
+  auto slice_gemm = [&](auto& acc, int n_mt, uint32_t a_base, auto a_row) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half, ++hs) {
+      cpa_wait<0>();
+      __syncthreads();                       // half-slice hs landed; every warp is done with buffer (hs + 1) & 1
+      if (hs + 1 < 32) load_half(hs + 1);
+      warp_gemm_half<PX, PH, (int)(sizeof(acc) / sizeof(acc[0]))>(acc, n_mt, a_base, a_row, half * 128,
+                                                                   sb + Cfg::OFF_WB + (uint32_t)((hs & 1) * 64 * PH * 2), npair, lane);
+    }
+  };
+
+  for (int hg = 0; hg < Cfg::NHG; ++hg) {
+    // ---- q, k, v projections of this head group --------------------------------------------------------------------
+    for (int which = 0; which < 3; ++which) {
+      const float* bsrc = p.bqkv + which * C + hg * 64 + npair * 16 + 2 * t;
+      const float2 bia0 = __ldg(reinterpret_cast<const float2*>(bsrc));
+      const float2 bia1 = __ldg(reinterpret_cast<const float2*>(bsrc + 8));
+      if (which == 0) {
+        float acc[1][2][4];
+        acc[0][0][0] = acc[0][0][1] = acc[0][0][2] = acc[0][0][3] = acc[0][1][0] = acc[0][1][1] = acc[0][1][2] = acc[0][1][3] = 0.f;
+        const int qrow0 = p.q_slot * kTok;
+        slice_gemm(acc, 1, xn_u32, [&](int i, int r) { return min(qrow0 + mq * 16 + r, XROWS - 1); });
+        const int r0 = mq * 16 + g;
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          const float2 bb = n == 0 ? bia0 : bia1;
+          const int col = npair * 16 + n * 8 + 2 * t;
+          *reinterpret_cast<uint32_t*>(qs + r0 * PQ + col) = pack2(acc[0][n][0] + bb.x, acc[0][n][1] + bb.y);
+          *reinterpret_cast<uint32_t*>(qs + (r0 + 8) * PQ + col) = pack2(acc[0][n][2] + bb.x, acc[0][n][3] + bb.y);
+        }
+      } else {
+        float acc[MTK][2][4];
+#pragma unroll
+        for (int i = 0; i < MTK; ++i)
+#pragma unroll
+          for (int n = 0; n < 2; ++n) acc[i][n][0] = acc[i][n][1] = acc[i][n][2] = acc[i][n][3] = 0.f;
+        const int mt0 = mq * MTK;
+        const int n_mt = max(0, min(MTK, KSTEPS - mt0));
+        slice_gemm(acc, n_mt, xn_u32, [&](int i, int r) { return (mt0 + i) * 16 + r; });
+        __nv_bfloat16* dstm = which == 1 ? ks : vs;
+        const int row_lim = which == 1 ? NKEY : XROWS;
+#pragma unroll
+        for (int i = 0; i < MTK; ++i) {
+          if (i < n_mt) {
+            const int r0 = (mt0 + i) * 16 + g;
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+              const float2 bb = n == 0 ? bia0 : bia1;
+              const int col = npair * 16 + n * 8 + 2 * t;
+              const float v00 = acc[i][n][0] + bb.x, v01 = acc[i][n][1] + bb.y, v10 = acc[i][n][2] + bb.x, v11 = acc[i][n][3] + bb.y;
+              if (r0 < row_lim) *reinterpret_cast<uint32_t*>(dstm + r0 * PQ + col) = which == 1 ? pack2(v00, v01) : pack2_h(v00, v01);
+              if (r0 + 8 < row_lim)
+                *reinterpret_cast<uint32_t*>(dstm + (r0 + 8) * PQ + col) = which == 1 ? pack2(v10, v11) : pack2_h(v10, v11);
+            }
+          }
+        }
+      }
+    }
+    // ---- bias table of this head group -> smem; q, k, v visible ----------------------------------------------------
+    {
+      const float* src = p.tbl + (size_t)hg * HG * tbl_ld;
+      const int n16 = HG * tbl_ld / 4;
+      for (int i = tid; i < n16; i += kThreadsW) cpa16(sb + Cfg::OFF_TBL + (uint32_t)(i * 16), src + i * 4);
+      cpa_commit();
+      cpa_wait<0>();   // also covers the weight half-slice that is in flight (needed next anyway)
+      __syncthreads();
+    }
+    // ---- attention: warp = (head of the group, 16-row query tile); scores stay in registers ---------------------------
+    {
+      const int hl = warp >> 2, mt = warp & 3;
+      const int row0 = mt * 16 + g, row1 = row0 + 8;
+      float s[NT][4];
+      const uint32_t r0a = tbl_u32 + (uint32_t)(hl * tbl_ld * 4 + roff[row0]);
+      const uint32_t r1a = tbl_u32 + (uint32_t)(hl * tbl_ld * 4 + roff[row1]);
+      uint32_t qa[4];
+      {
+        const __nv_bfloat16* q0 = qs + row0 * PQ + hl * HD;
+        const __nv_bfloat16* q1 = qs + row1 * PQ + hl * HD;
+        qa[0] = *reinterpret_cast<const uint32_t*>(q0 + 2 * t);
+        qa[1] = *reinterpret_cast<const uint32_t*>(q1 + 2 * t);
+        qa[2] = *reinterpret_cast<const uint32_t*>(q0 + 2 * t + 8);
+        qa[3] = *reinterpret_cast<const uint32_t*>(q1 + 2 * t + 8);
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const uint2 cp = lds_u64(coff_u32 + (uint32_t)((j * 8 + 2 * t) * 4));
+        s[j][0] = lds_f32(r0a + cp.x); s[j][1] = lds_f32(r0a + cp.y);
+        s[j][2] = lds_f32(r1a + cp.x); s[j][3] = lds_f32(r1a + cp.y);
+        if (j == NT - 1) {
+          if (j * 8 + 2 * t >= n_kv) s[j][0] = s[j][2] = -1e30f;
+          if (j * 8 + 2 * t + 1 >= n_kv) s[j][1] = s[j][3] = -1e30f;
+        }
+        const __nv_bfloat16* kr = ks + (j * 8 + g) * PQ + hl * HD;
+        const uint32_t kb0 = *reinterpret_cast<const uint32_t*>(kr + 2 * t);
+        const uint32_t kb1 = *reinterpret_cast<const uint32_t*>(kr + 2 * t + 8);
+        mma16816(s[j], qa, kb0, kb1);
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float m0s = mx0 * kLog2e, m1s = mx1 * kLog2e;
+      uint32_t pp[NT][2];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        pp[j][0] = ex2_h2(fmaf(s[j][0], kLog2e, -m0s), fmaf(s[j][1], kLog2e, -m0s));
+        pp[j][1] = ex2_h2(fmaf(s[j][2], kLog2e, -m1s), fmaf(s[j][3], kLog2e, -m1s));
+      }
+      float o[2][4], ol[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int v = 0; v < 2; ++v) o[v][0] = o[v][1] = o[v][2] = o[v][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < KSTEPS; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pp[2 * kk][0];
+        pa[1] = pp[2 * kk][1];
+        pa[2] = 2 * kk + 1 < NT ? pp[2 * kk + 1][0] : 0u;
+        pa[3] = 2 * kk + 1 < NT ? pp[2 * kk + 1][1] : 0u;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          uint32_t vb0, vb1;
+          ldsm_x2_trans(vb0, vb1, vs_u32 + (uint32_t)(((kk * 16 + (lane & 15)) * PQ + hl * HD + 8 * v) * 2));
+          mma16816_f16(o[v], pa, vb0, vb1);
+        }
+        mma16816_f16(ol, pa, kOnes, kOnes);   // row sums
+      }
+      const float inv0 = 1.0f / ol[0], inv1 = 1.0f / ol[2];
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int col = hg * 64 + hl * HD + 8 * v + 2 * t;
+        *reinterpret_cast<uint32_t*>(os + row0 * PX + col) = pack2(o[v][0] * inv0, o[v][1] * inv0);
+        *reinterpret_cast<uint32_t*>(os + row1 * PX + col) = pack2(o[v][2] * inv1, o[v][3] * inv1);
+      }
+    }
+    // the next slice_gemm starts with a __syncthreads(): q / k / v tiles are not rewritten before every warp is past here
+  }
+
+  // ---- output projection + window_reverse + shortcut: x[pix] += proj(o) + b, 64 output columns per weight slice --------
+  for (int js = 0; js < 4; ++js) {
+    float acc[1][2][4];
+    acc[0][0][0] = acc[0][0][1] = acc[0][0][2] = acc[0][0][3] = acc[0][1][0] = acc[0][1][1] = acc[0][1][2] = acc[0][1][3] = 0.f;
+    slice_gemm(acc, 1, os_u32, [&](int i, int r) { return mq * 16 + r; });
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const int r = mq * 16 + g + hrow * 8;
+      const int pix = r < kTok ? pix_s[r] : -1;
+      if (pix >= 0) {
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          const int col = js * 64 + npair * 16 + n * 8 + 2 * t;
+          const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bproj + col));
+          float2* dst = reinterpret_cast<float2*>(p.xs + (size_t)pix * C + col);
+          float2 cur = *dst;
+          cur.x += acc[0][n][hrow * 2 + 0] + bb.x;
+          cur.y += acc[0][n][hrow * 2 + 1] + bb.y;
+          *dst = cur;
+        }
+      }
+    }
+  }
+}
+
+template <int NT>
+int launch_win256(const FusedAttnParams& p, cudaStream_t s) {
+  using Cfg = WinCfg<NT>;
+  auto kern = attn_win256_kernel<NT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    BDE_REQUIRE(e == cudaSuccess, "bde_window_attention_fused: smem attribute (%d bytes): %s", Cfg::SMEM, cudaGetErrorString(e));
+    configured = true;
+  }
+  kern<<<p.n_win, kThreadsW, Cfg::SMEM, s>>>(p);
+  return check_launch("attn_win256_kernel");
+}
+
 }  // namespace
 }  // namespace bde
 
@@ -626,8 +991,8 @@ extern "C" int bde_window_attention_fused(const float* const* frames_host, int D
   BDE_REQUIRE(q_slot >= 0 && q_slot < D && frames_host != nullptr && tok_map != nullptr && wqkv != nullptr && bqkv != nullptr &&
                   bias_tbl != nullptr,
               "bde_window_attention_fused: bad arguments");
-  BDE_REQUIRE(c == 64 ? (wproj != nullptr && bproj != nullptr && xs != nullptr) : o_out != nullptr,
-              "bde_window_attention_fused: missing output operands");
+  const bool with_proj = wproj != nullptr && bproj != nullptr && xs != nullptr;
+  BDE_REQUIRE(c == 64 ? with_proj : (with_proj || o_out != nullptr), "bde_window_attention_fused: missing output operands");
   BDE_REQUIRE((((uintptr_t)wqkv) & 15) == 0 && (((uintptr_t)bias_tbl) & 15) == 0 && (((uintptr_t)wproj) & 15) == 0,
               "bde_window_attention_fused: operands must be 16-byte aligned");
   FusedAttnParams p;
@@ -649,6 +1014,13 @@ extern "C" int bde_window_attention_fused(const float* const* frames_host, int D
     default: return launch_fused<C_, HD_, 19>(p, s);             \
   }
   if (c == 64) { BDE_FUSED(64, 4) }
+  if (with_proj) {   // c == 256 with the projection fused: whole-window kernel
+    switch (D) {
+      case 1: return launch_win256<7>(p, s);
+      case 2: return launch_win256<13>(p, s);
+      default: return launch_win256<19>(p, s);
+    }
+  }
   BDE_FUSED(256, 16)
 #undef BDE_FUSED
 }

@@ -118,6 +118,7 @@ class Engine:
         self.depths = cfg["depths"]
         self.fuse_attn = os.environ.get("BDE2VID_FUSED_ATTN", "1") != "0"
         self.fuse_mlp = os.environ.get("BDE2VID_FUSED_MLP", "1") != "0"
+        self.fuse_win256 = os.environ.get("BDE2VID_ATTN_WIN256", "1") != "0"
         if self.bins > VOX_CPAD:
             raise NotImplementedError("num_bins > %d" % VOX_CPAD)
         dt = self.dtype
@@ -495,7 +496,10 @@ class _Plan:
                 fr[eng.q_ind] = xs
                 if blk["tbl"] is not None:
                     # one kernel for the attention half; C == 64 also projects and scatters into xs
-                    if C == 64:
+                    if C == 64 or (eng.fuse_win256 and nwin >= 64):
+                        # C = 256: whole-window kernel (gather + LN once per window, projection + scatter fused) once
+                        # there are enough windows to fill the SMs with one CTA each; below that (a single sequence
+                        # has 35 level-3 windows) the per-head-group kernel's 4 CTAs per window finish sooner
                         ops.window_attention_fused(fr, eng.q_ind, tm.view(-1), nwin, C, eng.heads, blk["qkv"].w,
                                                    blk["qkv"].bias, blk["tbl"], blk["proj"].w, blk["proj"].bias, xs=xs)
                         self.launches += 1
