@@ -382,9 +382,10 @@ extern "C" int bde_voxelize_seq_strided(const float* xs, const float* ys, const 
     if (e != nullptr && e[0] >= '1' && e[0] <= '3') algo = e[0] - '0';
   }
   if (algo == 0) algo = cluster_ok ? 3 : ((bands <= 16) ? 1 : 2);
+  // the cluster form needs a grid that fits 8 CTAs' shared memory, Wp % 4 == 0 and a 16-byte aligned output; otherwise
+  // the request degrades to the row-band / atomic kernels
+  if (algo == 3 && !cluster_ok) algo = (bands <= 16) ? 1 : 2;
   if (algo == 3) {
-    BDE_REQUIRE(cluster_ok, "bde_voxelize_seq: the cluster algorithm needs a grid that fits 8 CTAs' shared memory, Wp %% 4 == 0 and a "
-                            "16-byte aligned output");
     const size_t smem = (size_t)num_bins * crow * W * sizeof(float);
     static size_t configured = 0;
     if (smem > configured) {

@@ -262,3 +262,88 @@ def test_tcgen05_layernorm_gather_gemm(C, N, D):
     err = (out.float().cpu() - ref).abs().max()
     print("ln-gemm", C, N, D, float(err), float(ref.abs().max()))
     assert err <= 3e-2 * max(1.0, float(ref.abs().max()))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# TMA-fed persistent convolution kernel (gemm_tc_conv.cu): every form it can take, against torch conv2d
+# ---------------------------------------------------------------------------------------------------------------------
+TMA_CONV_CASES = [
+    # n, cin, cout, h, w, k, stride
+    (8, 128, 64, 40, 70, 5, 1),     # decoder-like, enough tiles for the dual-tile form, ragged right / bottom border
+    (6, 64, 32, 37, 90, 5, 1),      # N = 32 (dec2-like)
+    (8, 256, 128, 24, 44, 3, 1),    # 3x3, N = 128
+    (1, 64, 64, 8, 16, 3, 1),       # exactly one tile
+    (2, 64, 128, 33, 44, 5, 2),     # stride 2: strided TMA taps
+    (2, 128, 256, 16, 24, 5, 2),
+]
+TMA_CONV_MODES = {
+    "default": {},
+    "single_tile": {"BDE2VID_CONV_DUAL": "0"},
+    "tap_boxes": {"BDE2VID_CONV_HALO": "0"},
+    "cta_pair": {"BDE2VID_CONV_PAIR": "1", "BDE2VID_CONV_DUAL": "0"},
+    "x_major_atoms": {"BDE2VID_CONV_SWAP": "0"},
+    "generic_epilogue": {"BDE2VID_CONV_EPI_SPEC": "0"},
+    "old_engine": {"BDE2VID_CONV_TMA": "0"},
+}
+
+
+@pytest.mark.parametrize("mode", sorted(TMA_CONV_MODES))
+@pytest.mark.parametrize("case", TMA_CONV_CASES)
+def test_conv_tma_forms(case, mode):
+    from bde2vid_b200 import ops
+    n, ci, co, h, w, k, s = case
+    g = torch.Generator().manual_seed(sum(case) + 5)
+    x = bf16r(torch.randn(n, ci, h, w, generator=g))
+    wt = bf16r(torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5)
+    b = torch.randn(co, generator=g)
+    ref = F.relu(F.conv2d(x, wt, b, stride=s, padding=k // 2))
+    old = {kk: os.environ.get(kk) for kk in TMA_CONV_MODES[mode]}
+    os.environ.update(TMA_CONV_MODES[mode])
+    try:
+        got = run_conv([x], wt, b, s, ops.ENGINE_TCGEN05, torch.bfloat16, act=ops.ACT_RELU, chunk_major=True)
+    finally:
+        for kk, v in old.items():
+            if v is None:
+                os.environ.pop(kk, None)
+            else:
+                os.environ[kk] = v
+    err = (got - ref).abs().max()
+    print("conv_tma", mode, case, float(err))
+    assert err <= 1e-2 * max(1.0, ref.abs().max())
+
+
+@pytest.mark.parametrize("pair", ["0", "1"])
+@pytest.mark.parametrize("B,hid,h,w", [(2, 64, 17, 22), (3, 128, 9, 19), (1, 256, 33, 44), (4, 64, 40, 48)])
+def test_conv_tma_lstm_epilogue(B, hid, h, w, pair):
+    """ConvLSTM step through the TMA conv kernel (chunk-major weights, two A sources, specialised gate epilogue;
+    submodules.py:316-332), with and without the cta_group::2 pair form."""
+    from bde2vid_b200 import ops
+    from bde2vid_b200.engine import _pack_conv
+    g = torch.Generator().manual_seed(hid + h + w)
+    rnd = lambda *s: bf16r(torch.randn(*s, generator=g))  # noqa: E731
+    x, hp = rnd(B, hid, h, w), rnd(B, hid, h, w) * 0.5
+    cp = torch.randn(B, hid, h, w, generator=g)
+    wt = bf16r(rnd(4 * hid, 2 * hid, 3, 3) / (18 * hid) ** 0.5)
+    b = torch.randn(4 * hid, generator=g) * 0.1
+    h_ref, c_ref = lstm_ref(x, hp, cp, wt, b)
+    wi = wt.view(4, hid, 2 * hid, 3, 3).permute(1, 0, 2, 3, 4).reshape(4 * hid, 2 * hid, 3, 3)
+    bi = b.view(4, hid).t().reshape(-1).contiguous()
+    pw, ld = _pack_conv(wi.to(DEV), torch.bfloat16, chunk_major=True)
+    hout = torch.zeros(B, h, w, hid, dtype=torch.bfloat16, device=DEV)
+    cout = torch.zeros(B, h, w, hid, dtype=torch.float32, device=DEV)
+    old = os.environ.get("BDE2VID_CONV_PAIR")
+    os.environ["BDE2VID_CONV_PAIR"] = pair
+    try:
+        ops.gemm(nhwc(x, torch.bfloat16), pw, bi.to(DEV), hout, n_img=B, h_in=h, w_in=w, c0=hid, n=4 * hid, ksize=3, stride=1,
+                 pad=1, a1=nhwc(hp, torch.bfloat16), c1=hid, w_ld=ld, epi=ops.EPI_LSTM, c_prev=nhwc(cp, torch.float32),
+                 c_out=cout, engine=ops.ENGINE_TCGEN05, dtype=torch.bfloat16, k_order=1)
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("BDE2VID_CONV_PAIR", None)
+        else:
+            os.environ["BDE2VID_CONV_PAIR"] = old
+    eh = (hout.float().cpu().permute(0, 3, 1, 2) - h_ref).abs().max()
+    ec = (cout.cpu().permute(0, 3, 1, 2) - c_ref).abs().max()
+    print("conv_tma lstm pair", pair, (B, hid, h, w), float(eh), float(ec))
+    assert ec <= 2e-3 and eh <= 6e-3
