@@ -70,9 +70,8 @@ __device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
   return v;
 }
-// P.V runs in fp16 (fp32 accumulate): the probabilities come out of ONE MUFU op per pair (ex2.approx.f16x2 -- the
-// special-function unit is the busiest pipe of this kernel at head_dim 4) and fp16 carries 3 more mantissa bits
-// than bf16; p <= 1 and |v| is O(10), far inside the fp16 range.
+// P.V runs in fp16 (fp32 accumulate): fp16 carries 3 more mantissa bits than bf16 for the probabilities;
+// p <= 1 and |v| is O(10), far inside the fp16 range.
 __device__ __forceinline__ void mma16816_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -84,11 +83,13 @@ __device__ __forceinline__ uint32_t pack2_h(float lo, float hi) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
-// (2^lo, 2^hi) as an fp16 pair
+// (2^lo, 2^hi) as an fp16 pair.  Two fp32 MUFU.EX2 + one packing convert: ex2.approx.f16x2 is NOT a single MUFU op on
+// sm_100a (ptxas expands it to unpack + 2 x MUFU.EX2 + pack: measured +30 % instructions in this kernel).
 __device__ __forceinline__ uint32_t ex2_h2(float lo, float hi) {
-  uint32_t x = pack2_h(lo, hi), y;
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
+  float a, b;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(lo));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(hi));
+  return pack2_h(a, b);
 }
 
 template <int C, int HD, int NT>
