@@ -11,8 +11,13 @@ CMD="python bench.py --windows 6 --steps 1 --warmup 3 --concurrent 1 --batch 4 -
 timeout 600 $CMD > gpurun_out/plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu.log 2>&1
 echo "ncu launch list exit $?"
-CMD1="python bench.py --windows 4 --steps 1 --warmup 3 --concurrent 1 --batch 1 --no-cpu-baseline --no-kernel-timing"
-timeout 600 $CMD1 > gpurun_out/plain1.log 2>&1 && \
-timeout 600 ncu --set full --clock-control none -k regex:gemm_tc_kernel -s 3 -c 2 -o gpurun_out/prof_lstm_l1 $CMD1 > gpurun_out/ncu1.log 2>&1; echo "ncu full exit $?"
-ncu -i gpurun_out/prof_lstm_l1.ncu-rep --page raw --csv > gpurun_out/prof_lstm_l1.raw.csv 2>/dev/null
-ls -la gpurun_out | head -30
+CMD1="python bench.py --windows 4 --steps 1 --warmup 3 --concurrent 1 --batch 4 --no-cpu-baseline --no-kernel-timing"
+timeout 600 $CMD1 > gpurun_out/plain1.log 2>&1
+# ConvLSTM gate conv (L1, then L2, L3 of the same step), level-1 / level-3 fused attention, fused MLPs, voxeliser
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:conv_tma_kernel -s 12 -c 3 -o gpurun_out/prof_conv_lstm $CMD1 > gpurun_out/ncu1.log 2>&1; echo "ncu conv exit $?"
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:attn_fused_kernel -s 20 -c 1 -o gpurun_out/prof_attn64 $CMD1 > gpurun_out/ncu2.log 2>&1; echo "ncu attn64 exit $?"
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:attn_win256_kernel -s 30 -c 1 -o gpurun_out/prof_attn_win256 $CMD1 > gpurun_out/ncu3.log 2>&1; echo "ncu win256 exit $?"
+timeout 600 ncu --set full --clock-control none -k regex:mlp_fused -s 60 -c 2 -o gpurun_out/prof_mlp $CMD1 > gpurun_out/ncu4.log 2>&1; echo "ncu mlp exit $?"
+timeout 600 ncu --set full --clock-control none -k regex:voxel_cluster_kernel -s 4 -c 1 -o gpurun_out/prof_voxel $CMD1 > gpurun_out/ncu5.log 2>&1; echo "ncu voxel exit $?"
+for f in prof_conv_lstm prof_attn64 prof_attn_win256 prof_mlp prof_voxel; do ncu -i gpurun_out/$f.ncu-rep --page raw --csv > gpurun_out/$f.raw.csv 2>/dev/null; done
+ls -la gpurun_out | head -40
