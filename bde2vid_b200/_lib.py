@@ -45,6 +45,7 @@ EXPORTS = {
     "bde_voxelize_seq": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "bde_voxelize_seq_strided": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 8 + [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
                                            C.c_void_p]),
+    "bde_frame_metrics": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_double, C.c_void_p, C.c_void_p]),
     "bde_head_conv": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]),
     "bde_pack_voxel_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_void_p]),
     "bde_profile_begin": (C.c_int, [C.c_int]),

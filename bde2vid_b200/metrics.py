@@ -1,0 +1,42 @@
+"""Evaluation metrics on the device + the path's only collective.
+
+The reference computes MSE / SSIM / LPIPS per frame on the host (eval_models_seq.py:242-258 -> evaluate/metrics.py) and
+averages them per file (:278-282).  Here one kernel launch produces (mse, ssim) for every frame of a sequence, the sums
+stay on the GPU until a single all-reduce across the ranks that share the evaluation.  LPIPS needs AlexNet weights that
+are not available offline and stays out of scope.
+"""
+import torch
+
+from . import ops
+from .dist import finalize_means, reduce_metric_sums
+
+
+def sequence_metric_sums(frames, gts, croper, data_range=1.0):
+    """frames: list of T tensors [1, 1, Hp, Wp] (model output, padded) or one tensor [T, Hp, Wp]; gts: [T, H, W] float32.
+    Returns {'mse': sum, 'ssim': sum, 'n': T} for this sequence (python floats; one device -> host read)."""
+    if isinstance(frames, (list, tuple)):
+        pred = torch.stack([f.reshape(f.shape[-2], f.shape[-1]) for f in frames], 0)
+    else:
+        pred = frames
+    pred = pred.to(torch.float32).contiguous()
+    gts = gts.to(device=pred.device, dtype=torch.float32).contiguous()
+    T, Hp, Wp = pred.shape
+    H, W = gts.shape[-2:]
+    y0 = Hp // 2 - H // 2        # Croper.crop: rows [cy - floor(H/2), cy + ceil(H/2))  (inference_utils.py:26-32,112-114)
+    x0 = Wp // 2 - W // 2
+    if croper is not None:
+        assert (croper.height_crop_size, croper.width_crop_size) == (Hp, Wp)
+    per_frame = ops.frame_metrics(pred, gts.reshape(T, H, W), y0, x0, data_range)
+    s = per_frame.sum(0).tolist()
+    return {"mse": s[0], "ssim": s[1], "n": float(T)}, per_frame
+
+
+def evaluate(sequences, data_range=1.0):
+    """sequences: iterable of (frames, gts, croper) owned by THIS rank.  Returns the per-frame means over all ranks
+    (one all-reduce of the metric sums; eval_models_seq.py:278-282)."""
+    total = {"mse": 0.0, "ssim": 0.0, "n": 0.0}
+    for frames, gts, croper in sequences:
+        s, _ = sequence_metric_sums(frames, gts, croper, data_range)
+        for k in total:
+            total[k] += s[k]
+    return finalize_means(reduce_metric_sums(total))

@@ -52,6 +52,19 @@ def pack_voxel_nhwc(vox, c_pad, dtype, out=None):
     return out
 
 
+def frame_metrics(pred, gt, y0, x0, data_range=1.0):
+    """pred float32 [n, Hp, Wp] (padded model output), gt float32 [n, H, W] -> float64 [n, 2] = (mse, ssim) per frame
+    of pred[:, y0:y0+H, x0:x0+W] vs gt (evaluate/metrics.py:42-65)."""
+    lib = _lib.require_device()
+    n, Hp, Wp = pred.shape
+    _, H, W = gt.shape
+    assert pred.dtype == torch.float32 and gt.dtype == torch.float32 and pred.is_contiguous() and gt.is_contiguous()
+    out = torch.zeros(n, 2, dtype=torch.float64, device=pred.device)
+    check(lib.bde_frame_metrics(ptr(pred), ptr(gt), n, H, W, Hp, Wp, y0, x0, float(data_range), ptr(out), stream_ptr()),
+          "bde_frame_metrics")
+    return out
+
+
 def head_conv(vox, w, bias, out, act=ACT_RELU):
     """float32 planar [N, Cin, H, W] voxels x float32 [32, Cin, 5, 5] weights -> bf16 NHWC [N, H, W, 32]."""
     lib = _lib.require_device()

@@ -327,7 +327,11 @@ def main():
         peak = pk["tc_sustained"]
         roofline = {"kernel": "bde_gemm tcgen05 kernels: conv_tma_kernel (TMA-fed persistent convs: ConvLSTM gates, "
                               "decoders, stride-2 encoders) + gemm_tc_kernel (enc0, L3 proj)", "bound": "tensor",
-                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    # DRAM bytes (read + write) per launch from the committed ncu --set full capture of three
+                    # consecutive ConvLSTM gate convs (profiles/r01_ncu_full_prof_conv_lstm.metrics.txt): 26.3 / 49.2 /
+                    # 14.3 MB; operands are served from L2 (algorithmic operand bytes per launch: 24-48 MB)
+                    "traffic": 29.9e6, "traffic_source": "ncu capture, mean of 3 ConvLSTM launches (not live)",
                     "launches": n_rec, "avg_launch_us": gemm_ms * 1e3 / max(1, n_rec),
                     "kernel_ms_per_step": gemm_ms, "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
                     "flops_per_step": flops}

@@ -146,6 +146,14 @@ typedef struct bde_gemm_desc {
 
 int bde_gemm(const bde_gemm_desc* desc, void* stream);
 
+/* Per-frame MSE and SSIM of the centre-cropped prediction against the ground truth, on the device
+ * (eval_models_seq.py:242-258; evaluate/metrics.py:42-65: F.mse_loss, skimage structural_similarity defaults: 7x7
+ * uniform window, K1 = .01, K2 = .03, sample covariance, mean over the valid interior; data_range as given).
+ *   pred float32 [n, Hp, Wp] (crop window at (y0, x0), size H x W = Croper.crop)   gt float32 [n, H, W]
+ *   out  float64 [n, 2] = (mse, ssim) per frame; accumulated atomically, the caller zeroes it first. */
+int bde_frame_metrics(const float* pred, const float* gt, int n, int H, int W, int Hp, int Wp, int y0, int x0,
+                      double data_range, double* out, void* stream);
+
 /* Measurement hook: between bde_profile_begin(max) and bde_profile_end every tcgen05 bde_gemm launch is
  * bracketed by a pair of CUDA events on its stream; bde_profile_end returns the summed kernel time (ms)
  * and the number of launches.  Not for use under stream capture. */

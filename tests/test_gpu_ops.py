@@ -227,3 +227,20 @@ def test_head_conv(shape):
     err = float((got - ref).abs().max())
     print("head_conv", shape, err, float(ref.abs().max()))
     assert err <= 1e-2 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("H,W,Hp,Wp", [(260, 346, 264, 352), (180, 240, 184, 240), (33, 47, 40, 48)])
+def test_frame_metrics_vs_oracle(H, W, Hp, Wp):
+    """Device MSE / SSIM of the centre crop vs the oracle restatement (evaluate/metrics.py:42-65)."""
+    from bde2vid_b200 import ops
+    from oracle import oracle_torch as O
+    g = torch.Generator().manual_seed(H + W)
+    n = 3
+    pred = torch.rand(n, Hp, Wp, generator=g)
+    y0, x0 = Hp // 2 - H // 2, Wp // 2 - W // 2
+    gt = (pred[:, y0:y0 + H, x0:x0 + W] + 0.1 * torch.randn(n, H, W, generator=g)).clamp(0, 1).contiguous()
+    out = ops.frame_metrics(pred.to(DEV), gt.to(DEV), y0, x0, 1.0).cpu()
+    for i in range(n):
+        crop = pred[i, y0:y0 + H, x0:x0 + W]
+        assert abs(float(out[i, 0]) - O.mse(crop, gt[i])) <= 1e-7
+        assert abs(float(out[i, 1]) - O.ssim_uniform7(crop, gt[i])) <= 1e-6
