@@ -70,6 +70,8 @@ EXPORTS = {
     "bde_window_attention_fused_supported": (C.c_int, [C.c_int] * 4),
     "bde_window_attention_fused": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
                                    + [C.c_void_p] * 8),
+    "bde_window_attention_fused_kvpre": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p,
+                                                    C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7),
     "bde_mlp_fused_supported": (C.c_int, [C.c_int, C.c_int]),
     "bde_mlp_fused": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int] + [C.c_void_p] * 5),
     "bde_cast": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),

@@ -32,6 +32,10 @@ struct FusedAttnParams {
   float* xs;                     // fp32 [P, C] += proj(attn)      (C == 64)
   __nv_bfloat16* o_out;          // bf16 [n_win * 49, C]           (C == 256)
   int n_win, D, q_slot, heads;
+  // whole-window kernel with precomputed neighbour k / v (kPre): bf16 [P, kv_ld[d]] rows = [k (C) | v (C)] of frame d,
+  // already offset to the block's columns; NULL = all-zero frame (k / v = bias).  Unused for the query slot.
+  const __nv_bfloat16* kvpre[8];
+  int kv_ld[8];
 };
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -618,7 +622,7 @@ int launch_fused(const FusedAttnParams& p, cudaStream_t s) {
 // =====================================================================================================================
 constexpr int kThreadsW = 512;
 
-template <int NT>
+template <int NT, bool kPre = false>
 struct WinCfg {
   static constexpr int C = 256, HD = 16, HG = 4, NHG = 4;
   static constexpr int PX = C + 8;                // LayerNorm'ed tokens / attention-output pitch (bf16 elements)
@@ -628,9 +632,11 @@ struct WinCfg {
   static constexpr int XROWS = KSTEPS * 16;
   static constexpr int NKEY = NT * 8;
   static constexpr int DMAX = NT <= 7 ? 1 : (NT <= 13 ? 2 : 3);
+  static constexpr int XNROWS = kPre ? 64 : XROWS;                // LayerNorm'ed token rows staged (kPre: query frame only)
+  static constexpr int NBUF = kPre ? 5 : 2;                       // weight half-slice buffers (prefetch distance NBUF - 1)
   static constexpr int OFF_XN = 0;
-  static constexpr int OFF_WB = OFF_XN + XROWS * PX * 2;          // 2 x [64 x PH]
-  static constexpr int OFF_Q = OFF_WB + 2 * 64 * PH * 2;
+  static constexpr int OFF_WB = OFF_XN + XNROWS * PX * 2;         // NBUF x [64 x PH]
+  static constexpr int OFF_Q = OFF_WB + NBUF * 64 * PH * 2;
   static constexpr int OFF_K = OFF_Q + 64 * PQ * 2;
   static constexpr int OFF_V = OFF_K + NKEY * PQ * 2;
   static constexpr int OFF_O = OFF_V + XROWS * PQ * 2;            // [64 x PX] attention output of all heads
@@ -643,32 +649,49 @@ struct WinCfg {
 };
 
 // acc[i][n][4] += A[rows, k0 .. k0 + 128) (smem, pitch PX) * Whalf[64, 128]^T (smem, pitch PH)
+// Software pipelined: the ldmatrix loads of k step kk + 1 are issued before the MMAs of step kk (the profile of the
+// straight loop showed the HMMAs stalled on the short scoreboard, i.e. on their own fragments).
 template <int PX, int PH, int MT, typename RowFn>
 __device__ __forceinline__ void warp_gemm_half(float (&acc)[MT][2][4], int n_mt, uint32_t a_base, RowFn a_row, int k0, uint32_t w_base,
                                                int npair, int lane) {
   const int bm = lane >> 3;
   const uint32_t b_addr0 = w_base + (uint32_t)(((npair * 16 + (bm >> 1) * 8 + (lane & 7)) * PH + (bm & 1) * 8) * 2);
-#pragma unroll 4
+  uint32_t a_addr[MT];
+#pragma unroll
+  for (int i = 0; i < MT; ++i) a_addr[i] = a_base + (uint32_t)((a_row(i, lane & 15) * PX + k0 + (lane >> 4) * 8) * 2);
+  uint32_t b[2][4], a[2][MT][4];
+  ldsm_x4(b[0], b_addr0);
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+    if (i < n_mt) ldsm_x4(a[0][i], a_addr[i]);
+#pragma unroll
   for (int kk = 0; kk < 8; ++kk) {
-    uint32_t b[4];
-    ldsm_x4(b, b_addr0 + (uint32_t)(kk * 32));
+    const int cur = kk & 1, nxt = cur ^ 1;
+    if (kk + 1 < 8) {
+      ldsm_x4(b[nxt], b_addr0 + (uint32_t)((kk + 1) * 32));
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+        if (i < n_mt) ldsm_x4(a[nxt][i], a_addr[i] + (uint32_t)((kk + 1) * 32));
+    }
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
       if (i < n_mt) {
-        uint32_t a[4];
-        ldsm_x4(a, a_base + (uint32_t)((a_row(i, lane & 15) * PX + k0 + kk * 16 + (lane >> 4) * 8) * 2));
-        mma16816(acc[i][0], a, b[0], b[1]);
-        mma16816(acc[i][1], a, b[2], b[3]);
+        mma16816(acc[i][0], a[cur][i], b[cur][0], b[cur][1]);
+        mma16816(acc[i][1], a[cur][i], b[cur][2], b[cur][3]);
       }
     }
   }
 }
 
-template <int NT>
+// kPre: the k / v rows of the D - 1 neighbour frames were produced ahead of the chain by LayerNorm-GEMM launches on the
+// tcgen05 engine (they do not depend on the running x) and are only gathered here; the kernel then normalises and
+// projects just the 49 query-frame tokens (q, k, v), i.e. 64 instead of 160 rows per weight slice.
+template <int NT, bool kPre>
 __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAttnParams p) {
-  using Cfg = WinCfg<NT>;
+  using Cfg = WinCfg<NT, kPre>;
+  constexpr int XNROWS = Cfg::XNROWS;
   constexpr int C = Cfg::C, HD = Cfg::HD, HG = Cfg::HG, PX = Cfg::PX, PH = Cfg::PH, PQ = Cfg::PQ;
-  constexpr int KSTEPS = Cfg::KSTEPS, XROWS = Cfg::XROWS, NKEY = Cfg::NKEY;
+  constexpr int KSTEPS = Cfg::KSTEPS, XROWS = Cfg::XROWS, NKEY = Cfg::NKEY, NBUF = Cfg::NBUF;
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
   __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_XN);
@@ -696,14 +719,15 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
     } else {
       src = p.wproj + (size_t)((sl - 12) * 64) * C + half * 128;
     }
-    const uint32_t dst = sb + Cfg::OFF_WB + (uint32_t)((hs & 1) * 64 * PH * 2);
+    const uint32_t dst = sb + Cfg::OFF_WB + (uint32_t)((hs % NBUF) * 64 * PH * 2);
     for (int i = tid; i < 64 * 16; i += kThreadsW) {
       const int r = i >> 4, ch = i & 15;
       cpa16(dst + (uint32_t)((r * PH + ch * 8) * 2), src + (size_t)r * C + ch * 8);
     }
     cpa_commit();
   };
-  load_half(0);
+#pragma unroll
+  for (int i = 0; i < NBUF - 1; ++i) load_half(i);
 
   // ---- index tables -----------------------------------------------------------------------------------
   for (int n = tid; n < NKEY; n += kThreadsW) {
@@ -724,12 +748,12 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
   // ---- gather + LayerNorm, once per window: 8 lanes per token, 64 tokens per pass ---------------------
   {
     const int j = lane & 7, sub = lane >> 3;
-    for (int pass = 0; pass * 64 < XROWS; ++pass) {
+    for (int pass = 0; pass * 64 < XNROWS; ++pass) {
       const int n = pass * 64 + warp * 4 + sub;
-      if (n >= XROWS) continue;   // uniform per 4-token group; XROWS is a multiple of 16
+      if (n >= XNROWS) continue;   // uniform per 4-token group; XNROWS is a multiple of 16
       const float* src = nullptr;
-      if (n < n_kv) {
-        const int d = n / kTok, tok = n - d * kTok;
+      if (kPre ? n < kTok : n < n_kv) {
+        const int d = kPre ? p.q_slot : n / kTok, tok = kPre ? n : n - (n / kTok) * kTok;
         const int pix = pix_s[tok];
         const float* fr = p.frames[0];
 #pragma unroll
@@ -793,15 +817,57 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
   auto slice_gemm = [&](auto& acc, int n_mt, uint32_t a_base, auto a_row) {
 #pragma unroll
     for (int half = 0; half < 2; ++half, ++hs) {
-      cpa_wait<0>();
-      __syncthreads();                       // half-slice hs landed; every warp is done with buffer (hs + 1) & 1
-      if (hs + 1 < 32) load_half(hs + 1);
+      cpa_wait<NBUF - 2>();                  // all but the NBUF - 2 youngest groups are complete: half-slice hs landed
+      __syncthreads();                       // ... for every thread; every warp is done with buffer (hs - 1) % NBUF
+      if (hs + NBUF - 1 < 32) load_half(hs + NBUF - 1); else cpa_commit();   // (empty group keeps the count uniform)
       warp_gemm_half<PX, PH, (int)(sizeof(acc) / sizeof(acc[0]))>(acc, n_mt, a_base, a_row, half * 128,
-                                                                   sb + Cfg::OFF_WB + (uint32_t)((hs & 1) * 64 * PH * 2), npair, lane);
+                                                                   sb + Cfg::OFF_WB + (uint32_t)((hs % NBUF) * 64 * PH * 2), npair, lane);
     }
   };
 
+  if (kPre) {
+    // rows past the last key: finite zeros (they are masked in the scores / multiplied by p = 0)
+    for (int i = tid; i < (NKEY - n_kv) * 64; i += kThreadsW) ks[(n_kv + i / 64) * PQ + (i & 63)] = __float2bfloat16_rn(0.f);
+    for (int i = tid; i < (XROWS - n_kv) * 64; i += kThreadsW) vs[(n_kv + i / 64) * PQ + (i & 63)] = __float2bfloat16_rn(0.f);
+  }
   for (int hg = 0; hg < Cfg::NHG; ++hg) {
+    if (kPre) {
+      // ---- neighbour frames: gather the precomputed k / v columns of this head group (v: bf16 -> fp16) -------------------
+      if (hg > 0) __syncthreads();   // every warp is done with the previous group's k / v tiles
+      const int per = kTok * (p.D - 1);
+      for (int i = tid; i < 2 * per * 8; i += kThreadsW) {
+        const int c8 = i & 7, rest = i >> 3;
+        const int which = rest / per, ti = rest - which * per;          // 0 = k, 1 = v
+        const int dd = ti / kTok, tok = ti - dd * kTok;
+        const int d = dd < p.q_slot ? dd : dd + 1;
+        const int pix = pix_s[tok];
+        const __nv_bfloat16* src = p.kvpre[0];
+        int ld = p.kv_ld[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) {
+          src = (d == q) ? p.kvpre[q] : src;
+          ld = (d == q) ? p.kv_ld[q] : ld;
+        }
+        uint4 val;
+        if (src != nullptr && pix >= 0) {
+          val = __ldg(reinterpret_cast<const uint4*>(src + (size_t)pix * ld + which * C + hg * 64 + c8 * 8));
+        } else {   // zero token: LayerNorm(0) = 0 -> k / v = folded bias
+          const float* bs = p.bqkv + (1 + which) * C + hg * 64 + c8 * 8;
+          val.x = pack2(__ldg(bs + 0), __ldg(bs + 1)); val.y = pack2(__ldg(bs + 2), __ldg(bs + 3));
+          val.z = pack2(__ldg(bs + 4), __ldg(bs + 5)); val.w = pack2(__ldg(bs + 6), __ldg(bs + 7));
+        }
+        if (which == 1) {
+          uint32_t wv[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[e]));
+            wv[e] = pack2_h(f2.x, f2.y);
+          }
+          val = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        }
+        *reinterpret_cast<uint4*>((which == 0 ? ks : vs) + (d * kTok + tok) * PQ + c8 * 8) = val;
+      }
+    }
     // ---- q, k, v projections of this head group --------------------------------------------------------------------
     for (int which = 0; which < 3; ++which) {
       const float* bsrc = p.bqkv + which * C + hg * 64 + npair * 16 + 2 * t;
@@ -811,7 +877,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
         float acc[1][2][4];
         acc[0][0][0] = acc[0][0][1] = acc[0][0][2] = acc[0][0][3] = acc[0][1][0] = acc[0][1][1] = acc[0][1][2] = acc[0][1][3] = 0.f;
         const int qrow0 = p.q_slot * kTok;
-        slice_gemm(acc, 1, xn_u32, [&](int i, int r) { return min(qrow0 + mq * 16 + r, XROWS - 1); });
+        slice_gemm(acc, 1, xn_u32, [&](int i, int r) { return kPre ? mq * 16 + r : min(qrow0 + mq * 16 + r, XNROWS - 1); });
         const int r0 = mq * 16 + g;
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
@@ -819,6 +885,22 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
           const int col = npair * 16 + n * 8 + 2 * t;
           *reinterpret_cast<uint32_t*>(qs + r0 * PQ + col) = pack2(acc[0][n][0] + bb.x, acc[0][n][1] + bb.y);
           *reinterpret_cast<uint32_t*>(qs + (r0 + 8) * PQ + col) = pack2(acc[0][n][2] + bb.x, acc[0][n][3] + bb.y);
+        }
+      } else if (kPre) {
+        // k / v of the query frame's own 49 tokens (XN rows 0..63) -> tile rows q_slot * 49 + token
+        float acc[1][2][4];
+        acc[0][0][0] = acc[0][0][1] = acc[0][0][2] = acc[0][0][3] = acc[0][1][0] = acc[0][1][1] = acc[0][1][2] = acc[0][1][3] = 0.f;
+        slice_gemm(acc, 1, xn_u32, [&](int i, int r) { return mq * 16 + r; });
+        __nv_bfloat16* dstm = which == 1 ? ks : vs;
+        const int tok0 = mq * 16 + g, base = p.q_slot * kTok;
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          const float2 bb = n == 0 ? bia0 : bia1;
+          const int col = npair * 16 + n * 8 + 2 * t;
+          const float v00 = acc[0][n][0] + bb.x, v01 = acc[0][n][1] + bb.y, v10 = acc[0][n][2] + bb.x, v11 = acc[0][n][3] + bb.y;
+          if (tok0 < kTok) *reinterpret_cast<uint32_t*>(dstm + (base + tok0) * PQ + col) = which == 1 ? pack2(v00, v01) : pack2_h(v00, v01);
+          if (tok0 + 8 < kTok)
+            *reinterpret_cast<uint32_t*>(dstm + (base + tok0 + 8) * PQ + col) = which == 1 ? pack2(v10, v11) : pack2_h(v10, v11);
         }
       } else {
         float acc[MTK][2][4];
@@ -958,10 +1040,10 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
   }
 }
 
-template <int NT>
+template <int NT, bool kPre>
 int launch_win256(const FusedAttnParams& p, cudaStream_t s) {
-  using Cfg = WinCfg<NT>;
-  auto kern = attn_win256_kernel<NT>;
+  using Cfg = WinCfg<NT, kPre>;
+  auto kern = attn_win256_kernel<NT, kPre>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
@@ -1007,6 +1089,7 @@ extern "C" int bde_window_attention_fused(const float* const* frames_host, int D
   p.xs = xs;
   p.o_out = (__nv_bfloat16*)o_out;
   p.n_win = n_win; p.D = D; p.q_slot = q_slot; p.heads = heads;
+  for (int i = 0; i < 8; ++i) { p.kvpre[i] = nullptr; p.kv_ld[i] = 0; }
   cudaStream_t s = (cudaStream_t)stream;
 #define BDE_FUSED(C_, HD_)                                       \
   switch (D) {                                                   \
@@ -1017,11 +1100,47 @@ extern "C" int bde_window_attention_fused(const float* const* frames_host, int D
   if (c == 64) { BDE_FUSED(64, 4) }
   if (with_proj) {   // c == 256 with the projection fused: whole-window kernel
     switch (D) {
-      case 1: return launch_win256<7>(p, s);
-      case 2: return launch_win256<13>(p, s);
-      default: return launch_win256<19>(p, s);
+      case 1: return launch_win256<7, false>(p, s);
+      case 2: return launch_win256<13, false>(p, s);
+      default: return launch_win256<19, false>(p, s);
     }
   }
   BDE_FUSED(256, 16)
 #undef BDE_FUSED
+}
+
+extern "C" int bde_window_attention_fused_kvpre(const float* xq, const void* const* kv_host, const int* kv_ld, int D, int q_slot,
+                                                const int* tok_map, int n_win, int c, int heads, const void* wqkv,
+                                                const float* bqkv, const float* bias_tbl, const void* wproj, const float* bproj,
+                                                float* xs, void* stream) {
+  if (n_win == 0) return 0;
+  BDE_REQUIRE(c == 256 && heads == 16 && D >= 2 && D <= 3, "bde_window_attention_fused_kvpre: c = 256, 16 heads, D in {2, 3}");
+  BDE_REQUIRE(q_slot >= 0 && q_slot < D && xq != nullptr && kv_host != nullptr && kv_ld != nullptr && tok_map != nullptr &&
+                  wqkv != nullptr && bqkv != nullptr && bias_tbl != nullptr && wproj != nullptr && bproj != nullptr && xs != nullptr,
+              "bde_window_attention_fused_kvpre: bad arguments");
+  FusedAttnParams p;
+  for (int i = 0; i < 8; ++i) {
+    p.frames[i] = nullptr;
+    p.kvpre[i] = nullptr;
+    p.kv_ld[i] = 0;
+  }
+  p.frames[q_slot] = xq;
+  for (int d = 0; d < D; ++d) {
+    if (d == q_slot) continue;
+    p.kvpre[d] = (const __nv_bfloat16*)kv_host[d];
+    p.kv_ld[d] = kv_ld[d];
+    BDE_REQUIRE(kv_host[d] == nullptr || ((((uintptr_t)kv_host[d]) & 15) == 0 && kv_ld[d] % 8 == 0 && kv_ld[d] >= 2 * c),
+                "bde_window_attention_fused_kvpre: k / v rows must be 16-byte aligned with a pitch >= 2c");
+  }
+  p.tok_map = tok_map;
+  p.wqkv = (const __nv_bfloat16*)wqkv;
+  p.bqkv = bqkv;
+  p.tbl = bias_tbl;
+  p.wproj = (const __nv_bfloat16*)wproj;
+  p.bproj = bproj;
+  p.xs = xs;
+  p.o_out = nullptr;
+  p.n_win = n_win; p.D = D; p.q_slot = q_slot; p.heads = heads;
+  cudaStream_t s = (cudaStream_t)stream;
+  return D == 2 ? launch_win256<13, true>(p, s) : launch_win256<19, true>(p, s);
 }

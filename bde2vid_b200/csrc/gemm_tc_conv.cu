@@ -670,7 +670,13 @@ static int env_int(const char* name, int dflt) {
 // 1 if this problem is served by the TMA convolution kernel
 bool conv_tma_eligible(const TcParams& p, bool ln) {
   if (ln || !env_flag("BDE2VID_CONV_TMA", true)) return false;
-  if (p.ksize < 3 || p.ksize > 5 || p.k_order != 1 || p.epi == BDE_EPI_SCATTER) return false;
+  // 3x3 .. 5x5 with chunk-major K, or a 1x1 convolution (any K order: one tap) -- a per-pixel linear layer on an NHWC map
+  if (p.epi == BDE_EPI_SCATTER) return false;
+  if (p.ksize == 1) {
+    if (p.stride != 1 || p.pad != 0 || p.out_f32 || p.residual != nullptr || !env_flag("BDE2VID_CONV_1X1", true)) return false;
+  } else if (p.ksize < 3 || p.ksize > 5 || p.k_order != 1) {
+    return false;
+  }
   if (p.c0 % BK != 0 || p.c1 % BK != 0) return false;
   if (p.stride == 2) {
     if (!env_flag("BDE2VID_CONV_S2", true)) return false;

@@ -119,6 +119,11 @@ class Engine:
         self.fuse_attn = os.environ.get("BDE2VID_FUSED_ATTN", "1") != "0"
         self.fuse_mlp = os.environ.get("BDE2VID_FUSED_MLP", "1") != "0"
         self.fuse_win256 = os.environ.get("BDE2VID_ATTN_WIN256", "1") != "0"
+        # precomputed neighbour k | v for the level-3 attention (bde_window_attention_fused_kvpre): OFF by default.
+        # Measured on B200 (round 1): the attention kernel stays at 66 us per launch with 60 % fewer MMAs and a 5-deep
+        # weight prefetch (it is bound by barrier / shared-memory latency at 16 warps per SM, not by the projections),
+        # while the extra LayerNorm + 1x1-conv launches cost ~12 us per frame: 1982 vs 2021 frames/s.
+        self.kv_pre = os.environ.get("BDE2VID_ATTN_KVPRE", "0") != "0"
         if self.bins > VOX_CPAD:
             raise NotImplementedError("num_bins > %d" % VOX_CPAD)
         dt = self.dtype
@@ -180,7 +185,7 @@ class Engine:
                         #   Linear(LN(x)) = (W diag(gamma)) xhat + (W beta + b),  xhat = (x - mean) / sqrt(var + eps)
                         # q and kv share xhat, so ONE GEMM with N = 3C produces [q | k | v] for every kv token.
                         fused = tc and use_mma and C in (64, 128, 256)
-                        qkv_l = fc1_l = None
+                        qkv_l = fc1_l = kv_l = None
                         if fused:
                             sc = hd ** -0.5
                             Wq, bq = a.q.weight.detach().float(), a.q.bias.detach().float()
@@ -191,6 +196,8 @@ class Engine:
                             bqkv = torch.cat([sc * (Wq @ btq + bq), Wkv @ btk + bkv], 0)
                             w, ld = _pack_linear(Wqkv, dt)
                             qkv_l = _Layer(w, ld, bqkv.contiguous(), 3 * C)
+                            # rows [C, 3C) = k | v: the projection of the neighbour frames, precomputable outside the chain
+                            kv_l = _Layer(w[C:], ld, bqkv[C:].contiguous(), 2 * C)
                             W1, b1 = blk.mlp.fc1.weight.detach().float(), blk.mlp.fc1.bias.detach().float()
                             g2, bt2 = blk.norm2.weight.detach().float(), blk.norm2.bias.detach().float()
                             w, ld = _pack_linear(W1 * g2[None, :], dt)
@@ -207,7 +214,7 @@ class Engine:
                             rows = [tab[((self.q_ind - d) + self.D - 1) * rel:((self.q_ind - d) + self.D) * rel] for d in range(self.D)]
                             tbl = torch.stack(rows, 0).permute(2, 0, 1).contiguous()       # [heads, D, 169]
                         blocks.append(dict(
-                            qkv=qkv_l, fc1_ln=fc1_l, tbl=tbl,
+                            qkv=qkv_l, kv_l=kv_l, fc1_ln=fc1_l, tbl=tbl,
                             bias_mma=ops.pad_bias_for_mma(bias_hmn, self.D * n_tok) if use_mma else None,
                             nq_g=f32(a.norm_q.weight), nq_b=f32(a.norm_q.bias),
                             nkv_g=f32(a.norm_kv.weight), nkv_b=f32(a.norm_kv.bias),
@@ -216,6 +223,11 @@ class Engine:
                             n2_g=f32(blk.norm2.weight), n2_b=f32(blk.norm2.bias),
                             fc1=lin_layer(blk.mlp.fc1), fc2=lin_layer(blk.mlp.fc2)))
                 self.attn.append(blocks)
+                # all blocks' k | v projections stacked: one LayerNorm-GEMM per finished frame (the "past" neighbour)
+                if blocks and all(b["kv_l"] is not None for b in blocks):
+                    w_all = torch.cat([b["kv_l"].w for b in blocks], 0).contiguous()
+                    b_all = torch.cat([b["kv_l"].bias for b in blocks], 0).contiguous()
+                    blocks[0]["kv_all"] = _Layer(w_all, blocks[0]["kv_l"].w_ld, b_all, w_all.shape[0])
             self.dec = [conv_layer(gen.decoders[i][1].conv2d, 1) for i in range(self.L)]
             self.pred_w = f32(gen.predI[1].weight.reshape(-1))
             self.pred_b = f32(gen.predI[1].bias)
@@ -317,6 +329,16 @@ class _Plan:
                          qb=E(nwin * ntok, C), kvb=E(nwin * eng.D * ntok, 2 * C), ob=E(nwin * ntok, C),
                          qkv=E(nwin * eng.D * ntok, 3 * C),
                          yn=E(P, C), hid=E(P, 4 * C))
+                blocks = eng.attn[l]
+                if (C == 256 and eng.fuse_win256 and eng.kv_pre and nwin >= 64 and list(eng.buf) == [-1, 0, 1]
+                        and eng.q_ind == 1 and blocks and "kv_all" in blocks[0]
+                        and all(b["tbl"] is not None for b in blocks)):
+                    # precomputed neighbour k | v: future frames for every block and frame, past frame ping-pong
+                    d["kv_fut"] = E(len(blocks), T, P, 2 * C)
+                    d["kv_past"] = [E(P, len(blocks) * 2 * C) for _ in range(2)]
+                    d["xn_all"] = E(T * P, C)          # LayerNorm'ed (no affine: folded into the weights) features, bf16
+                    d["ln_one"] = torch.ones(C, dtype=f32, device=dev)
+                    d["ln_zero"] = torch.zeros(C, dtype=f32, device=dev)
             self.lv.append(d)
         Tc = min(eng.dec_chunk, T)
         self.Tc = Tc
@@ -481,6 +503,14 @@ class _Plan:
         feat = d["feat"].view(T, P, C)
         feat_t = d["feat_t"].view(T, P, C)
         xs = d["xs"]
+        pre = "kv_fut" in d
+        if pre:
+            # k | v of the (pre-attention) future neighbours, all frames at once per block
+            # (one LayerNorm pass, then per block a 1x1 convolution over the [T*B, h, w, C] map on the TMA conv kernel)
+            ops.layernorm(feat.view(T * P, C), T * P, C, d["ln_one"], d["ln_zero"], d["xn_all"])
+            for i, blk in enumerate(eng.attn[l]):
+                eng._gemm(blk["kv_l"], d["xn_all"], d["kv_fut"][i].view(T * P, 2 * C), T * B, h, w, C)
+            self.launches += 1 + len(eng.attn[l])
         for t in range(T):
             # past neighbours are already post-attention (updated in place), future ones are not: quirk Q1
             frames = [feat[t + o] if 0 <= t + o < T else None for o in eng.buf]      # None = all-zero map (Q4)
@@ -494,6 +524,17 @@ class _Plan:
                 tm = d["tm"][i & 1]
                 fr = list(frames)
                 fr[eng.q_ind] = xs
+                if blk["tbl"] is not None and pre:
+                    kv = [None] * D
+                    if t >= 1:
+                        kv[0] = d["kv_past"][(t - 1) & 1][:, i * 2 * C:(i + 1) * 2 * C]
+                    if t + 1 < T:
+                        kv[2] = d["kv_fut"][i, t + 1]
+                    ops.window_attention_fused_kvpre(xs, kv, eng.q_ind, tm.view(-1), nwin, C, eng.heads, blk["qkv"].w,
+                                                     blk["qkv"].bias, blk["tbl"], blk["proj"].w, blk["proj"].bias, xs)
+                    self.launches += 1
+                    self._mlp(blk, d, xs, P, C)
+                    continue
                 if blk["tbl"] is not None:
                     # one kernel for the attention half; C == 64 also projects and scatters into xs
                     if C == 64 or (eng.fuse_win256 and nwin >= 64):
@@ -545,5 +586,11 @@ class _Plan:
             ops.add(xs, feat[t], out_f32=feat[t], out_t=None if eng.dtype == torch.float32 else feat_t[t],
                     dtype=eng.dtype)
             self.launches += 1
+            if pre and t + 1 < T:
+                # this frame is final: its k | v for every block of the next step (the "past" neighbour there)
+                xn_t = d["xn_all"][t * P:(t + 1) * P]      # (its pre-attention copy is not needed any more)
+                ops.layernorm(feat[t], P, C, d["ln_one"], d["ln_zero"], xn_t)
+                eng._gemm(eng.attn[l][0]["kv_all"], xn_t, d["kv_past"][t & 1], B, h, w, C)
+                self.launches += 2
             if on_frame_done is not None:
                 on_frame_done(t)

@@ -249,6 +249,16 @@ int bde_window_attention_fused(const float* const* frames_host, int D, int q_slo
                                int c, int heads, const void* wqkv, const float* bqkv, const float* bias_tbl,
                                const void* wproj, const float* bproj, float* xs, void* o_out, void* stream);
 
+/* Whole-window form for c = 256 with the k / v rows of the D - 1 neighbour frames precomputed (they do not depend on the
+ * running x, DTransformer.py:376-389: only frames[q_ind] changes inside the block stack): LayerNorm-GEMM launches
+ * (bde_gemm, ln_mode = 1, weights = rows [c, 3c) of wqkv) write bf16 [P, >= 2c] rows = [k | v]; this kernel gathers them
+ * per window, normalises + projects only the 49 query-frame tokens, and fuses attention, projection, window_reverse and
+ * the shortcut into xs.  kv_host[d] = NULL means an all-zero neighbour frame; kv_host[q_slot] is ignored.
+ *   xq: float32 [P, c] query frame (may alias xs)   kv_ld[d]: row pitch of kv_host[d] in elements */
+int bde_window_attention_fused_kvpre(const float* xq, const void* const* kv_host, const int* kv_ld, int D, int q_slot,
+                                     const int* tok_map, int n_win, int c, int heads, const void* wqkv, const float* bqkv,
+                                     const float* bias_tbl, const void* wproj, const float* bproj, float* xs, void* stream);
+
 /* Fused MLP half of a SwinTransformerBlock3D (DTransformer.py:279-283,302-304), in place on the fp32
  * residual stream:  x[m, :] += fc2(GELU(fc1(LayerNorm(x[m, :]))))   for x float32 [rows, c].
  *   w1, b1 : bf16 [hidden, c] / float32 [hidden] with norm2's affine folded in (W diag(gamma), W beta + b)

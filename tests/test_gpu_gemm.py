@@ -275,6 +275,7 @@ TMA_CONV_CASES = [
     (1, 64, 64, 8, 16, 3, 1),       # exactly one tile
     (2, 64, 128, 33, 44, 5, 2),     # stride 2: strided TMA taps
     (2, 128, 256, 16, 24, 5, 2),
+    (4, 256, 512, 33, 44, 1, 1),    # 1x1: a per-pixel linear layer on an NHWC map (k | v precompute)
 ]
 TMA_CONV_MODES = {
     "default": {},

@@ -244,3 +244,66 @@ def test_frame_metrics_vs_oracle(H, W, Hp, Wp):
         crop = pred[i, y0:y0 + H, x0:x0 + W]
         assert abs(float(out[i, 0]) - O.mse(crop, gt[i])) <= 1e-7
         assert abs(float(out[i, 1]) - O.ssim_uniform7(crop, gt[i])) <= 1e-6
+
+
+@pytest.mark.parametrize("dilated,zero_frame", [(False, None), (True, 2), (False, 0)])
+def test_window_attention_whole_window_kernel_c256(dilated, zero_frame):
+    """C = 256: the whole-window kernel (one CTA per window, projection + scatter fused; selected from 64 windows up)
+    against the per-head-group kernel + an fp32 torch projection / window_reverse / shortcut
+    (DTransformer.py:183-207, 294-299).  70 windows, plain and dilated token maps, a missing neighbour frame."""
+    from bde2vid_b200 import ops
+    from bde2vid_b200.engine import window_token_map
+    g = torch.Generator().manual_seed(5 + int(dilated))
+    B, h, w, C, heads, D, q_ind = 2, 35, 49, 256, 16, 3, 1
+    P = B * h * w
+    tm, _ = window_token_map(B, h, w, (7, 7), dilated, DEV)
+    nwin = tm.shape[0]
+    assert nwin >= 64
+    frames = [(torch.randn(P, C, generator=g) * 1.5 + 0.2).to(DEV) for _ in range(D)]
+    if zero_frame is not None:
+        frames[zero_frame] = None
+    wqkv = (torch.randn(3 * C, C, generator=g) / C ** 0.5).to(torch.bfloat16).to(DEV)
+    bqkv = (torch.randn(3 * C, generator=g) * 0.1).to(DEV)
+    table = torch.randn((2 * D - 1) * 169, heads, generator=g) * 0.5
+    rows = [table[((q_ind - d) + D - 1) * 169:((q_ind - d) + D) * 169] for d in range(D)]
+    tbl = torch.stack(rows, 0).permute(2, 0, 1).contiguous().to(DEV)          # [heads, D, 169]
+    wproj = (torch.randn(C, C, generator=g) / C ** 0.5).to(torch.bfloat16).to(DEV)
+    bproj = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    xs0 = frames[q_ind].clone()
+    # reference: per-head-group kernel -> bf16 attention output, then projection + scatter in fp32 torch
+    ob = torch.zeros(nwin * 49, C, dtype=torch.bfloat16, device=DEV)
+    fr = list(frames)
+    fr[q_ind] = xs0
+    ops.window_attention_fused(fr, q_ind, tm.view(-1), nwin, C, heads, wqkv, bqkv, tbl, o_out=ob)
+    proj = ob.float() @ wproj.float().t() + bproj
+    ref = xs0.clone()
+    idx = tm.view(-1).long()
+    keep = idx >= 0
+    ref[idx[keep]] += proj[keep]
+    # whole-window kernel, in place on a copy of the query frame
+    xs = xs0.clone()
+    fr[q_ind] = xs
+    ops.window_attention_fused(fr, q_ind, tm.view(-1), nwin, C, heads, wqkv, bqkv, tbl, wproj, bproj, xs=xs)
+    torch.cuda.synchronize()
+    err = float((xs - ref).abs().max())
+    print("win256", dilated, zero_frame, err, float((ref - xs0).abs().max()))
+    assert err <= 2e-2
+    assert float((ref - xs0).abs().max()) > 0.1      # the attention path really contributes
+    # same kernel fed with precomputed neighbour k | v (LayerNorm + rows [C, 3C) of wqkv, bf16), as the executor does
+    if zero_frame != q_ind:
+        kv = []
+        for d in range(D):
+            if d == q_ind or frames[d] is None:
+                kv.append(None)
+                continue
+            xhat = F.layer_norm(frames[d], (C,), eps=1e-5).to(torch.bfloat16).float()
+            full = (xhat @ wqkv[C:].float().t() + bqkv[C:]).to(torch.bfloat16)
+            pad = torch.zeros(P, 3 * 2 * C, dtype=torch.bfloat16, device=DEV)     # a wider row pitch, block 1 of 3
+            pad[:, 2 * C:4 * C] = full
+            kv.append(pad[:, 2 * C:4 * C])
+        xs2 = xs0.clone()
+        ops.window_attention_fused_kvpre(xs2, kv, q_ind, tm.view(-1), nwin, C, heads, wqkv, bqkv, tbl, wproj, bproj, xs2)
+        torch.cuda.synchronize()
+        err2 = float((xs2 - ref).abs().max())
+        print("win256 kvpre", dilated, zero_frame, err2)
+        assert err2 <= 2e-2
