@@ -15,6 +15,10 @@
 #include "common.cuh"
 
 namespace bde {
+namespace tc {
+extern long long* g_dbg;   // bring-up cycle-counter buffer owned by gemm_tc.cu (bde_tc_debug_enable)
+extern size_t g_dbg_ctas;
+}  // namespace tc
 namespace {
 
 constexpr int kTok = 49;       // 7 x 7 window
@@ -36,6 +40,7 @@ struct FusedAttnParams {
   // already offset to the block's columns; NULL = all-zero frame (k / v = bias).  Unused for the query slot.
   const __nv_bfloat16* kvpre[8];
   int kv_ld[8];
+  long long* dbg;   // optional per-CTA phase cycle counters (8 slots per CTA), bring-up profiling
 };
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -710,6 +715,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
   const int tbl_ld = p.D * kRel;
 
   // weight half-slice hs (0 .. 31): slice = hs / 2 (q, k, v of head group 0..3, then the 4 proj slices), K half = hs & 1
+  long long t_ln = 0, t_gemm = 0, t_gather = 0, t_tbl = 0, t_attn = 0, t_proj = 0;
+  const bool dbg = p.dbg != nullptr;
+  const long long t_begin = dbg ? clock64() : 0;
   auto load_half = [&](int hs) {
     const int sl = hs >> 1, half = hs & 1;
     const __nv_bfloat16* src;
@@ -805,6 +813,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
     }
   }
 
+  if (dbg) t_ln = clock64() - t_begin;
   const int npair = warp & 3, mq = warp >> 2;
   const uint32_t xn_u32 = sb + Cfg::OFF_XN, os_u32 = sb + Cfg::OFF_O;
   const uint32_t vs_u32 = sb + Cfg::OFF_V, tbl_u32 = sb + Cfg::OFF_TBL, coff_u32 = sb + Cfg::OFF_COFF;
@@ -831,6 +840,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
     for (int i = tid; i < (XROWS - n_kv) * 64; i += kThreadsW) vs[(n_kv + i / 64) * PQ + (i & 63)] = __float2bfloat16_rn(0.f);
   }
   for (int hg = 0; hg < Cfg::NHG; ++hg) {
+    long long t0 = dbg ? clock64() : 0;
     if (kPre) {
       // ---- neighbour frames: gather the precomputed k / v columns of this head group (v: bf16 -> fp16) -------------------
       if (hg > 0) __syncthreads();   // every warp is done with the previous group's k / v tiles
@@ -868,6 +878,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
         *reinterpret_cast<uint4*>((which == 0 ? ks : vs) + (d * kTok + tok) * PQ + c8 * 8) = val;
       }
     }
+    if (dbg) { const long long t1 = clock64(); t_gather += t1 - t0; t0 = t1; }
     // ---- q, k, v projections of this head group --------------------------------------------------------------------
     for (int which = 0; which < 3; ++which) {
       const float* bsrc = p.bqkv + which * C + hg * 64 + npair * 16 + 2 * t;
@@ -930,6 +941,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
         }
       }
     }
+    if (dbg) { const long long t1 = clock64(); t_gemm += t1 - t0; t0 = t1; }
     // ---- bias table of this head group -> smem; q, k, v visible ----------------------------------------------------
     {
       const float* src = p.tbl + (size_t)hg * HG * tbl_ld;
@@ -939,6 +951,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
       cpa_wait<0>();   // also covers the weight half-slice that is in flight (needed next anyway)
       __syncthreads();
     }
+    if (dbg) { const long long t1 = clock64(); t_tbl += t1 - t0; t0 = t1; }
     // ---- attention: warp = (head of the group, 16-row query tile); scores stay in registers ---------------------------
     {
       const int hl = warp >> 2, mt = warp & 3;
@@ -1012,8 +1025,10 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
         *reinterpret_cast<uint32_t*>(os + row1 * PX + col) = pack2(o[v][2] * inv1, o[v][3] * inv1);
       }
     }
+    if (dbg) t_attn += clock64() - t0;
     // the next slice_gemm starts with a __syncthreads(): q / k / v tiles are not rewritten before every warp is past here
   }
+  const long long t_p0 = dbg ? clock64() : 0;
 
   // ---- output projection + window_reverse + shortcut: x[pix] += proj(o) + b, 64 output columns per weight slice --------
   for (int js = 0; js < 4; ++js) {
@@ -1038,6 +1053,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
       }
     }
   }
+  if (dbg && tid == 0) {
+    long long* o = p.dbg + (size_t)blockIdx.x * 8;
+    const long long t_end = clock64();
+    o[0] = t_end - t_begin; o[1] = t_ln; o[2] = t_gather; o[3] = t_gemm; o[4] = t_tbl; o[5] = t_attn; o[6] = t_end - t_p0;
+  }
 }
 
 template <int NT, bool kPre>
@@ -1050,7 +1070,9 @@ int launch_win256(const FusedAttnParams& p, cudaStream_t s) {
     BDE_REQUIRE(e == cudaSuccess, "bde_window_attention_fused: smem attribute (%d bytes): %s", Cfg::SMEM, cudaGetErrorString(e));
     configured = true;
   }
-  kern<<<p.n_win, kThreadsW, Cfg::SMEM, s>>>(p);
+  FusedAttnParams q = p;
+  q.dbg = (tc::g_dbg != nullptr && (size_t)p.n_win <= tc::g_dbg_ctas) ? tc::g_dbg : nullptr;
+  kern<<<p.n_win, kThreadsW, Cfg::SMEM, s>>>(q);
   return check_launch("attn_win256_kernel");
 }
 
@@ -1090,6 +1112,7 @@ extern "C" int bde_window_attention_fused(const float* const* frames_host, int D
   p.o_out = (__nv_bfloat16*)o_out;
   p.n_win = n_win; p.D = D; p.q_slot = q_slot; p.heads = heads;
   for (int i = 0; i < 8; ++i) { p.kvpre[i] = nullptr; p.kv_ld[i] = 0; }
+  p.dbg = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
 #define BDE_FUSED(C_, HD_)                                       \
   switch (D) {                                                   \
@@ -1140,6 +1163,7 @@ extern "C" int bde_window_attention_fused_kvpre(const float* xq, const void* con
   p.bproj = bproj;
   p.xs = xs;
   p.o_out = nullptr;
+  p.dbg = nullptr;
   p.n_win = n_win; p.D = D; p.q_slot = q_slot; p.heads = heads;
   cudaStream_t s = (cudaStream_t)stream;
   return D == 2 ? launch_win256<13, true>(p, s) : launch_win256<19, true>(p, s);
