@@ -74,6 +74,7 @@ EXPORTS = {
                                                     C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7),
     "bde_mlp_fused_supported": (C.c_int, [C.c_int, C.c_int]),
     "bde_mlp_fused": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int] + [C.c_void_p] * 5),
+    "bde_mlp_fused_sum": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int] + [C.c_void_p] * 7),
     "bde_cast": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
 }
 

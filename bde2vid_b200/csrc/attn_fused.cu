@@ -590,7 +590,8 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
             const int col = npair * 16 + n * 8 + 2 * t;
             const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bproj + col));
             float2* dst = reinterpret_cast<float2*>(p.xs + (size_t)pix * C + col);
-            float2 cur = *dst;
+            // shortcut = the query frame (DTransformer.py:294-299); it is xs itself when the block runs in place
+            float2 cur = *reinterpret_cast<const float2*>(p.frames[p.q_slot] + (size_t)pix * C + col);
             cur.x += acc[i][n][hrow * 2 + 0] + bb.x;
             cur.y += acc[i][n][hrow * 2 + 1] + bb.y;
             *dst = cur;
@@ -1045,7 +1046,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
           const int col = js * 64 + npair * 16 + n * 8 + 2 * t;
           const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bproj + col));
           float2* dst = reinterpret_cast<float2*>(p.xs + (size_t)pix * C + col);
-          float2 cur = *dst;
+          float2 cur = *reinterpret_cast<const float2*>(p.frames[p.q_slot] + (size_t)pix * C + col);   // shortcut = query frame
           cur.x += acc[0][n][hrow * 2 + 0] + bb.x;
           cur.y += acc[0][n][hrow * 2 + 1] + bb.y;
           *dst = cur;
@@ -1097,6 +1098,7 @@ extern "C" int bde_window_attention_fused(const float* const* frames_host, int D
                   bias_tbl != nullptr,
               "bde_window_attention_fused: bad arguments");
   const bool with_proj = wproj != nullptr && bproj != nullptr && xs != nullptr;
+  BDE_REQUIRE(!with_proj || frames_host[q_slot] != nullptr, "bde_window_attention_fused: the query frame (shortcut source) must not be NULL");
   BDE_REQUIRE(c == 64 ? with_proj : (with_proj || o_out != nullptr), "bde_window_attention_fused: missing output operands");
   BDE_REQUIRE((((uintptr_t)wqkv) & 15) == 0 && (((uintptr_t)bias_tbl) & 15) == 0 && (((uintptr_t)wproj) & 15) == 0,
               "bde_window_attention_fused: operands must be 16-byte aligned");

@@ -33,7 +33,24 @@ struct MlpParams {
   const float* b1;   // [256]
   const float* b2;   // [64]
   int P;
+  // optional fused "x + merged" of the generator (..._V5.py:166-169) after the last block of a frame:
+  // sum_io[m] += x_new[m] (fp32, in place) and sum_t[m] = bf16(sum_io[m])
+  float* sum_io;
+  __nv_bfloat16* sum_t;
 };
+
+__device__ __forceinline__ void mlp_fused_sum(float* sum_io, __nv_bfloat16* sum_t, size_t off, float4 xnew) {
+  float4 s4 = *reinterpret_cast<const float4*>(sum_io + off);
+  s4.x += xnew.x; s4.y += xnew.y; s4.z += xnew.z; s4.w += xnew.w;
+  *reinterpret_cast<float4*>(sum_io + off) = s4;
+  if (sum_t != nullptr) {
+    const __nv_bfloat162 t0 = __floats2bfloat162_rn(s4.x, s4.y), t1 = __floats2bfloat162_rn(s4.z, s4.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&t0);
+    pk.y = *reinterpret_cast<const uint32_t*>(&t1);
+    *reinterpret_cast<uint2*>(sum_t + off) = pk;
+  }
+}
 
 __global__ void __launch_bounds__(kMlpThreads, 2)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2, const MlpParams p) {
@@ -163,6 +180,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
           float4 cur = *dst;
           cur.x += acc.x + bb.x; cur.y += acc.y + bb.y; cur.z += acc.z + bb.z; cur.w += acc.w + bb.w;
           *dst = cur;
+          if (p.sum_io != nullptr) mlp_fused_sum(p.sum_io, p.sum_t, (size_t)mm * kMlpC + half * 32 + cq, cur);
         }
       }
     }
@@ -242,6 +260,8 @@ struct Mlp3Params {
   const float* b1;   // [1024]
   const float* b2;   // [256]
   int P;
+  float* sum_io;             // optional fused "x + merged" (see MlpParams)
+  __nv_bfloat16* sum_t;
 };
 
 __global__ void __launch_bounds__(kM3Threads, 1)
@@ -407,9 +427,11 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
         const int r = it * 4 + rq;
         const int mm = m0 + q * 32 + r;
         const float4 acc = *reinterpret_cast<const float4*>(stg + r * 32 + ((cq4 ^ (r & 7)) << 2));
-        if (mm < p.P)
-          *reinterpret_cast<float4*>(p.x + (size_t)mm * kM3C + cb + cq4 * 4) =
-              make_float4(cur[it].x + acc.x + bb.x, cur[it].y + acc.y + bb.y, cur[it].z + acc.z + bb.z, cur[it].w + acc.w + bb.w);
+        if (mm < p.P) {
+          const float4 xnew = make_float4(cur[it].x + acc.x + bb.x, cur[it].y + acc.y + bb.y, cur[it].z + acc.z + bb.z, cur[it].w + acc.w + bb.w);
+          *reinterpret_cast<float4*>(p.x + (size_t)mm * kM3C + cb + cq4 * 4) = xnew;
+          if (p.sum_io != nullptr) mlp_fused_sum(p.sum_io, p.sum_t, (size_t)mm * kM3C + cb + cq4 * 4, xnew);
+        }
       }
     }
     tcgen05_fence_before();
@@ -518,9 +540,18 @@ extern "C" int bde_mlp_fused_supported(int c, int hidden) {
   return ((c == tc::kMlpC && hidden == tc::kMlpH) || (c == tc::kM3C && hidden == tc::kM3H)) ? 1 : 0;
 }
 
+extern "C" int bde_mlp_fused_sum(float* x, size_t rows, int c, int hidden, const void* w1, const float* b1, const void* w2,
+                                 const float* b2, float* sum_io, void* sum_t, void* stream);
+
 extern "C" int bde_mlp_fused(float* x, size_t rows, int c, int hidden, const void* w1, const float* b1, const void* w2,
                              const float* b2, void* stream) {
+  return bde_mlp_fused_sum(x, rows, c, hidden, w1, b1, w2, b2, nullptr, nullptr, stream);
+}
+
+extern "C" int bde_mlp_fused_sum(float* x, size_t rows, int c, int hidden, const void* w1, const float* b1, const void* w2,
+                                 const float* b2, float* sum_io, void* sum_t, void* stream) {
   using namespace bde::tc;
+  BDE_REQUIRE((((uintptr_t)sum_io) & 15) == 0 && (((uintptr_t)sum_t) & 7) == 0, "bde_mlp_fused: sum operands must be 16 / 8-byte aligned");
   if (rows == 0) return 0;
   BDE_REQUIRE(bde_mlp_fused_supported(c, hidden) == 1, "bde_mlp_fused: (c, hidden) must be (64, 256) or (256, 1024) (got %d, %d)", c, hidden);
   BDE_REQUIRE(x != nullptr && w1 != nullptr && w2 != nullptr && b1 != nullptr && b2 != nullptr, "bde_mlp_fused: null operand");
@@ -543,6 +574,7 @@ extern "C" int bde_mlp_fused(float* x, size_t rows, int c, int hidden, const voi
     }
     Mlp3Params p3;
     p3.x = x; p3.b1 = b1; p3.b2 = b2; p3.P = (int)rows;
+    p3.sum_io = sum_io; p3.sum_t = (__nv_bfloat16*)sum_t;
     mlp_fused256_kernel<<<(unsigned)ceil_div(rows, BM), kM3Threads, kM3Smem, (cudaStream_t)stream>>>(t1, t2, p3);
     return check_launch("mlp_fused256_kernel");
   }
@@ -558,6 +590,7 @@ extern "C" int bde_mlp_fused(float* x, size_t rows, int c, int hidden, const voi
   }
   MlpParams p;
   p.x = x; p.b1 = b1; p.b2 = b2; p.P = (int)rows;
+  p.sum_io = sum_io; p.sum_t = (__nv_bfloat16*)sum_t;
   mlp_fused_kernel<<<(unsigned)ceil_div(rows, BM), kMlpThreads, kMlpSmem, (cudaStream_t)stream>>>(t1, t2, p);
   return check_launch("mlp_fused_kernel");
 }

@@ -482,16 +482,20 @@ class _Plan:
         ops.pred_sigmoid(cur, self.head[s], eng.pred_w, eng.pred_b, eng.bc, n * Hp * Wp, self.img[s])
         self.launches += 1
 
-    def _mlp(self, blk, d, xs, P, C):
-        """xs += fc2(GELU(fc1(LN(xs)))) (DTransformer.py:279-283,302-304): one fused kernel where supported."""
+    def _mlp(self, blk, d, xs, P, C, sum_io=None, sum_t=None):
+        """xs += fc2(GELU(fc1(LN(xs)))) (DTransformer.py:279-283,302-304): one fused kernel where supported.
+        Returns True when the optional "x + merged" sum (sum_io += xs, sum_t = bf16) was fused into that kernel."""
         eng = self.eng
         if eng.fuse_mlp and ops.mlp_fused_supported(C, 4 * C):
-            ops.mlp_fused(xs, P, C, 4 * C, blk["fc1_ln"].w, blk["fc1_ln"].bias, blk["fc2"].w, blk["fc2"].bias)
+            ops.mlp_fused(xs, P, C, 4 * C, blk["fc1_ln"].w, blk["fc1_ln"].bias, blk["fc2"].w, blk["fc2"].bias,
+                          sum_io=sum_io, sum_t=sum_t)
             self.launches += 1
+            return sum_io is not None
         else:
             eng._gemm(blk["fc1_ln"], None, d["hid"], 1, P, 1, C, act=ACT_GELU, ln_frames=[xs])
             eng._gemm(blk["fc2"], d["hid"], xs, 1, P, 1, 4 * C, out_f32=True, residual=xs)
             self.launches += 2
+        return False
 
     def _attention_level(self, l, on_frame_done=None):
         """In-place sequential multi-frame window attention (...V5.py:151-169; DTransformer.py:254-389)."""
@@ -515,25 +519,35 @@ class _Plan:
             # past neighbours are already post-attention (updated in place), future ones are not: quirk Q1
             frames = [feat[t + o] if 0 <= t + o < T else None for o in eng.buf]      # None = all-zero map (Q4)
             qsrc = frames[eng.q_ind]
-            if qsrc is None:
-                xs.zero_()
-            else:
-                ops.cast(qsrc, xs)
-            self.launches += 1
+            blk0 = eng.attn[l][0]
+            # the first block (plain windows: every pixel belongs to exactly one window) of the fused-projection kernels
+            # reads the query frame / shortcut straight from feat[t] and writes x: no copy of feat[t] into xs
+            direct0 = (qsrc is not None and blk0["tbl"] is not None
+                       and (C == 64 or pre or (eng.fuse_win256 and nwin >= 64)))
+            if not direct0:
+                if qsrc is None:
+                    xs.zero_()
+                else:
+                    ops.cast(qsrc, xs)
+                self.launches += 1
+            sum_done = False
             for i, blk in enumerate(eng.attn[l]):
                 tm = d["tm"][i & 1]
+                # the last block's fused MLP also does "x + merged[t]" (feat[t] += x, bf16 copy) -- bf16 engine only
+                last = i == len(eng.attn[l]) - 1 and eng.dtype != torch.float32
+                sum_args = (feat[t], feat_t[t]) if last else (None, None)
                 fr = list(frames)
-                fr[eng.q_ind] = xs
+                fr[eng.q_ind] = qsrc if (direct0 and i == 0) else xs
                 if blk["tbl"] is not None and pre:
                     kv = [None] * D
                     if t >= 1:
                         kv[0] = d["kv_past"][(t - 1) & 1][:, i * 2 * C:(i + 1) * 2 * C]
                     if t + 1 < T:
                         kv[2] = d["kv_fut"][i, t + 1]
-                    ops.window_attention_fused_kvpre(xs, kv, eng.q_ind, tm.view(-1), nwin, C, eng.heads, blk["qkv"].w,
+                    ops.window_attention_fused_kvpre(fr[eng.q_ind], kv, eng.q_ind, tm.view(-1), nwin, C, eng.heads, blk["qkv"].w,
                                                      blk["qkv"].bias, blk["tbl"], blk["proj"].w, blk["proj"].bias, xs)
                     self.launches += 1
-                    self._mlp(blk, d, xs, P, C)
+                    sum_done = self._mlp(blk, d, xs, P, C, *sum_args)
                     continue
                 if blk["tbl"] is not None:
                     # one kernel for the attention half; C == 64 also projects and scatters into xs
@@ -549,7 +563,7 @@ class _Plan:
                                                    blk["qkv"].bias, blk["tbl"], o_out=d["ob"])
                         eng._gemm(blk["proj"], d["ob"], xs, 1, nwin * ntok, 1, C, epi=EPI_SCATTER, row_map=tm.view(-1))
                         self.launches += 2
-                    self._mlp(blk, d, xs, P, C)
+                    sum_done = self._mlp(blk, d, xs, P, C, *sum_args)
                     continue
                 if blk["qkv"] is not None:
                     # fused: [window gather + LayerNorm + q/k/v projection] -> attention -> proj+scatter ->
@@ -559,7 +573,7 @@ class _Plan:
                     ops.window_attention_mma_qkv(d["qkv"], blk["bias_mma"], nwin, ntok, D * ntok, eng.q_ind * ntok, C,
                                                  eng.heads, d["ob"])
                     eng._gemm(blk["proj"], d["ob"], xs, 1, nwin * ntok, 1, C, epi=EPI_SCATTER, row_map=tm.view(-1))
-                    self._mlp(blk, d, xs, P, C)
+                    sum_done = self._mlp(blk, d, xs, P, C, *sum_args)
                     self.launches += 3
                     continue
                 if C in (64, 128, 256):
@@ -582,10 +596,11 @@ class _Plan:
                 eng._gemm(blk["fc1"], d["yn"], d["hid"], 1, P, 1, C, act=ACT_GELU)
                 eng._gemm(blk["fc2"], d["hid"], xs, 1, P, 1, 4 * C, out_f32=True, residual=xs)
                 self.launches += 9
-            # x + merged[t], stored back in place (...V5.py:166-169)
-            ops.add(xs, feat[t], out_f32=feat[t], out_t=None if eng.dtype == torch.float32 else feat_t[t],
-                    dtype=eng.dtype)
-            self.launches += 1
+            # x + merged[t], stored back in place (...V5.py:166-169), unless the last MLP kernel already did it
+            if not sum_done:
+                ops.add(xs, feat[t], out_f32=feat[t], out_t=None if eng.dtype == torch.float32 else feat_t[t],
+                        dtype=eng.dtype)
+                self.launches += 1
             if pre and t + 1 < T:
                 # this frame is final: its k | v for every block of the next step (the "past" neighbour there)
                 xn_t = d["xn_all"][t * P:(t + 1) * P]      # (its pre-attention copy is not needed any more)

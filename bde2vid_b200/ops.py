@@ -228,11 +228,17 @@ def mlp_fused_supported(c, hidden):
     return _lib.load().bde_mlp_fused_supported(c, hidden) == 1
 
 
-def mlp_fused(x, rows, c, hidden, w1, b1, w2, b2):
-    """x (float32 [rows, c]) += fc2(GELU(fc1(LayerNorm(x)))) in place; see include/bde2vid.h."""
+def mlp_fused(x, rows, c, hidden, w1, b1, w2, b2, sum_io=None, sum_t=None):
+    """x (float32 [rows, c]) += fc2(GELU(fc1(LayerNorm(x)))) in place; see include/bde2vid.h.  With ``sum_io`` (float32
+    [rows, c]) the kernel also does sum_io += x_new and, if given, sum_t = bf16(sum_io)  ("x + merged", ...V5.py:166-169)."""
     lib = _lib.require_device()
     assert x.dtype == torch.float32
-    check(lib.bde_mlp_fused(ptr(x), rows, c, hidden, ptr(w1), ptr(b1), ptr(w2), ptr(b2), stream_ptr()), "bde_mlp_fused")
+    if sum_io is None:
+        check(lib.bde_mlp_fused(ptr(x), rows, c, hidden, ptr(w1), ptr(b1), ptr(w2), ptr(b2), stream_ptr()), "bde_mlp_fused")
+        return
+    assert sum_io.dtype == torch.float32 and (sum_t is None or sum_t.dtype == torch.bfloat16)
+    check(lib.bde_mlp_fused_sum(ptr(x), rows, c, hidden, ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(sum_io), ptr(sum_t), stream_ptr()),
+          "bde_mlp_fused_sum")
 
 
 def cast(src, dst):

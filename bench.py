@@ -174,7 +174,7 @@ def main():
     ap.add_argument("--ref-windows", type=int, default=6, help="windows of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
-    ap.add_argument("--concurrent", type=int, default=2, help="CUDA streams (independent model calls in flight) per GPU")
+    ap.add_argument("--concurrent", type=int, default=3, help="CUDA streams (independent model calls in flight) per GPU")
     ap.add_argument("--batch", type=int, default=4, help="independent sequences batched into each model call")
     args = ap.parse_args()
 

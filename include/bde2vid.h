@@ -268,6 +268,10 @@ int bde_window_attention_fused_kvpre(const float* xq, const void* const* kv_host
 int bde_mlp_fused_supported(int c, int hidden);
 int bde_mlp_fused(float* x, size_t rows, int c, int hidden, const void* w1, const float* b1, const void* w2,
                   const float* b2, void* stream);
+/* Same, and additionally (after the last block of a frame, ..._V5.py:166-169 "x + merged"): sum_io[m] += x_new[m]
+ * (float32 [rows, c], in place) and, when sum_t != NULL, sum_t[m] = bf16(sum_io[m]). */
+int bde_mlp_fused_sum(float* x, size_t rows, int c, int hidden, const void* w1, const float* b1, const void* w2,
+                      const float* b2, float* sum_io, void* sum_t, void* stream);
 
 /* float32 -> dtype copy/cast (and back); n elements */
 int bde_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, void* stream);
