@@ -501,7 +501,6 @@ int fill_params(const bde_gemm_desc* d, TcParams& p, bool& ln) {
 
 }  // namespace tc
 
-int gemm_tcgen05_persistent(const bde_gemm_desc* d, cudaStream_t s);
 namespace tc {
 bool conv_tma_eligible(const TcParams& p, bool ln);
 int conv_tma_launch(const bde_gemm_desc* d, const TcParams& p, cudaStream_t s);
@@ -509,10 +508,6 @@ int conv_tma_launch(const bde_gemm_desc* d, const TcParams& p, cudaStream_t s);
 
 int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s) {
   using namespace tc;
-  // The persistent variant (gemm_tc_persistent.cu) is kept as an experiment: with one CTA per SM its four
-  // epilogue warps cannot keep up with the ALU-heavy epilogues (GELU / LSTM gates) that sixteen warps share in
-  // the two-CTAs-per-SM kernel below (measured 571 vs 837 frames/s on the bench workload).
-  if (env_flag("BDE2VID_TC_PERSISTENT", false)) return gemm_tcgen05_persistent(d, s);
   TcParams p;
   bool ln = false;
   int rc0 = fill_params(d, p, ln);

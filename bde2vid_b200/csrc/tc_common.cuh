@@ -1,6 +1,6 @@
 // Shared pieces of the tcgen05 implicit-GEMM kernels: parameters, PTX wrappers, tile geometry,
-// UMMA descriptors and the fused quad epilogue.  Included by gemm_tc.cu (one tile per CTA) and
-// gemm_tc_persistent.cu (persistent CTAs with an overlapped epilogue).
+// UMMA descriptors and the fused quad epilogue.  Included by gemm_tc.cu (one tile per CTA), gemm_tc_conv.cu
+// (persistent TMA-fed convolutions with an overlapped epilogue) and mlp_fused.cu.
 #pragma once
 #include <cuda.h>
 #include <cudaTypedefs.h>

@@ -207,6 +207,15 @@ def test_mlp_fused(rows, C):
     assert err <= 2e-2     # bf16 rounding of the hidden activations at values of order 1..8
     full = x + F.gelu(F.layer_norm(x, (C,), gamma, beta, 1e-5) @ W1.t() + b1) @ W2.t() + b2
     assert float((xd.cpu() - full).abs().max()) <= 6e-2
+    # fused "x + merged" (..._V5.py:166-169): sum_io += x_new, sum_t = bf16(sum_io); x itself as without the option
+    merged = torch.randn(rows, C, generator=g)
+    x2, sm = x.to(DEV).contiguous(), merged.to(DEV).contiguous()
+    st = torch.zeros(rows, C, dtype=torch.bfloat16, device=DEV)
+    ops.mlp_fused(x2, rows, C, Hd, w1f.to(DEV).contiguous(), b1f.to(DEV), w2f.to(DEV).contiguous(), b2.to(DEV), sum_io=sm, sum_t=st)
+    torch.cuda.synchronize()
+    assert torch.equal(x2, xd)
+    assert float((sm.cpu() - (xd.cpu() + merged)).abs().max()) <= 1e-5
+    assert torch.equal(st, sm.to(torch.bfloat16))
 
 
 @pytest.mark.parametrize("shape", [(3, 5, 40, 56), (2, 5, 33, 47), (1, 3, 16, 32), (2, 6, 19, 70)])
