@@ -181,6 +181,9 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
+  const bool dbg = p.dbg != nullptr;
+  const long long t_begin = dbg ? clock64() : 0;
+  long long t_mark = t_begin, t_ln = 0, t_qkv = 0, t_tbl = 0, t_attn = 0;
   constexpr int NHG = C / 64;
   const int w = blockIdx.x / NHG, hg = blockIdx.x - w * NHG;
   const int n_kv = p.D * kTok;
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
     (void)NPASS;
   }
 
+  if (dbg) { const long long c = clock64(); t_ln = c - t_mark; t_mark = c; }
   // ---- q, k, v projections (mma.sync): warp = (n-tile pair, m half) --------------------------------------
   const int npair = warp & 3, mh = warp >> 2;
   const uint32_t xn_u32 = sb + Cfg::OFF_XN;
@@ -355,6 +359,7 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
     }
   }
   __syncthreads();  // q, k, v complete; the token / weight region is free
+  if (dbg) { const long long c = clock64(); t_qkv = c - t_mark; t_mark = c; }
 
   // ---- bias table (+ projection weights) -> smem ------------------------------------------------------------
   {
@@ -372,6 +377,7 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
     __syncthreads();
   }
 
+  if (dbg) { const long long c = clock64(); t_tbl = c - t_mark; t_mark = c; }
   // ---- attention: unit = (head of the group, 16-row query tile); scores stay in registers ----------------------
   // head_dim 4: the 49th query row would cost a whole tile per head, so the normal units cover rows 0..47 and one
   // "special" unit packs row 48 of all 16 heads into a single tile (tile row = head; the query fragment carries only
@@ -572,6 +578,7 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
     }
   }
 
+  if (dbg) { const long long c = clock64(); t_attn = c - t_mark; t_mark = c; }
   if (C == 64) {
     // ---- output projection + window_reverse + shortcut: x[pix] += proj(o) + b (DTransformer.py:204,294-299) ----
     __syncthreads();
@@ -600,6 +607,11 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
       }
     }
   }
+  if (dbg && tid == 0) {
+    long long* o = p.dbg + (size_t)blockIdx.x * 8;
+    const long long c = clock64();
+    o[0] = c - t_begin; o[1] = t_ln; o[2] = 0; o[3] = t_qkv; o[4] = t_tbl; o[5] = t_attn; o[6] = c - t_mark;
+  }
 }
 
 template <int C, int HD, int NT>
@@ -613,7 +625,9 @@ int launch_fused(const FusedAttnParams& p, cudaStream_t s) {
     BDE_REQUIRE(e == cudaSuccess, "bde_window_attention_fused: smem attribute (%d bytes): %s", Cfg::SMEM, cudaGetErrorString(e));
     configured = true;
   }
-  kern<<<p.n_win * (C / 64), kThreadsF, Cfg::SMEM, s>>>(p);
+  FusedAttnParams q = p;
+  q.dbg = (tc::g_dbg != nullptr && (size_t)p.n_win * (C / 64) <= tc::g_dbg_ctas) ? tc::g_dbg : nullptr;
+  kern<<<p.n_win * (C / 64), kThreadsF, Cfg::SMEM, s>>>(q);
   return check_launch("attn_fused_kernel");
 }
 
