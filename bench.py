@@ -348,7 +348,7 @@ def main():
         torch.cuda.synchronize()
         vms = s.elapsed_time(e) / 10
         vach = VOXEL_BYTES_PER_WINDOW * T / (vms * 1e-3) / 1e9
-        voxel_roof = {"kernel": "voxel_cluster_kernel (one cluster of 8 CTAs per window, grid in distributed shared memory)", "bound": "hbm", "achieved": vach, "peak": pk["hbm"], "unit": "GB/s",
+        voxel_roof = {"kernel": "voxel_atomic_kernel (grid memset + global RED.ADD.F32, executed by L2)", "bound": "hbm", "achieved": vach, "peak": pk["hbm"], "unit": "GB/s",
                       "frac": vach / pk["hbm"], "traffic": None, "ms_per_launch": vms,
                       "bytes_per_launch": VOXEL_BYTES_PER_WINDOW * T}
 

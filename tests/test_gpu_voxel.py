@@ -33,7 +33,7 @@ def _value_gate(got, ref, mass):
     assert (err <= tol).all(), "max err %.3e" % err.max()
 
 
-@pytest.mark.parametrize("algo", [1, 2, 3])
+@pytest.mark.parametrize("algo", [1, 2, 3, 4])
 def test_unique_pixels_bit_exact(algo):
     """One event per pixel -> no accumulation-order freedom: bins AND weights must be bit-exact."""
     H, W, N = 64, 80, 64 * 80
@@ -57,7 +57,7 @@ def test_unique_pixels_bit_exact(algo):
         assert touched <= allowed
 
 
-@pytest.mark.parametrize("algo", [1, 2, 3])
+@pytest.mark.parametrize("algo", [1, 2, 3, 4])
 def test_golden_small(algo):
     g = load_golden("voxel_small")
     for name in ("a", "b"):
@@ -72,7 +72,7 @@ def test_golden_small(algo):
             _value_gate(got[w], g["ref_%s_%d" % (name, w)], mass)
 
 
-@pytest.mark.parametrize("algo", [1, 2, 3])
+@pytest.mark.parametrize("algo", [1, 2, 3, 4])
 @pytest.mark.parametrize("H,W,N", [(180, 240, 15000), (260, 346, 31500)])
 def test_sensor_shapes_padded(algo, H, W, N):
     T = 3
@@ -106,7 +106,7 @@ def test_gen4_shape_atomic_vs_oracle():
         _value_gate(got[w], ref, mass)
 
 
-@pytest.mark.parametrize("algo", [1, 2, 3])
+@pytest.mark.parametrize("algo", [1, 2, 3, 4])
 def test_edge_cases(algo):
     H, W = 16, 24
     # ragged windows: empty, one event, two events, unaligned starts; duplicates on one pixel
@@ -130,7 +130,7 @@ def test_out_of_range_events_are_counted():
     H, W = 8, 8
     xs = np.array([1, 8, -1, 2], np.float32); ys = np.array([1, 2, 3, 9], np.float32)
     ts = np.array([0, .1, .2, 1], np.float32); ps = np.ones(4, np.float32)
-    for algo in (1, 2, 3):
+    for algo in (1, 2, 3, 4):
         got, oob = _run((xs, ys, ts, ps), np.array([0, 4], np.int64), H, W, algo)
         assert oob == 3
         assert got[0][0, 1, 1] == 1.0 and np.count_nonzero(got[0]) == 1
