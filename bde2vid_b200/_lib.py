@@ -35,6 +35,7 @@ class GemmDesc(C.Structure):
         ("epi", C.c_int), ("act", C.c_int), ("out_f32", C.c_int),
         ("out", C.c_void_p), ("residual", C.c_void_p), ("c_prev", C.c_void_p), ("c_out", C.c_void_p),
         ("row_map", C.c_void_p), ("out2", C.c_void_p), ("res_mode", C.c_int),
+        ("a0_ld", C.c_int), ("a1_ld", C.c_int),
     ]
 
 

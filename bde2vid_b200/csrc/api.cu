@@ -108,6 +108,10 @@ extern "C" int bde_gemm(const bde_gemm_desc* d, void* stream) {
   } else {
     BDE_REQUIRE(d->epi == BDE_EPI_STORE, "bde_gemm: unknown epilogue %d", d->epi);
   }
+  BDE_REQUIRE(d->a0_ld == 0 || d->a0_ld >= d->c0, "bde_gemm: a0_ld smaller than c0");
+  BDE_REQUIRE(d->a1_ld == 0 || d->a1_ld >= d->c1, "bde_gemm: a1_ld smaller than c1");
+  const bool pitched = (d->a0_ld != 0 && d->a0_ld != d->c0) || (d->c1 > 0 && d->a1_ld != 0 && d->a1_ld != d->c1);
+  BDE_REQUIRE(!pitched || d->engine == BDE_ENGINE_TCGEN05, "bde_gemm: pitched A operands need the tcgen05 engine");
   if (d->engine == BDE_ENGINE_SIMT) return gemm_simt(d, s);
   if (d->engine == BDE_ENGINE_TCGEN05) {
     const bool prof = g_prof_on && g_prof_used + 2 <= g_prof_ev.size();

@@ -515,6 +515,8 @@ int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s) {
   if (p.M == 0) return 0;
   // convolutions over 64-channel slabs: persistent kernel with both operands fed by the TMA (gemm_tc_conv.cu)
   if (conv_tma_eligible(p, ln)) return conv_tma_launch(d, p, s);
+  BDE_REQUIRE((d->a0_ld == 0 || d->a0_ld == d->c0) && (d->c1 == 0 || d->a1_ld == 0 || d->a1_ld == d->c1),
+              "bde_gemm(tcgen05): pitched A operands are only supported by the TMA convolution kernel");
   // tile width: widest tile that still gives most SMs work (measured on the LSTM / encoder shapes: a 256-wide tile
   // gathers the A operand half as often and wins as soon as it yields >= ~100 CTAs; tools/tc_phase_probe.py bn)
   int bn = 32;

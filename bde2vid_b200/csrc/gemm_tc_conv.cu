@@ -596,11 +596,12 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
 PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn();
 
 // 4-D activation map (C, d1, d2, N) over an NHWC tensor; box {64, box1, box2, 1}; element stride es along d1 / d2
-static int get_act_tmap(const void* base, int C, int H, int W, int N, int swap, int box1, int box2, int es, CUtensorMap* out) {
+// `pitch` = elements between consecutive pixels (>= C: the source may be a channel slice of a wider map)
+static int get_act_tmap(const void* base, int C, int pitch, int H, int W, int N, int swap, int box1, int box2, int es, CUtensorMap* out) {
   static std::mutex mu;
-  static std::map<std::tuple<const void*, int, int, int, int, int, int, int, int>, CUtensorMap> cache;
+  static std::map<std::tuple<const void*, int, int, int, int, int, int, int, int, int>, CUtensorMap> cache;
   std::lock_guard<std::mutex> lock(mu);
-  auto key = std::make_tuple(base, C, H, W, N, swap, box1, box2, es);
+  auto key = std::make_tuple(base, C, pitch, H, W, N, swap, box1, box2, es);
   auto it = cache.find(key);
   if (it != cache.end()) {
     *out = it->second;
@@ -608,7 +609,7 @@ static int get_act_tmap(const void* base, int C, int H, int W, int N, int swap, 
   }
   auto encode = get_encode_fn();
   BDE_REQUIRE(encode != nullptr, "cuTensorMapEncodeTiled entry point not available");
-  const cuuint64_t row = (cuuint64_t)C * 2, line = (cuuint64_t)W * C * 2, image = (cuuint64_t)H * W * C * 2;
+  const cuuint64_t row = (cuuint64_t)pitch * 2, line = (cuuint64_t)W * pitch * 2, image = (cuuint64_t)H * W * pitch * 2;
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)(swap ? H : W), (cuuint64_t)(swap ? W : H), (cuuint64_t)N};
   cuuint64_t gstride[3] = {swap ? line : row, swap ? row : line, image};
   cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)box1, (cuuint32_t)box2, 1};
@@ -764,10 +765,12 @@ int conv_tma_launch(const bde_gemm_desc* d, const TcParams& p0, cudaStream_t s) 
   CUtensorMap ta0, ta1, tb;
   const int box1 = halo ? kCvHaloPitch : (p.stride == 2 ? 2 * kCvD1 : kCvD1);
   const int box2 = halo ? kCvD2 * nsub + p.ksize - 1 : (p.stride == 2 ? 2 * kCvD2 : kCvD2);
-  int rc = get_act_tmap(d->a0, p.c0, p.h_in, p.w_in, p.n_img, cp.swap, box1, box2, p.stride, &ta0);
+  const int ld0 = d->a0_ld > 0 ? d->a0_ld : p.c0, ld1 = d->a1_ld > 0 ? d->a1_ld : p.c1;
+  BDE_REQUIRE(ld0 % 8 == 0 && ld1 % 8 == 0, "bde_gemm(tcgen05 conv): pixel pitches must be multiples of 8 elements");
+  int rc = get_act_tmap(d->a0, p.c0, ld0, p.h_in, p.w_in, p.n_img, cp.swap, box1, box2, p.stride, &ta0);
   if (rc != 0) return rc;
   if (p.c1 > 0) {
-    rc = get_act_tmap(d->a1, p.c1, p.h_in, p.w_in, p.n_img, cp.swap, box1, box2, p.stride, &ta1);
+    rc = get_act_tmap(d->a1, p.c1, ld1, p.h_in, p.w_in, p.n_img, cp.swap, box1, box2, p.stride, &ta1);
     if (rc != 0) return rc;
   } else {
     ta1 = ta0;

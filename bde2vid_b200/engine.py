@@ -137,6 +137,16 @@ class Engine:
             w, ld = _pack_conv(conv.weight.detach().float(), dt, cin_pad, chunk_major=cm)
             return _Layer(w, ld, f32(conv.bias), conv.weight.shape[0], k, stride, k // 2, k_order=int(cm))
 
+        def merged_conv_layer(conv_f, conv_b, stride):
+            """forward + backward encoder convs read the same input (...V5.py:129-130): one GEMM with N doubled;
+            output channels [0, C) = forward, [C, 2C) = backward."""
+            wcat = torch.cat([conv_f.weight.detach().float(), conv_b.weight.detach().float()], 0)
+            k = wcat.shape[-1]
+            cm = tc and k > 1 and wcat.shape[1] % 64 == 0
+            w, ld = _pack_conv(wcat, dt, chunk_major=cm)
+            bias = torch.cat([conv_f.bias.detach().float(), conv_b.bias.detach().float()], 0).contiguous()
+            return _Layer(w, ld, bias, wcat.shape[0], k, stride, k // 2, k_order=int(cm))
+
         def lstm_layer(conv):
             # rows reordered so that n = 4*c + gate (gate order in, remember, out, cell: submodules.py:320)
             w = conv.weight.detach().float()
@@ -166,6 +176,9 @@ class Engine:
                     b_conv=conv_layer(gen.backward_encoder[l].conv.conv2d, 2),
                     f_lstm=lstm_layer(gen.forward_encoder[l].recurrent_block.Gates),
                     b_lstm=lstm_layer(gen.backward_encoder[l].recurrent_block.Gates)))
+                if tc and os.environ.get("BDE2VID_MERGE_ENC", "1") != "0":
+                    self.enc[-1]["fb_conv"] = merged_conv_layer(gen.forward_encoder[l].conv.conv2d,
+                                                                gen.backward_encoder[l].conv.conv2d, 2)
             self.attn = []
             n_tok = self.ws[0] * self.ws[1]
             for l in range(self.L):
@@ -307,8 +320,14 @@ class _Plan:
         self.lv = []
         for l in range(eng.L):
             h, w, C = Hp >> (l + 1), Wp >> (l + 1), eng.bc * 2 ** (l + 1)
-            d = dict(h=h, w=w, C=C,
-                     ef=E(N, h, w, C), eb=E(N, h, w, C), hf=E(N, h, w, C), hb=E(N, h, w, C),
+            # merged forward / backward encoder conv: the ConvLSTM chains then read channel halves of one [.., 2C] map,
+            # which only the TMA conv kernel can do (it needs C % 64 == 0 and a map of at least 8 x 8)
+            merged = ("fb_conv" in eng.enc[l] and C % 64 == 0 and h >= 8 and w >= 8
+                      and os.environ.get("BDE2VID_CONV_TMA", "1") != "0")
+            efb = E(N, h, w, 2 * C) if merged else None      # [.., :C] forward encoder conv, [.., C:] backward
+            d = dict(h=h, w=w, C=C, efb=efb,
+                     ef=None if merged else E(N, h, w, C), eb=None if merged else E(N, h, w, C),
+                     hf=E(N, h, w, C), hb=E(N, h, w, C),
                      cf=[E(B, h, w, C, dtype=f32) for _ in range(2)], cb=[E(B, h, w, C, dtype=f32) for _ in range(2)],
                      zero=torch.zeros(B, h, w, C, dtype=dt, device=dev),
                      feat=E(N, h, w, C, dtype=f32))
@@ -422,20 +441,33 @@ class _Plan:
             # of each other: the backward direction (conv + chain) runs on a second stream
             main = torch.cuda.current_stream()
             side = self.side if self.overlap else main
+            merged = d["efb"] is not None
+            if merged:
+                # both directions' encoder convs in one launch over all T (same input, N doubled); each chain then reads
+                # its channel half of the [.., 2C] map through a pitched TMA descriptor
+                eng._gemm(e["fb_conv"], x, d["efb"], N, xh, xw, xc, act=ACT_RELU)
+                self.launches += 1
             side.wait_stream(main)
             for (strm, conv, src, hbuf, cbuf, layer, rev) in (
                     (main, e["f_conv"], d["ef"], d["hf"], d["cf"], e["f_lstm"], False),
                     (side, e["b_conv"], d["eb"], d["hb"], d["cb"], e["b_lstm"], True)):
                 with torch.cuda.stream(strm):
-                    # encoder conv is not recurrent: one launch over all T (...V5.py:129-130, conv part)
-                    eng._gemm(conv, x, src, N, xh, xw, xc, act=ACT_RELU)
+                    if not merged:
+                        # encoder conv is not recurrent: one launch over all T (...V5.py:129-130, conv part)
+                        eng._gemm(conv, x, src, N, xh, xw, xc, act=ACT_RELU)
+                        self.launches += 1
                     for k in range(T):
                         t, tprev = (T - 1 - k, T - k) if rev else (k, k - 1)
                         first = k == 0
-                        eng._gemm(layer, src[t * B:(t + 1) * B], hbuf[t * B:(t + 1) * B], B, h, w, C,
+                        if merged:
+                            xin = d["efb"][t * B:(t + 1) * B, :, :, (C if rev else 0):(2 * C if rev else C)]
+                            pitch = dict(a0_ld=2 * C)
+                        else:
+                            xin, pitch = src[t * B:(t + 1) * B], {}
+                        eng._gemm(layer, xin, hbuf[t * B:(t + 1) * B], B, h, w, C,
                                   a1=d["zero"] if first else hbuf[tprev * B:(tprev + 1) * B], c1=C,
-                                  epi=EPI_LSTM, c_prev=None if first else cbuf[(k + 1) & 1], c_out=cbuf[k & 1])
-                    self.launches += 1 + T
+                                  epi=EPI_LSTM, c_prev=None if first else cbuf[(k + 1) & 1], c_out=cbuf[k & 1], **pitch)
+                    self.launches += T
             main.wait_stream(side)
             # merged = ff + fb (...V5.py:137-147)
             ops.add(d["hf"], d["hb"], out_f32=d["feat"], out_t=None if eng.dtype == torch.float32 else d["feat_t"],

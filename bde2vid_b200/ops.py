@@ -79,7 +79,7 @@ def head_conv(vox, w, bias, out, act=ACT_RELU):
 def gemm(a0, w, bias, out, *, n_img, h_in, w_in, c0, n, ksize=1, stride=1, pad=0, a1=None, c1=0, w_ld=0,
          epi=EPI_STORE, act=ACT_NONE, out_f32=False, residual=None, c_prev=None, c_out=None, row_map=None,
          out2=None, engine=ENGINE_SIMT, dtype=None, k_order=0, ln_frames=None, ln_tok_map=None, ln_n_tok=1,
-         res_mode=0):
+         res_mode=0, a0_ld=0, a1_ld=0):
     """Implicit-GEMM conv / linear (see bde_gemm in include/bde2vid.h).  Returns (h_out, w_out).
     ``ln_frames`` (list of float32 [*, c0] tensors or None) switches the A operand to the fused
     LayerNorm-gather form (``a0`` is then ignored and may be None)."""
@@ -87,7 +87,9 @@ def gemm(a0, w, bias, out, *, n_img, h_in, w_in, c0, n, ksize=1, stride=1, pad=0
     d = _lib.GemmDesc()
     d.engine = engine
     d.dtype = BDE_DTYPE[a0.dtype if dtype is None else dtype]
-    d.a0, d.a1 = ptr(a0), ptr(a1)
+    # a pitched source is a channel slice of a wider NHWC map: not contiguous by construction, only its base matters
+    d.a0 = C.c_void_p(a0.data_ptr()) if (a0_ld and a0 is not None) else ptr(a0)
+    d.a1 = C.c_void_p(a1.data_ptr()) if (a1_ld and a1 is not None) else ptr(a1)
     if ln_frames is not None:
         d.ln_mode, d.ln_D, d.ln_n_tok = 1, len(ln_frames), ln_n_tok
         for i, f in enumerate(ln_frames):
@@ -102,6 +104,7 @@ def gemm(a0, w, bias, out, *, n_img, h_in, w_in, c0, n, ksize=1, stride=1, pad=0
     d.epi, d.act, d.out_f32 = epi, act, int(out_f32)
     d.out, d.residual, d.c_prev, d.c_out = ptr(out), ptr(residual), ptr(c_prev), ptr(c_out)
     d.row_map, d.out2, d.res_mode = ptr(row_map), ptr(out2), res_mode
+    d.a0_ld, d.a1_ld = a0_ld, a1_ld
     check(lib.bde_gemm(C.byref(d), stream_ptr()), "bde_gemm")
     return d.h_out, d.w_out
 

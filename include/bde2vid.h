@@ -142,6 +142,10 @@ typedef struct bde_gemm_desc {
                          /* MLP, DTransformer.py:302-304); 1 = `residual` has element type `dtype`   */
                          /* and is added BEFORE the activation (ResidualBlock,                        */
                          /* model/e2vid/submodules.py:234-247: out = relu(conv2(..) + x))            */
+  int a0_ld, a1_ld;      /* pixel pitch of a0 / a1 in elements (0 = c0 / c1): lets a source be a      */
+                         /* channel slice of a wider NHWC buffer (the forward / backward encoder convs */
+                         /* write one [.., 2C] map, each ConvLSTM chain reads its half).  Only the      */
+                         /* TMA convolution kernel of the tcgen05 engine accepts a pitch != c.          */
 } bde_gemm_desc;
 
 int bde_gemm(const bde_gemm_desc* desc, void* stream);

@@ -348,3 +348,35 @@ def test_conv_tma_lstm_epilogue(B, hid, h, w, pair):
     ec = (cout.cpu().permute(0, 3, 1, 2) - c_ref).abs().max()
     print("conv_tma lstm pair", pair, (B, hid, h, w), float(eh), float(ec))
     assert ec <= 2e-3 and eh <= 6e-3
+
+
+@pytest.mark.parametrize("k,stride", [(3, 1), (5, 2)])
+def test_conv_tma_pitched_source(k, stride):
+    """A operand = channel slice [C, 2C) of a wider NHWC map through a0_ld (how each ConvLSTM chain reads its half of the
+    merged forward / backward encoder conv output)."""
+    from bde2vid_b200 import ops
+    from bde2vid_b200.engine import _pack_conv
+    g = torch.Generator().manual_seed(k + stride)
+    n, C, co, h, w = 3, 64, 128, 24, 40
+    wide = bf16r(torch.randn(n, 2 * C, h, w, generator=g))
+    wt = bf16r(torch.randn(co, C, k, k, generator=g) / (C * k * k) ** 0.5)
+    b = torch.randn(co, generator=g)
+    ref = F.conv2d(wide[:, C:], wt, b, stride=stride, padding=k // 2)
+    pw, ld = _pack_conv(wt.to(DEV), torch.bfloat16, chunk_major=True)
+    a = nhwc(wide, torch.bfloat16)                                   # [n, h, w, 2C]
+    ho, wo = (h + 2 * (k // 2) - k) // stride + 1, (w + 2 * (k // 2) - k) // stride + 1
+    out = torch.zeros(n, ho, wo, co, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(a[..., C:], pw, b.to(DEV), out, n_img=n, h_in=h, w_in=w, c0=C, n=co, ksize=k, stride=stride, pad=k // 2, w_ld=ld,
+             engine=ops.ENGINE_TCGEN05, dtype=torch.bfloat16, k_order=1, a0_ld=2 * C)
+    torch.cuda.synchronize()
+    err = (out.float().cpu().permute(0, 3, 1, 2) - ref).abs().max()
+    print("pitched", k, stride, float(err))
+    assert err <= 1e-2 * max(1.0, ref.abs().max())
+    # the cp.async engine refuses a pitched source loudly instead of reading the wrong pixels
+    os.environ["BDE2VID_CONV_TMA"] = "0"
+    try:
+        with pytest.raises(RuntimeError):
+            ops.gemm(a[..., C:], pw, b.to(DEV), out, n_img=n, h_in=h, w_in=w, c0=C, n=co, ksize=k, stride=stride, pad=k // 2,
+                     w_ld=ld, engine=ops.ENGINE_TCGEN05, dtype=torch.bfloat16, k_order=1, a0_ld=2 * C)
+    finally:
+        os.environ.pop("BDE2VID_CONV_TMA", None)
