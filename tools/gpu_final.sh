@@ -18,6 +18,6 @@ timeout 600 ncu --set full --import-source on --clock-control none -k regex:conv
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:attn_fused_kernel -s 20 -c 1 -o gpurun_out/prof_attn64 $CMD1 > gpurun_out/ncu2.log 2>&1; echo "ncu attn64 exit $?"
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:attn_win256_kernel -s 30 -c 1 -o gpurun_out/prof_attn_win256 $CMD1 > gpurun_out/ncu3.log 2>&1; echo "ncu win256 exit $?"
 timeout 600 ncu --set full --clock-control none -k regex:mlp_fused -s 60 -c 2 -o gpurun_out/prof_mlp $CMD1 > gpurun_out/ncu4.log 2>&1; echo "ncu mlp exit $?"
-timeout 600 ncu --set full --clock-control none -k regex:voxel_cluster_kernel -s 4 -c 1 -o gpurun_out/prof_voxel $CMD1 > gpurun_out/ncu5.log 2>&1; echo "ncu voxel exit $?"
+timeout 600 ncu --set full --clock-control none -k regex:voxel_atomic_kernel -s 4 -c 1 -o gpurun_out/prof_voxel $CMD1 > gpurun_out/ncu5.log 2>&1; echo "ncu voxel exit $?"
 for f in prof_conv_lstm prof_attn64 prof_attn_win256 prof_mlp prof_voxel; do ncu -i gpurun_out/$f.ncu-rep --page raw --csv > gpurun_out/$f.raw.csv 2>/dev/null; done
 ls -la gpurun_out | head -40
