@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
   const int tbl_ld = p.D * kRel;
 
   // weight half-slice hs (0 .. 31): slice = hs / 2 (q, k, v of head group 0..3, then the 4 proj slices), K half = hs & 1
-  long long t_ln = 0, t_gemm = 0, t_gather = 0, t_tbl = 0, t_attn = 0, t_proj = 0;
+  long long t_ln = 0, t_gemm = 0, t_gather = 0, t_tbl = 0, t_attn = 0;
   const bool dbg = p.dbg != nullptr;
   const long long t_begin = dbg ? clock64() : 0;
   auto load_half = [&](int hs) {

@@ -45,7 +45,6 @@ constexpr int kCvEpiWarp0 = 2;
 constexpr int kCvEpiWarps = 8;
 constexpr int kCvD1 = 8, kCvD2 = 16;   // output tile: 8 pixels along the atom axis x 16 along the other one
 constexpr int kCvHaloPitch = 16;       // pixels per halo column (8 + k - 1 <= 16)
-constexpr int kCvMaxHaloCols = 20;     // 16 + 5 - 1
 
 // epilogue specialisations (compile-time: the generic one interprets the descriptor at run time)
 constexpr int kEpiGeneric = 0;  // anything bde_gemm supports (fp32 output, residuals, every activation)
