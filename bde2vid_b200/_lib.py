@@ -12,8 +12,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbde2vid_sm100.so")
 
 F32, BF16 = 0, 1
+ABI_VERSION = 2
 ACT_NONE, ACT_RELU, ACT_RELU6, ACT_GELU, ACT_SIGMOID = 0, 1, 2, 3, 4
-EPI_STORE, EPI_LSTM, EPI_SCATTER = 0, 1, 2
+EPI_STORE, EPI_LSTM, EPI_SCATTER, EPI_GRU_UR, EPI_GRU_OUT = 0, 1, 2, 3, 4
 ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1
 
 TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16}
@@ -43,9 +44,13 @@ EXPORTS = {
     "bde_last_error": (C.c_char_p, []),
     "bde_abi_version": (C.c_int, []),
     "bde_device_ok": (C.c_int, []),
-    "bde_voxelize_seq": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "bde_voxelize_seq": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 8 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "bde_voxelize_seq_strided": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 8 + [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
-                                           C.c_void_p]),
+                                           C.c_int, C.c_void_p, C.c_void_p]),
+    "bde_voxelize_raw_strided": (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 8 + [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int,
+                                           C.c_int, C.c_void_p, C.c_void_p]),
+    "bde_voxel_normalize": (C.c_int, [C.c_void_p, C.c_size_t] + [C.c_int] * 9 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "bde_hot_pixel_mask": (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bde_frame_metrics": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 7 + [C.c_double, C.c_void_p, C.c_void_p]),
     "bde_head_conv": (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 7 + [C.c_void_p]),
     "bde_pack_voxel_nhwc": (C.c_int, [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_void_p]),
@@ -57,7 +62,9 @@ EXPORTS = {
                           C.c_void_p]),
     "bde_upsample2x_sum": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float] + [C.c_int] * 4
                            + [C.c_void_p, C.c_int, C.c_void_p]),
-    "bde_pred_sigmoid": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]),
+    "bde_pred_sigmoid": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "bde_window_reduce": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bde_ln_gather": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "bde_layernorm": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
@@ -96,7 +103,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.bde_abi_version() != 1:
+    if lib.bde_abi_version() != ABI_VERSION:
         raise RuntimeError("libbde2vid_sm100.so ABI mismatch")
     _lib = lib
     return lib

@@ -105,6 +105,10 @@ extern "C" int bde_gemm(const bde_gemm_desc* d, void* stream) {
     BDE_REQUIRE(d->n % 4 == 0 && d->c_out != nullptr, "bde_gemm: LSTM epilogue needs n %% 4 == 0 and c_out");
   } else if (d->epi == BDE_EPI_SCATTER) {
     BDE_REQUIRE(d->row_map != nullptr, "bde_gemm: SCATTER epilogue needs row_map");
+  } else if (d->epi == BDE_EPI_GRU_UR) {
+    BDE_REQUIRE(d->n % 4 == 0 && d->c_out != nullptr, "bde_gemm: GRU_UR epilogue needs n %% 4 == 0 and c_out (u)");
+  } else if (d->epi == BDE_EPI_GRU_OUT) {
+    BDE_REQUIRE(d->c_out != nullptr && d->residual != nullptr, "bde_gemm: GRU_OUT epilogue needs c_out (h') and residual (u)");
   } else {
     BDE_REQUIRE(d->epi == BDE_EPI_STORE, "bde_gemm: unknown epilogue %d", d->epi);
   }

@@ -140,24 +140,74 @@ __global__ void __launch_bounds__(256) upsample2x_sum_block_kernel(const TS* __r
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void pred_sigmoid_kernel(const T* __restrict__ x, const T* __restrict__ head,
-                                    const float* __restrict__ wt, const float* __restrict__ bias, int c,
-                                    size_t n_pix, float* __restrict__ img) {
-  extern __shared__ float sw[];
-  for (int i = threadIdx.x; i < c; i += blockDim.x) sw[i] = wt[i];
+                                    const float* __restrict__ wt, const float* __restrict__ wt_head,
+                                    const float* __restrict__ bias, int c, size_t n_pix, float* __restrict__ img, int act) {
+  extern __shared__ float sw[];   // [2][c]: weights of x, weights of head
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    sw[i] = wt[i];
+    sw[c + i] = wt_head != nullptr ? wt_head[i] : wt[i];
+  }
   __syncthreads();
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pix) return;
   float acc = bias[0];
   const T* xp = x + p * c;
   const T* hp = head + p * c;
-  for (int k = 0; k < c; k += 4) {
-    float4 a = load4<T>(xp + k), b = load4<T>(hp + k);
-    acc = fmaf(sw[k + 0], a.x + b.x, acc);
-    acc = fmaf(sw[k + 1], a.y + b.y, acc);
-    acc = fmaf(sw[k + 2], a.z + b.z, acc);
-    acc = fmaf(sw[k + 3], a.w + b.w, acc);
+  if (wt_head == nullptr) {       // skip_sum: w . (x + head), the reference's order
+    for (int k = 0; k < c; k += 4) {
+      float4 a = load4<T>(xp + k), b = load4<T>(hp + k);
+      acc = fmaf(sw[k + 0], a.x + b.x, acc);
+      acc = fmaf(sw[k + 1], a.y + b.y, acc);
+      acc = fmaf(sw[k + 2], a.z + b.z, acc);
+      acc = fmaf(sw[k + 3], a.w + b.w, acc);
+    }
+  } else {                        // skip_concat: the two 1x1 convolutions folded into one [2c] vector
+    for (int k = 0; k < c; k += 4) {
+      float4 a = load4<T>(xp + k), b = load4<T>(hp + k);
+      acc = fmaf(sw[k + 0], a.x, acc); acc = fmaf(sw[c + k + 0], b.x, acc);
+      acc = fmaf(sw[k + 1], a.y, acc); acc = fmaf(sw[c + k + 1], b.y, acc);
+      acc = fmaf(sw[k + 2], a.z, acc); acc = fmaf(sw[c + k + 2], b.z, acc);
+      acc = fmaf(sw[k + 3], a.w, acc); acc = fmaf(sw[c + k + 3], b.w, acc);
+    }
   }
-  img[p] = sigmoid_f(acc);
+  img[p] = act == BDE_ACT_SIGMOID ? sigmoid_f(acc) : acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Window "feature reduction" of WindowAttention3D with nwin_size set (DTransformer.py:128-131, 172-175): a depthwise
+// convolution whose kernel covers the whole window, Conv2d(C, X*C, kernel = window, groups = C), turns the n_tok tokens of
+// a (frame, window) into X = nwin0 * nwin1 tokens.  The reference then VIEWS the [C*X] output vector (index o = c*X + j)
+// as [X, C] (index j'*C + c'), which this kernel reproduces: out[(win*D + d)*X + j', c'] = conv[o = j'*C + c'],
+// conv[o] = b[o] + sum_tok w[o, tok] * x[d, win, tok, o / X].   One warp per (win, d, j'); zero tokens contribute 0.
+// ---------------------------------------------------------------------------------------------
+struct FramePtrs8 {
+  const float* f[8];
+};
+__global__ void __launch_bounds__(256) window_reduce_kernel(FramePtrs8 frames, int D, const int* __restrict__ tok_map, int n_tok, int c,
+                                                            int X, const float* __restrict__ w, const float* __restrict__ b,
+                                                            float* __restrict__ out, size_t total_rows) {
+  const size_t row = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // (win, d, j')
+  const int lane = threadIdx.x & 31;
+  if (row >= total_rows) return;
+  const int jp = (int)(row % X);
+  const size_t wd = row / X;
+  const int d = (int)(wd % D);
+  const size_t win = wd / D;
+  const float* fr = frames.f[d];
+  const int* tm = tok_map + win * n_tok;
+  for (int cp = lane; cp < c; cp += 32) {
+    const int o = jp * c + cp;
+    const int ch = o / X;
+    float acc = b != nullptr ? b[o] : 0.f;
+    if (fr != nullptr) {
+      const float* wo = w + (size_t)o * n_tok;
+      for (int t = 0; t < n_tok; ++t) {
+        const int src = tm[t];
+        if (src >= 0) acc = fmaf(wo[t], fr[(size_t)src * c + ch], acc);
+      }
+    }
+    out[row * c + cp] = acc;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -372,17 +422,32 @@ extern "C" int bde_upsample2x_sum(const void* skip, int skip_f32, const void* x,
   return launch_upsample<__nv_bfloat16>(skip, skip_f32, x, x_f32, x_scale, n_img, h, w, c, dst, s);
 }
 
-extern "C" int bde_pred_sigmoid(const void* x, const void* head, const float* wt, const float* bias, int c,
-                                size_t n_pix, float* img, int dtype, void* stream) {
+extern "C" int bde_pred_sigmoid(const void* x, const void* head, const float* wt, const float* wt_head, const float* bias, int c,
+                                size_t n_pix, float* img, int dtype, int act, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   BDE_REQUIRE(c % 4 == 0 && c <= 4096, "bde_pred_sigmoid: bad channel count");
+  BDE_REQUIRE(act == BDE_ACT_SIGMOID || act == BDE_ACT_NONE, "bde_pred_sigmoid: activation must be SIGMOID or NONE");
   if (n_pix == 0) return 0;
   unsigned blocks = (unsigned)ceil_div(n_pix, 128);
+  const size_t smem = (size_t)2 * c * sizeof(float);
   if (dtype == BDE_F32)
-    pred_sigmoid_kernel<float><<<blocks, 128, c * sizeof(float), s>>>((const float*)x, (const float*)head, wt, bias, c, n_pix, img);
+    pred_sigmoid_kernel<float><<<blocks, 128, smem, s>>>((const float*)x, (const float*)head, wt, wt_head, bias, c, n_pix, img, act);
   else
-    pred_sigmoid_kernel<__nv_bfloat16><<<blocks, 128, c * sizeof(float), s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)head, wt, bias, c, n_pix, img);
+    pred_sigmoid_kernel<__nv_bfloat16><<<blocks, 128, smem, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)head, wt, wt_head, bias, c, n_pix, img, act);
   return check_launch("pred_sigmoid_kernel");
+}
+
+extern "C" int bde_window_reduce(const float* const* frames_host, int D, const int* tok_map, int n_win, int n_tok, int c, int X,
+                                 const float* w, const float* b, float* out, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  BDE_REQUIRE(D >= 1 && D <= 8 && X >= 1 && c >= 1 && n_tok >= 1, "bde_window_reduce: bad sizes");
+  BDE_REQUIRE(tok_map != nullptr && w != nullptr && out != nullptr, "bde_window_reduce: null pointer");
+  FramePtrs8 fp;
+  for (int i = 0; i < 8; ++i) fp.f[i] = i < D ? frames_host[i] : nullptr;
+  const size_t rows = (size_t)n_win * D * X;
+  if (rows == 0) return 0;
+  window_reduce_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, s>>>(fp, D, tok_map, n_tok, c, X, w, b, out, rows);
+  return check_launch("window_reduce_kernel");
 }
 
 extern "C" int bde_ln_gather(const float* const* frames_host, int D, const int* tok_map, int n_win, int n_tok, int c,

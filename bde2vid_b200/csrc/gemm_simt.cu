@@ -168,6 +168,27 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_kernel(GemmParams p) {
       lstm_update(v[0], v[1], v[2], v[3], cp, h, c);
       p.c_out[o] = c;
       reinterpret_cast<T*>(p.out)[o] = from_f32<T>(h);
+    } else if (p.epi == BDE_EPI_GRU_UR) {
+      // columns nb..nb+3 = (update, reset) of hidden channels nb/2 and nb/2 + 1 (submodules.py:371-373)
+      const int hid = p.N / 2, ch = nb / 2;
+      size_t o = (size_t)m * hid + ch;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float hp = p.c_prev != nullptr ? p.c_prev[o + j] : 0.f;
+        p.c_out[o + j] = sigmoid_f(v[2 * j]);
+        reinterpret_cast<T*>(p.out)[o + j] = from_f32<T>(hp * sigmoid_f(v[2 * j + 1]));
+      }
+    } else if (p.epi == BDE_EPI_GRU_OUT) {
+      // h' = h (1 - u) + tanh(out_gate) u (submodules.py:374-375)
+      size_t o = (size_t)m * p.N + nb;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float hp = p.c_prev != nullptr ? p.c_prev[o + j] : 0.f;
+        const float u = reinterpret_cast<const float*>(p.residual)[o + j];
+        const float hn = hp * (1.0f - u) + tanh_f(v[j]) * u;
+        p.c_out[o + j] = hn;
+        reinterpret_cast<T*>(p.out)[o + j] = from_f32<T>(hn);
+      }
     } else {  // BDE_EPI_SCATTER
       int dst = p.row_map[m];
       if (dst >= 0) {

@@ -337,6 +337,13 @@ __device__ __forceinline__ float4 aux_load(const TcParams& p, int m, int nb, int
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p.epi == BDE_EPI_LSTM) {
     if (p.c_prev != nullptr) a.x = p.c_prev[(size_t)m * (p.N >> 2) + (nb >> 2)];
+  } else if (p.epi == BDE_EPI_GRU_UR) {   // h_prev of the two hidden channels of this quad
+    if (p.c_prev != nullptr) {
+      const float2 h2 = *reinterpret_cast<const float2*>(p.c_prev + (size_t)m * (p.N >> 1) + (nb >> 1));
+      a.x = h2.x; a.y = h2.y;
+    }
+  } else if (p.epi == BDE_EPI_GRU_OUT) {  // h_prev of the four hidden channels
+    if (p.c_prev != nullptr) a = *reinterpret_cast<const float4*>(p.c_prev + (size_t)m * p.N + nb);
   } else if (p.epi == BDE_EPI_STORE) {
     if (p.residual != nullptr) {
       const size_t o = (size_t)m * p.N + nb;
@@ -349,7 +356,7 @@ __device__ __forceinline__ float4 aux_load(const TcParams& p, int m, int nb, int
         a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + o);
       }
     }
-  } else if (dst_row >= 0) {
+  } else if (p.epi == BDE_EPI_SCATTER && dst_row >= 0) {
     a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + (size_t)dst_row * p.N + nb);
   }
   return a;
@@ -386,6 +393,24 @@ __device__ __forceinline__ void epilogue_quad_aux(const TcParams& p, int m, int 
     const float h = mufu_sigmoid(v2) * mufu_tanh(c);
     p.c_out[o] = c;
     reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16_rn(h);
+  } else if (p.epi == BDE_EPI_GRU_UR) {
+    // ConvGRU, first conv (submodules.py:371-373): quad = (update, reset) of hidden channels nb/2, nb/2 + 1
+    const size_t o = (size_t)m * (p.N >> 1) + (nb >> 1);
+    *reinterpret_cast<float2*>(p.c_out + o) = make_float2(mufu_sigmoid(v0), mufu_sigmoid(v2));
+    *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) =
+        __floats2bfloat162_rn(aux.x * mufu_sigmoid(v1), aux.y * mufu_sigmoid(v3));
+  } else if (p.epi == BDE_EPI_GRU_OUT) {
+    // ConvGRU, second conv (submodules.py:374-375): h' = h (1 - u) + tanh(out_gate) u
+    const size_t o = (size_t)m * p.N + nb;
+    const float4 u = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + o));
+    const float h0 = fmaf(aux.x, 1.0f - u.x, mufu_tanh(v0) * u.x), h1 = fmaf(aux.y, 1.0f - u.y, mufu_tanh(v1) * u.y);
+    const float h2 = fmaf(aux.z, 1.0f - u.z, mufu_tanh(v2) * u.z), h3 = fmaf(aux.w, 1.0f - u.w, mufu_tanh(v3) * u.w);
+    *reinterpret_cast<float4*>(p.c_out + o) = make_float4(h0, h1, h2, h3);
+    const __nv_bfloat162 t0 = __floats2bfloat162_rn(h0, h1), t1 = __floats2bfloat162_rn(h2, h3);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&t0);
+    pk.y = *reinterpret_cast<const uint32_t*>(&t1);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = pk;
   } else if (dst_row >= 0) {  // BDE_EPI_SCATTER
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (size_t)dst_row * p.N + nb) =
         make_float4(aux.x + v0, aux.y + v1, aux.z + v2, aux.w + v3);

@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(512) voxel_band_kernel(
     const float* __restrict__ xs, const float* __restrict__ ys, const float* __restrict__ ts,
     const float* __restrict__ ps, const int64_t* __restrict__ offsets, int bins, int H, int W,
     int pad_top, int pad_left, int Hp, int Wp, int band_rows, int vec_ok, float* __restrict__ out,
-    size_t win_stride, int* oob_count) {
+    size_t win_stride, int* oob_count, int min_events) {
   extern __shared__ float tile[];  // [bins][band_rows][W]
   const int win = blockIdx.y;
   const int r0 = blockIdx.x * band_rows;           // first padded row of this band
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(512) voxel_band_kernel(
   __syncthreads();
 
   const int64_t ea = offsets[win], eb = offsets[win + 1];
-  if (eb > ea) {
+  if (eb - ea >= min_events) {
     const float t0 = ts[ea];
     const float dt = __fsub_rn(ts[eb - 1], t0);
     const float bm1 = (float)(bins - 1);
@@ -169,38 +169,152 @@ __global__ void __launch_bounds__(512) voxel_band_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
-// Algorithm 2: global float atomics (RED) into a zeroed grid.  Used for sensors too large for the
-// row-band tiling (each band would have to re-scan the whole window).
+// Algorithm 2 (default): global float reductions (RED.ADD.F32, executed in place by L2) into a zeroed grid.
+// Event sources: the loader format (four float32 streams, 16 B / event) or the reference's ON-DISK format
+// (events_contrast_maximization/tools/event_packagers.py:44-47: xs, ys int16, ts float64 seconds, ps bool; 13 B / event)
+// with the loader's conversions done in registers (data_loader/h5_dataset.py:222-225, :414):
+//   x, y -> float32 (exact), t -> float32(ts - ts[window start]) (float64 subtraction, then the cast), p -> 2 p - 1.
+// Each thread takes FOUR consecutive events per iteration with 128-bit (64- / 32-bit for the narrow types) loads;
+// kAgg adds a warp-level pre-reduction: lanes whose event hits the same (pixel, left bin) cell are found with
+// __match_any_sync and only the group leader issues the reductions -- a win for spatially clustered streams, a loss
+// for uniform ones (tools/voxel_probe.py measures both), hence selectable.
 // ------------------------------------------------------------------------------------------------
+struct EvSrcF32 {
+  const float *x, *y, *t, *p;
+  __device__ __forceinline__ bool vec_ok() const {
+    return ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)t) | ((uintptr_t)p)) & 15) == 0;
+  }
+  __device__ __forceinline__ void window(int64_t ea, int64_t eb, float& dt) const { t0 = t[ea]; dt = __fsub_rn(t[eb - 1], t0); }
+  __device__ __forceinline__ void load1(int64_t e, float& xx, float& yy, float& tt, float& pp) const {
+    xx = __ldg(x + e); yy = __ldg(y + e); tt = __fsub_rn(__ldg(t + e), t0); pp = __ldg(p + e);
+  }
+  __device__ __forceinline__ void load4(int64_t e, float (&xx)[4], float (&yy)[4], float (&tt)[4], float (&pp)[4]) const {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + e)), b = __ldg(reinterpret_cast<const float4*>(y + e));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(t + e)), d = __ldg(reinterpret_cast<const float4*>(p + e));
+    xx[0] = a.x; xx[1] = a.y; xx[2] = a.z; xx[3] = a.w;
+    yy[0] = b.x; yy[1] = b.y; yy[2] = b.z; yy[3] = b.w;
+    tt[0] = __fsub_rn(c.x, t0); tt[1] = __fsub_rn(c.y, t0); tt[2] = __fsub_rn(c.z, t0); tt[3] = __fsub_rn(c.w, t0);
+    pp[0] = d.x; pp[1] = d.y; pp[2] = d.z; pp[3] = d.w;
+  }
+  mutable float t0;
+};
+
+struct EvSrcRaw {
+  const int16_t *x, *y;
+  const double* t;
+  const uint8_t* p;
+  __device__ __forceinline__ bool vec_ok() const {
+    return ((((uintptr_t)x) | ((uintptr_t)y)) & 7) == 0 && (((uintptr_t)t) & 15) == 0 && (((uintptr_t)p) & 3) == 0;
+  }
+  // h5_dataset.py:222-225: ts_0 = ts[0] (float64); ts = (ts - ts_0).astype(float32); then event_utils.py:489 dt = ts[-1] - ts[0]
+  __device__ __forceinline__ void window(int64_t ea, int64_t eb, float& dt) const {
+    t0 = t[ea];
+    dt = __fsub_rn(__double2float_rn(__dsub_rn(t[eb - 1], t0)), 0.0f);
+  }
+  __device__ __forceinline__ float rel(double tv) const { return __fsub_rn(__double2float_rn(__dsub_rn(tv, t0)), 0.0f); }
+  __device__ __forceinline__ void load1(int64_t e, float& xx, float& yy, float& tt, float& pp) const {
+    xx = (float)x[e]; yy = (float)y[e]; tt = rel(t[e]); pp = p[e] ? 1.0f : -1.0f;     // h5_dataset.py:414 ps * 2.0 - 1.0
+  }
+  __device__ __forceinline__ void load4(int64_t e, float (&xx)[4], float (&yy)[4], float (&tt)[4], float (&pp)[4]) const {
+    const short4 a = __ldg(reinterpret_cast<const short4*>(x + e)), b = __ldg(reinterpret_cast<const short4*>(y + e));
+    const double2 c0 = __ldg(reinterpret_cast<const double2*>(t + e)), c1 = __ldg(reinterpret_cast<const double2*>(t + e + 2));
+    const uchar4 d = __ldg(reinterpret_cast<const uchar4*>(p + e));
+    xx[0] = (float)a.x; xx[1] = (float)a.y; xx[2] = (float)a.z; xx[3] = (float)a.w;
+    yy[0] = (float)b.x; yy[1] = (float)b.y; yy[2] = (float)b.z; yy[3] = (float)b.w;
+    tt[0] = rel(c0.x); tt[1] = rel(c0.y); tt[2] = rel(c1.x); tt[3] = rel(c1.y);
+    pp[0] = d.x ? 1.0f : -1.0f; pp[1] = d.y ? 1.0f : -1.0f; pp[2] = d.z ? 1.0f : -1.0f; pp[3] = d.w ? 1.0f : -1.0f;
+  }
+  mutable double t0;
+};
+
+template <typename Src, bool kAgg>
 __global__ void __launch_bounds__(256) voxel_atomic_kernel(
-    const float* __restrict__ xs, const float* __restrict__ ys, const float* __restrict__ ts,
-    const float* __restrict__ ps, const int64_t* __restrict__ offsets, int bins, int H, int W,
-    int pad_top, int pad_left, int Hp, int Wp, float* __restrict__ out, size_t win_stride, int* oob_count) {
-  const int win = blockIdx.y;
+    const Src src, const int64_t* __restrict__ offsets, int win0, int bins, int H, int W, int pad_top, int pad_left, int Hp, int Wp,
+    float* __restrict__ out, size_t win_stride, int* oob_count, int min_events, const float* __restrict__ hot_mask) {
+  const int win = win0 + blockIdx.y;
   const int64_t ea = offsets[win], eb = offsets[win + 1];
-  if (eb <= ea) return;
-  const float t0 = ts[ea];
-  const float dt = __fsub_rn(ts[eb - 1], t0);
+  // loader contract (h5_dataset.py:219-221): windows with fewer than `min_events` events give an all-zero grid
+  if (eb - ea < (int64_t)min_events || eb <= ea) return;
+  float dt;
+  src.window(ea, eb, dt);
   const float bm1 = (float)(bins - 1);
   float* dst = out + (size_t)win * win_stride;
   const size_t plane = (size_t)Hp * Wp;
   int oob = 0;
-  for (int64_t e = ea + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < eb;
-       e += (int64_t)gridDim.x * blockDim.x) {
-    float x = __ldg(xs + e), y = __ldg(ys + e), t = __ldg(ts + e), p = __ldg(ps + e);
-    int xi = (int)x, yi = (int)y;
-    if (xi < 0 || xi >= W || yi < 0 || yi >= H) {
-      oob++;
-      continue;
+  // `live` = false lanes only take part in the warp votes of the aggregated form
+  auto one = [&](float x, float y, float t, float p, bool live) {
+    const int xi = (int)x, yi = (int)y;  // truncation == .long() (event_utils.py:371-374)
+    const bool inside = live && xi >= 0 && xi < W && yi >= 0 && yi < H;
+    if (live && !inside) oob++;
+    // hot-pixel mask (h5_dataset.py:163-172,364: voxel * mask with mask in {0, 1}): masked pixels receive nothing
+    const bool keep = inside && (hot_mask == nullptr || __ldg(hot_mask + (size_t)yi * W + xi) != 0.0f);
+    // tn = ((t - t0) / dt) * (B - 1); the sources hand over t - t0
+    EventContrib c;
+    {
+      const float tn = __fmul_rn(__fdiv_rn(t, dt), bm1);
+      if (!(tn == tn)) {
+        c.b0 = -1; c.w0 = tn; c.w1 = tn;
+      } else {
+        int b0 = (int)floorf(tn);
+        b0 = max(0, min(b0, bins - 1));
+        const float fb0 = (float)b0;
+        c.w0 = __fmul_rn(p, fmaxf(0.0f, __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fb0)))));
+        c.w1 = __fmul_rn(p, fmaxf(0.0f, __fsub_rn(1.0f, fabsf(__fsub_rn(tn, fb0 + 1.0f)))));
+        c.b0 = b0;
+      }
     }
-    EventContrib c = contrib(t, p, t0, dt, bm1, bins);
-    size_t pix = (size_t)(yi + pad_top) * Wp + (xi + pad_left);
-    if (c.b0 < 0) {
+    const size_t pix = keep ? (size_t)(yi + pad_top) * Wp + (xi + pad_left) : 0;
+    if (keep && c.b0 < 0) {  // NaN event (dt == 0): every bin of the pixel becomes NaN, as in the reference
       for (int b = 0; b < bins; ++b) atomicAdd(dst + b * plane + pix, c.w0);
-      continue;
     }
-    if (c.w0 != 0.0f) atomicAdd(dst + c.b0 * plane + pix, c.w0);
-    if (c.b0 + 1 < bins && c.w1 != 0.0f) atomicAdd(dst + (c.b0 + 1) * plane + pix, c.w1);
+    bool add = keep && c.b0 >= 0;
+    float w0 = c.w0, w1 = c.w1;
+    if (kAgg) {
+      const int lane = threadIdx.x & 31;
+      const int key = add ? (int)(c.b0 * plane + pix) : -1 - lane;
+      const unsigned peers = __match_any_sync(0xffffffffu, key);
+      if (__popc(peers) > 1) {
+        float s0 = 0.f, s1 = 0.f;
+        unsigned rem = peers;
+        while (rem) {
+          const int srcl = __ffs(rem) - 1;
+          rem &= rem - 1;
+          s0 += __shfl_sync(peers, w0, srcl);
+          s1 += __shfl_sync(peers, w1, srcl);
+        }
+        w0 = s0; w1 = s1;
+        add = add && lane == __ffs(peers) - 1;
+      }
+    }
+    if (add) {
+      if (w0 != 0.0f) atomicAdd(dst + c.b0 * plane + pix, w0);
+      if (c.b0 + 1 < bins && w1 != 0.0f) atomicAdd(dst + (c.b0 + 1) * plane + pix, w1);
+    }
+  };
+  const bool vec = src.vec_ok();
+  // scalar head up to a multiple of 4, vector body, scalar tail
+  const int64_t body_a = vec ? min(eb, (ea + 3) & ~(int64_t)3) : eb;
+  const int64_t body_b = vec ? max(body_a, eb & ~(int64_t)3) : eb;
+  const int64_t n_edge = (body_a - ea) + (eb - body_b);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+  // (warp-uniform trip counts so that the aggregated form's votes stay convergent)
+  for (int64_t base = 0; base < n_edge; base += nthr) {
+    const int64_t i = base + tid;
+    const bool valid = i < n_edge;
+    const int64_t e = valid ? (i < body_a - ea ? ea + i : body_b + (i - (body_a - ea))) : ea;
+    float x, y, t, p;
+    src.load1(e, x, y, t, p);
+    if (kAgg || valid) one(x, y, t, p, valid);
+  }
+  const int64_t nvec = (body_b - body_a) >> 2;
+  for (int64_t base = 0; base < nvec; base += nthr) {
+    const int64_t v = base + tid;
+    const bool valid = v < nvec;
+    if (!kAgg && !valid) break;
+    float x[4], y[4], t[4], p[4];
+    src.load4(body_a + 4 * (valid ? v : 0), x, y, t, p);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) one(x[k], y[k], t[k], p[k], valid);
   }
   if (oob_count != nullptr && oob > 0) atomicAdd(oob_count, oob);
 }
@@ -231,7 +345,7 @@ __global__ void __launch_bounds__(512, 1) voxel_cluster_kernel(
     const float* __restrict__ xs, const float* __restrict__ ys, const float* __restrict__ ts,
     const float* __restrict__ ps, const int64_t* __restrict__ offsets, int bins, int H, int W,
     int pad_top, int pad_left, int Hp, int Wp, int band_rows, int nc, int vec_ok, float* __restrict__ out,
-    size_t win_stride, int* oob_count, int scan_all) {
+    size_t win_stride, int* oob_count, int scan_all, int min_events) {
   extern __shared__ __align__(16) float tile[];  // [bins][band_rows][W] of this CTA's band
   const int win = blockIdx.x / nc;
   uint32_t rank;
@@ -249,7 +363,7 @@ __global__ void __launch_bounds__(512, 1) voxel_cluster_kernel(
   vx_cluster_sync();  // every tile of the cluster is zeroed before anyone adds into it
 
   const int64_t ea = offsets[win], eb = offsets[win + 1];
-  if (eb > ea) {
+  if (eb - ea >= min_events) {
     const float t0 = ts[ea];
     const float dt = __fsub_rn(ts[eb - 1], t0);
     const float bm1 = (float)(bins - 1);
@@ -347,7 +461,7 @@ __global__ void __launch_bounds__(256) voxel_cluster_red_kernel(
     const float* __restrict__ xs, const float* __restrict__ ys, const float* __restrict__ ts,
     const float* __restrict__ ps, const int64_t* __restrict__ offsets, int bins, int H, int W,
     int pad_top, int pad_left, int Hp, int Wp, int nc, int vec_ok, float* __restrict__ out, size_t win_stride,
-    int* oob_count) {
+    int* oob_count, int min_events) {
   const int win = blockIdx.x / nc;
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -363,7 +477,7 @@ __global__ void __launch_bounds__(256) voxel_cluster_red_kernel(
   __threadfence();
   vx_cluster_sync();
   const int64_t ea = offsets[win], eb = offsets[win + 1];
-  if (eb <= ea) return;
+  if (eb - ea < min_events) return;
   const float t0 = ts[ea];
   const float dt = __fsub_rn(ts[eb - 1], t0);
   const float bm1 = (float)(bins - 1);
@@ -423,23 +537,86 @@ __global__ void pack_voxel_kernel(const float* __restrict__ vox, int bins, size_
 
 using namespace bde;
 
-extern "C" int bde_voxelize_seq_strided(const float* xs, const float* ys, const float* ts, const float* ps,
-                                        const int64_t* offsets, int T, int num_bins, int H, int W, int pad_top,
-                                        int pad_left, int Hp, int Wp, float* out, size_t out_window_stride,
-                                        int* oob_count, int algo, void* stream);
-
-extern "C" int bde_voxelize_seq(const float* xs, const float* ys, const float* ts, const float* ps,
-                                const int64_t* offsets, int T, int num_bins, int H, int W, int pad_top,
-                                int pad_left, int Hp, int Wp, float* out, int* oob_count, int algo,
-                                void* stream) {
-  return bde_voxelize_seq_strided(xs, ys, ts, ps, offsets, T, num_bins, H, W, pad_top, pad_left, Hp, Wp, out,
-                                  (size_t)num_bins * Hp * Wp, oob_count, algo, stream);
+// memset + reduction kernel, in chunks of windows whose grids fit L2 together: the lines zeroed by the memset are still
+// resident when the reductions hit them, so the grid goes to HBM once (write-back) instead of memset-write + reduction
+// read + write-back.
+template <typename Src>
+static int launch_atomic(const Src& src, bool agg, const int64_t* offsets, int T, int num_bins, int H, int W, int pad_top, int pad_left,
+                         int Hp, int Wp, float* out, size_t out_window_stride, int* oob_count, int min_events, const float* hot_mask,
+                         cudaStream_t s) {
+  const size_t grid_elems = (size_t)num_bins * Hp * Wp;
+  size_t chunk_mb = 48;
+  if (const char* e = getenv("BDE2VID_VOXEL_CHUNK_MB")) {
+    const long v = atol(e);
+    if (v > 0) chunk_mb = (size_t)v;
+  }
+  int per_chunk = (int)((chunk_mb << 20) / (out_window_stride * sizeof(float)));
+  per_chunk = per_chunk < 1 ? 1 : (per_chunk > T ? T : per_chunk);
+  int n_sm = kNumSMs;
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  for (int w0 = 0; w0 < T; w0 += per_chunk) {
+    const int n = (T - w0 < per_chunk) ? T - w0 : per_chunk;
+    float* base = out + (size_t)w0 * out_window_stride;
+    cudaError_t e = cudaMemset2DAsync(base, out_window_stride * sizeof(float), 0, grid_elems * sizeof(float), (size_t)n, s);
+    BDE_REQUIRE(e == cudaSuccess, "bde_voxelize_seq: memset: %s", cudaGetErrorString(e));
+    // grid.x sized so that the chunk is a few waves over the SMs regardless of its window count
+    int bx = (int)ceil_div((size_t)n_sm * 8, (size_t)n);
+    bx = bx < 1 ? 1 : (bx > 1024 ? 1024 : bx);
+    dim3 grid(bx, n);
+    if (agg)
+      voxel_atomic_kernel<Src, true><<<grid, 256, 0, s>>>(src, offsets, w0, num_bins, H, W, pad_top, pad_left, Hp, Wp, out,
+                                                          out_window_stride, oob_count, min_events, hot_mask);
+    else
+      voxel_atomic_kernel<Src, false><<<grid, 256, 0, s>>>(src, offsets, w0, num_bins, H, W, pad_top, pad_left, Hp, Wp, out,
+                                                           out_window_stride, oob_count, min_events, hot_mask);
+    const int rc = check_launch("voxel_atomic_kernel");
+    if (rc != 0) return rc;
+  }
+  return 0;
 }
 
 extern "C" int bde_voxelize_seq_strided(const float* xs, const float* ys, const float* ts, const float* ps,
                                         const int64_t* offsets, int T, int num_bins, int H, int W, int pad_top,
                                         int pad_left, int Hp, int Wp, float* out, size_t out_window_stride,
-                                        int* oob_count, int algo, void* stream) {
+                                        int* oob_count, int algo, int min_events, const float* hot_mask, void* stream);
+
+extern "C" int bde_voxelize_seq(const float* xs, const float* ys, const float* ts, const float* ps,
+                                const int64_t* offsets, int T, int num_bins, int H, int W, int pad_top,
+                                int pad_left, int Hp, int Wp, float* out, int* oob_count, int algo, int min_events,
+                                void* stream) {
+  return bde_voxelize_seq_strided(xs, ys, ts, ps, offsets, T, num_bins, H, W, pad_top, pad_left, Hp, Wp, out,
+                                  (size_t)num_bins * Hp * Wp, oob_count, algo, min_events, nullptr, stream);
+}
+
+extern "C" int bde_voxelize_raw_strided(const int16_t* xs, const int16_t* ys, const double* ts, const uint8_t* ps,
+                                        const int64_t* offsets, int T, int num_bins, int H, int W, int pad_top,
+                                        int pad_left, int Hp, int Wp, float* out, size_t out_window_stride,
+                                        int* oob_count, int algo, int min_events, const float* hot_mask, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t grid_elems = (size_t)num_bins * Hp * Wp;
+  BDE_REQUIRE(out_window_stride >= grid_elems, "bde_voxelize_raw: window stride smaller than one grid");
+  BDE_REQUIRE(T >= 0 && num_bins >= 1 && H > 0 && W > 0, "bde_voxelize_raw: bad sizes");
+  BDE_REQUIRE(pad_top >= 0 && pad_left >= 0 && Hp >= H + pad_top && Wp >= W + pad_left,
+              "bde_voxelize_raw: padded grid %dx%d cannot hold %dx%d at (%d,%d)", Hp, Wp, H, W, pad_top, pad_left);
+  BDE_REQUIRE(algo == 0 || algo == 2 || algo == 5, "bde_voxelize_raw: only the reduction kernels (algo 2 / 5) read the raw format");
+  if (T == 0) return 0;
+  if (algo == 0) {
+    const char* e = getenv("BDE2VID_VOXEL_ALGO");
+    algo = (e != nullptr && e[0] == '5') ? 5 : 2;
+  }
+  EvSrcRaw src;
+  src.x = xs; src.y = ys; src.t = ts; src.p = ps; src.t0 = 0.0;
+  return launch_atomic(src, algo == 5, offsets, T, num_bins, H, W, pad_top, pad_left, Hp, Wp, out, out_window_stride, oob_count,
+                       min_events, hot_mask, s);
+}
+
+extern "C" int bde_voxelize_seq_strided(const float* xs, const float* ys, const float* ts, const float* ps,
+                                        const int64_t* offsets, int T, int num_bins, int H, int W, int pad_top,
+                                        int pad_left, int Hp, int Wp, float* out, size_t out_window_stride,
+                                        int* oob_count, int algo, int min_events, const float* hot_mask, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const size_t grid_elems = (size_t)num_bins * Hp * Wp;
   BDE_REQUIRE(out_window_stride >= grid_elems, "bde_voxelize_seq: window stride smaller than one grid");
@@ -465,7 +642,7 @@ extern "C" int bde_voxelize_seq_strided(const float* xs, const float* ys, const 
   const bool cluster_ok = nc > 0 && Wp % 4 == 0 && (((uintptr_t)out) & 15) == 0 && out_window_stride % 4 == 0;
   if (algo == 0) {
     const char* e = getenv("BDE2VID_VOXEL_ALGO");
-    if (e != nullptr && e[0] >= '1' && e[0] <= '4') algo = e[0] - '0';
+    if (e != nullptr && e[0] >= '1' && e[0] <= '5') algo = e[0] - '0';
   }
   // algorithm 4 (cluster: zero + global reductions in one launch) needs 16-byte stores into the grid
   const bool red_ok = Wp % 4 == 0 && (((uintptr_t)out) & 15) == 0 && out_window_stride % 4 == 0;
@@ -474,6 +651,7 @@ extern "C" int bde_voxelize_seq_strided(const float* xs, const float* ys, const 
   //   (scan-all + local atomics 0.33 ms) | 4 cluster zero + global reductions 0.20 ms
   // -- L2 executes float reductions in place faster than any shared-memory staging, and 8-CTA cluster launches are slow.
   if (algo == 0) algo = 2;
+  if (hot_mask != nullptr && algo != 5) algo = 2;   // only the reduction kernels apply the hot-pixel mask
   if (algo == 4 && !red_ok) algo = 2;
   if (algo == 4) {
     const int vec_ok = ((((uintptr_t)xs) | ((uintptr_t)ys) | ((uintptr_t)ts) | ((uintptr_t)ps)) & 15) == 0;
@@ -492,7 +670,7 @@ extern "C" int bde_voxelize_seq_strided(const float* xs, const float* ys, const 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, voxel_cluster_red_kernel, xs, ys, ts, ps, offsets, num_bins, H, W, pad_top, pad_left, Hp, Wp,
-                                       ncl, vec_ok, out, out_window_stride, oob_count);
+                                       ncl, vec_ok, out, out_window_stride, oob_count, min_events);
     BDE_REQUIRE(e == cudaSuccess, "bde_voxelize_seq: cluster launch: %s", cudaGetErrorString(e));
     return check_launch("voxel_cluster_red_kernel");
   }
@@ -501,11 +679,9 @@ extern "C" int bde_voxelize_seq_strided(const float* xs, const float* ys, const 
   if (algo == 3 && !cluster_ok) algo = (bands <= 16) ? 1 : 2;
   if (algo == 3) {
     const size_t smem = (size_t)num_bins * crow * W * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
+    {  // set per call: the attribute is per device and the call is cheap
       cudaError_t e = cudaFuncSetAttribute(voxel_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       BDE_REQUIRE(e == cudaSuccess, "bde_voxelize_seq: smem attr: %s", cudaGetErrorString(e));
-      configured = smem;
     }
     const int vec_ok = ((((uintptr_t)xs) | ((uintptr_t)ys) | ((uintptr_t)ts) | ((uintptr_t)ps)) & 15) == 0;
     cudaLaunchConfig_t cfg;
@@ -524,7 +700,7 @@ extern "C" int bde_voxelize_seq_strided(const float* xs, const float* ys, const 
     const char* sm = getenv("BDE2VID_VOXEL_SCANALL");
     const int scan_all = (sm != nullptr && sm[0] == '1') ? 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, voxel_cluster_kernel, xs, ys, ts, ps, offsets, num_bins, H, W, pad_top, pad_left, Hp, Wp,
-                                       crow, nc, vec_ok, out, out_window_stride, oob_count, scan_all);
+                                       crow, nc, vec_ok, out, out_window_stride, oob_count, scan_all, min_events);
     BDE_REQUIRE(e == cudaSuccess, "bde_voxelize_seq: cluster launch: %s", cudaGetErrorString(e));
     return check_launch("voxel_cluster_kernel");
   }
@@ -539,19 +715,14 @@ extern "C" int bde_voxelize_seq_strided(const float* xs, const float* ys, const 
     dim3 grid(bands, T);
     int vec_ok = ((((uintptr_t)xs) | ((uintptr_t)ys) | ((uintptr_t)ts) | ((uintptr_t)ps)) & 15) == 0;
     kern<<<grid, 512, smem, s>>>(xs, ys, ts, ps, offsets, num_bins, H, W, pad_top, pad_left, Hp, Wp,
-                                 band_rows, vec_ok, out, out_window_stride, oob_count);
+                                 band_rows, vec_ok, out, out_window_stride, oob_count, min_events);
     return check_launch("voxel_band_kernel");
   }
-  BDE_REQUIRE(algo == 2, "bde_voxelize_seq: unknown algo %d", algo);
-  cudaError_t e = cudaMemset2DAsync(out, out_window_stride * sizeof(float), 0, grid_elems * sizeof(float), (size_t)T, s);
-  BDE_REQUIRE(e == cudaSuccess, "bde_voxelize_seq: memset: %s", cudaGetErrorString(e));
-  // grid.x sized so the whole launch is a few waves over 148 SMs regardless of T
-  int bx = (int)ceil_div((size_t)kNumSMs * 8, (size_t)T);
-  bx = bx < 1 ? 1 : (bx > 1024 ? 1024 : bx);
-  dim3 grid(bx, T);
-  voxel_atomic_kernel<<<grid, 256, 0, s>>>(xs, ys, ts, ps, offsets, num_bins, H, W, pad_top, pad_left, Hp,
-                                           Wp, out, out_window_stride, oob_count);
-  return check_launch("voxel_atomic_kernel");
+  BDE_REQUIRE(algo == 2 || algo == 5, "bde_voxelize_seq: unknown algo %d", algo);
+  EvSrcF32 src;
+  src.x = xs; src.y = ys; src.t = ts; src.p = ps; src.t0 = 0.f;
+  return launch_atomic(src, algo == 5, offsets, T, num_bins, H, W, pad_top, pad_left, Hp, Wp, out, out_window_stride, oob_count,
+                       min_events, hot_mask, s);
 }
 
 extern "C" int bde_pack_voxel_nhwc(const float* vox, int T, int bins, int Hp, int Wp, int c_pad, void* out,

@@ -14,13 +14,15 @@ Weights are repacked once per engine (K-major [Cout, kh*kw*Cin], gate-interleave
 query scale folded into q, relative-position bias pre-gathered).
 """
 import os
+import warnings
+from collections import OrderedDict
 
 import torch
 
 from . import ops
 from .synth import relative_position_index
-from .ops import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_RELU6, ENGINE_SIMT, ENGINE_TCGEN05, EPI_LSTM, EPI_SCATTER,
-                  EPI_STORE)
+from .ops import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_RELU6, ENGINE_SIMT, ENGINE_TCGEN05, EPI_GRU_OUT, EPI_GRU_UR,
+                  EPI_LSTM, EPI_SCATTER, EPI_STORE)
 
 K_ALIGN = 64      # packed weight rows are zero-padded to a multiple of this (tcgen05 K block)
 VOX_CPAD = 8      # voxel channels padded 5 -> 8 so that a pixel is one 16-byte bf16 chunk
@@ -83,6 +85,24 @@ def _pack_linear(w, dtype, scale=1.0):
     return out.contiguous(), Kp
 
 
+def _fold_norm(conv, holder):
+    """Effective (weight, bias) of conv2d followed by the eval-mode norm_layer of a ConvLayer / UpsampleConvLayer
+    (submodules.py:100-111, 133-145): BatchNorm2d (affine, running statistics) or InstanceNorm2d(track_running_stats=True)
+    (running statistics, no affine) are per-channel affine maps  y = (x - mean) / sqrt(var + eps) * g + b."""
+    w = conv.weight.detach().float()
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0], device=w.device)
+    nl = getattr(holder, "norm_layer", None) if holder is not None else None
+    if nl is None:
+        return w, b
+    scale = 1.0 / torch.sqrt(nl.running_var.detach().float() + nl.eps)
+    if getattr(nl, "weight", None) is not None:
+        scale = scale * nl.weight.detach().float()
+    shift = -nl.running_mean.detach().float() * scale
+    if getattr(nl, "bias", None) is not None:
+        shift = shift + nl.bias.detach().float()
+    return w * scale.view(-1, 1, 1, 1), b * scale + shift
+
+
 class _Layer:
     """Packed weights of one conv / linear."""
 
@@ -116,6 +136,11 @@ class Engine:
         self.heads = cfg["num_heads"]
         self.ws = cfg["window_size"]
         self.depths = cfg["depths"]
+        self.rec = cfg.get("recurrent_block_type", "convlstm")        # 'convlstm' | 'convgru' | None (useRC=False)
+        self.concat = cfg.get("skip_type", "sum") == "concat"
+        self.nwin = cfg.get("nwindow_size")
+        self.net_act = cfg.get("net_act", ACT_RELU)
+        self.out_act = cfg.get("out_act", ops.ACT_SIGMOID)
         self.fuse_attn = os.environ.get("BDE2VID_FUSED_ATTN", "1") != "0"
         self.fuse_mlp = os.environ.get("BDE2VID_FUSED_MLP", "1") != "0"
         self.fuse_win256 = os.environ.get("BDE2VID_ATTN_WIN256", "1") != "0"
@@ -131,21 +156,39 @@ class Engine:
 
         tc = self.gemm_engine == ENGINE_TCGEN05
 
-        def conv_layer(conv, stride, cin_pad=None):
-            k = conv.weight.shape[-1]
-            cm = tc and k > 1 and conv.weight.shape[1] % 64 == 0      # chunk-major K: L1-friendly im2col order
-            w, ld = _pack_conv(conv.weight.detach().float(), dt, cin_pad, chunk_major=cm)
-            return _Layer(w, ld, f32(conv.bias), conv.weight.shape[0], k, stride, k // 2, k_order=int(cm))
+        def conv_layer(holder, stride, cin_pad=None):
+            """``holder``: a ConvLayer-like container (conv2d [+ norm_layer]) or a bare nn.Conv2d."""
+            conv = getattr(holder, "conv2d", holder)
+            wf, bf = _fold_norm(conv, holder if conv is not holder else None)
+            k = wf.shape[-1]
+            cm = tc and k > 1 and wf.shape[1] % 64 == 0      # chunk-major K: L1-friendly im2col order
+            w, ld = _pack_conv(wf, dt, cin_pad, chunk_major=cm)
+            return _Layer(w, ld, bf.contiguous(), wf.shape[0], k, stride, k // 2, k_order=int(cm))
 
-        def merged_conv_layer(conv_f, conv_b, stride):
+        def merged_conv_layer(hold_f, hold_b, stride):
             """forward + backward encoder convs read the same input (...V5.py:129-130): one GEMM with N doubled;
             output channels [0, C) = forward, [C, 2C) = backward."""
-            wcat = torch.cat([conv_f.weight.detach().float(), conv_b.weight.detach().float()], 0)
+            wf_, bf_ = _fold_norm(hold_f.conv2d, hold_f)
+            wb_, bb_ = _fold_norm(hold_b.conv2d, hold_b)
+            wcat = torch.cat([wf_, wb_], 0)
             k = wcat.shape[-1]
             cm = tc and k > 1 and wcat.shape[1] % 64 == 0
             w, ld = _pack_conv(wcat, dt, chunk_major=cm)
-            bias = torch.cat([conv_f.bias.detach().float(), conv_b.bias.detach().float()], 0).contiguous()
-            return _Layer(w, ld, bias, wcat.shape[0], k, stride, k // 2, k_order=int(cm))
+            return _Layer(w, ld, torch.cat([bf_, bb_], 0).contiguous(), wcat.shape[0], k, stride, k // 2, k_order=int(cm))
+
+        def gru_layers(blk):
+            """ConvGRU (submodules.py:337-375) as two convolutions: [update | reset] with rows interleaved n = 2c + g
+            (BDE_EPI_GRU_UR) and out_gate (BDE_EPI_GRU_OUT)."""
+            wu, wr = blk.update_gate.weight.detach().float(), blk.reset_gate.weight.detach().float()
+            hid = wu.shape[0]
+            w = torch.stack([wu, wr], 1).reshape(2 * hid, *wu.shape[1:])
+            b = torch.stack([blk.update_gate.bias.detach().float(), blk.reset_gate.bias.detach().float()], 1).reshape(-1)
+            cm = tc and hid % 64 == 0
+            pw, ld = _pack_conv(w, dt, chunk_major=cm)
+            ur = _Layer(pw, ld, b.contiguous(), 2 * hid, 3, 1, 1, k_order=int(cm))
+            po, ldo = _pack_conv(blk.out_gate.weight.detach().float(), dt, chunk_major=cm)
+            o = _Layer(po, ldo, f32(blk.out_gate.bias), hid, 3, 1, 1, k_order=int(cm))
+            return ur, o
 
         def lstm_layer(conv):
             # rows reordered so that n = 4*c + gate (gate order in, remember, out, cell: submodules.py:320)
@@ -162,23 +205,26 @@ class Engine:
             return _Layer(w, ld, f32(lin.bias * scale), lin.weight.shape[0])
 
         with torch.no_grad():
-            self.head = conv_layer(gen.head.conv2d, 1, cin_pad=VOX_CPAD)
+            self.head = conv_layer(gen.head, 1, cin_pad=VOX_CPAD)
             # dedicated first-layer kernel (planar fp32 voxels -> NHWC bf16, no packing pass): 32 channels, 5x5
-            hw = gen.head.conv2d.weight
+            hw, hb_ = _fold_norm(gen.head.conv2d, gen.head)
             self.head_direct = None
-            if (tc and hw.shape[0] == 32 and hw.shape[-1] == 5 and hw.shape[1] <= 6
+            if (tc and hw.shape[0] == 32 and hw.shape[-1] == 5 and hw.shape[1] <= 6 and self.net_act in (ACT_RELU, ACT_RELU6)
                     and os.environ.get("BDE2VID_HEAD_CONV", "1") != "0"):
-                self.head_direct = (f32(hw), f32(gen.head.conv2d.bias))
+                self.head_direct = (hw.contiguous(), hb_.contiguous())
             self.enc = []
             for l in range(self.L):
-                self.enc.append(dict(
-                    f_conv=conv_layer(gen.forward_encoder[l].conv.conv2d, 2),
-                    b_conv=conv_layer(gen.backward_encoder[l].conv.conv2d, 2),
-                    f_lstm=lstm_layer(gen.forward_encoder[l].recurrent_block.Gates),
-                    b_lstm=lstm_layer(gen.backward_encoder[l].recurrent_block.Gates)))
-                if tc and os.environ.get("BDE2VID_MERGE_ENC", "1") != "0":
-                    self.enc[-1]["fb_conv"] = merged_conv_layer(gen.forward_encoder[l].conv.conv2d,
-                                                                gen.backward_encoder[l].conv.conv2d, 2)
+                fe, be = gen.forward_encoder[l], gen.backward_encoder[l]
+                fc, bcv = (fe.conv, be.conv) if self.rec is not None else (fe, be)
+                e = dict(f_conv=conv_layer(fc, 2), b_conv=conv_layer(bcv, 2))
+                if self.rec == "convlstm":
+                    e.update(f_lstm=lstm_layer(fe.recurrent_block.Gates), b_lstm=lstm_layer(be.recurrent_block.Gates))
+                elif self.rec == "convgru":
+                    e.update(f_gru=gru_layers(fe.recurrent_block), b_gru=gru_layers(be.recurrent_block))
+                # the merged form feeds the chains through pitched TMA descriptors: recurrent encoders only
+                if tc and self.rec is not None and os.environ.get("BDE2VID_MERGE_ENC", "1") != "0":
+                    e["fb_conv"] = merged_conv_layer(fc, bcv, 2)
+                self.enc.append(e)
             self.attn = []
             n_tok = self.ws[0] * self.ws[1]
             for l in range(self.L):
@@ -186,18 +232,21 @@ class Engine:
                 if self.depths[l] > 0:
                     C = self.bc * 2 ** (l + 1)
                     hd = C // self.heads
+                    # kv tokens per frame: the window's tokens, or nwin0 * nwin1 after the reduction conv (DTransformer.py:172-175)
+                    n_kvf = n_tok if self.nwin is None else self.nwin[0] * self.nwin[1]
                     for blk in gen.feat_attns[l].blocks:
                         a = blk.attn
-                        idx = a.relative_position_index[self.q_ind * n_tok:(self.q_ind + 1) * n_tok, :self.D * n_tok]
+                        # (DTransformer.py:195-197: only the first N = D * n_kvf columns of the index are used)
+                        idx = a.relative_position_index[self.q_ind * n_tok:(self.q_ind + 1) * n_tok, :self.D * n_kvf]
                         bias = a.relative_position_bias_table.detach().float()[idx.reshape(-1)]
-                        bias_hmn = bias.reshape(n_tok, self.D * n_tok, self.heads).permute(2, 0, 1).contiguous()
+                        bias_hmn = bias.reshape(n_tok, self.D * n_kvf, self.heads).permute(2, 0, 1).contiguous()
                         bias = bias_hmn.permute(0, 2, 1).contiguous()
-                        use_mma = (dt == torch.bfloat16 and n_tok <= 64 and hd in (4, 8, 16) and self.heads % 2 == 0
-                                   and ops.attention_mma_bias_stride(self.D * n_tok) > 0)
+                        use_mma = (self.nwin is None and dt == torch.bfloat16 and n_tok <= 64 and hd in (4, 8, 16)
+                                   and self.heads % 2 == 0 and ops.attention_mma_bias_stride(self.D * n_tok) > 0)
                         # fused front end (tcgen05 only): LayerNorm folded into the projections.
                         #   Linear(LN(x)) = (W diag(gamma)) xhat + (W beta + b),  xhat = (x - mean) / sqrt(var + eps)
                         # q and kv share xhat, so ONE GEMM with N = 3C produces [q | k | v] for every kv token.
-                        fused = tc and use_mma and C in (64, 128, 256)
+                        fused = tc and use_mma and C in (64, 128, 256) and self.nwin is None
                         qkv_l = fc1_l = kv_l = None
                         if fused:
                             sc = hd ** -0.5
@@ -226,8 +275,12 @@ class Engine:
                             tab = a.relative_position_bias_table.detach().float()
                             rows = [tab[((self.q_ind - d) + self.D - 1) * rel:((self.q_ind - d) + self.D) * rel] for d in range(self.D)]
                             tbl = torch.stack(rows, 0).permute(2, 0, 1).contiguous()       # [heads, D, 169]
+                        red = None
+                        if self.nwin is not None:
+                            rc = a.reduction_conv
+                            red = (f32(rc.weight.reshape(rc.weight.shape[0], -1)), f32(rc.bias), n_kvf)
                         blocks.append(dict(
-                            qkv=qkv_l, kv_l=kv_l, fc1_ln=fc1_l, tbl=tbl,
+                            qkv=qkv_l, kv_l=kv_l, fc1_ln=fc1_l, tbl=tbl, red=red,
                             bias_mma=ops.pad_bias_for_mma(bias_hmn, self.D * n_tok) if use_mma else None,
                             nq_g=f32(a.norm_q.weight), nq_b=f32(a.norm_q.bias),
                             nkv_g=f32(a.norm_kv.weight), nkv_b=f32(a.norm_kv.bias),
@@ -241,10 +294,27 @@ class Engine:
                     w_all = torch.cat([b["kv_l"].w for b in blocks], 0).contiguous()
                     b_all = torch.cat([b["kv_l"].bias for b in blocks], 0).contiguous()
                     blocks[0]["kv_all"] = _Layer(w_all, blocks[0]["kv_l"].w_ld, b_all, w_all.shape[0])
-            self.dec = [conv_layer(gen.decoders[i][1].conv2d, 1) for i in range(self.L)]
-            self.pred_w = f32(gen.predI[1].weight.reshape(-1))
-            self.pred_b = f32(gen.predI[1].bias)
-        self.plans = {}
+            # last level with depth 0: ParseLayer + ResidualBlockNoBN x n (...V5.py:77-80, 261-282)
+            self.tail = None
+            if self.depths[-1] == 0:
+                self.tail = [(conv_layer(rb.conv1, 1), conv_layer(rb.conv2, 1)) for rb in list(gen.feat_attns[-1])[1:]]
+            self.dec = [conv_layer(gen.decoders[i][1], 1) for i in range(self.L)]
+            # skip_type 'concat': 1x1 fusion convolution over cat[skip, x] in front of every decoder (...V5.py:86-93)
+            self.dec_fus = [conv_layer(gen.decoders[i][0], 1) for i in range(self.L)] if self.concat else None
+            pw, pb = gen.predI[1].weight.detach().float().reshape(-1), gen.predI[1].bias.detach().float()
+            if self.concat:
+                # predI = conv1x1(2bc -> bc) then conv1x1(bc -> 1) with nothing in between: one [2bc] vector
+                W1 = gen.predI[0].weight.detach().float().reshape(self.bc, 2 * self.bc)
+                b1 = gen.predI[0].bias.detach().float()
+                w_eff = pw @ W1
+                self.pred_w, self.pred_wh = w_eff[:self.bc].contiguous(), w_eff[self.bc:].contiguous()
+                self.pred_b = (pw @ b1 + pb).reshape(1).contiguous()
+            else:
+                self.pred_w, self.pred_wh, self.pred_b = pw.contiguous(), None, pb.contiguous()
+        # plans (buffers + CUDA graph per (T, B, Hp, Wp, slot)) are kept in an LRU bounded in bytes: the reference driver
+        # with subseq_L=None calls the model with a different T per file (eval_models_seq.py:216-221)
+        self.plans = OrderedDict()
+        self.plan_cache_bytes = int(float(os.environ.get("BDE2VID_PLAN_CACHE_GB", "64")) * 2 ** 30)
         self.dec_chunk = 8
 
     # ------------------------------------------------------------------------------------
@@ -261,6 +331,15 @@ class Engine:
         if p is None:
             p = _Plan(self, T, B, Hp, Wp)
             self.plans[key] = p
+            # evict least-recently-used plans (never the one just built) until the cache fits its byte budget
+            total = sum(q.nbytes for q in self.plans.values())
+            for k in list(self.plans.keys()):
+                if total <= self.plan_cache_bytes or k == key:
+                    break
+                total -= self.plans[k].nbytes
+                self.plans.pop(k).release()
+        else:
+            self.plans.move_to_end(key)
         return p
 
     def forward(self, vox_list, use_graph=True, slot=0):
@@ -284,21 +363,23 @@ class Engine:
         img = p.img.clone().view(T, B, 1, Hp, Wp)
         return list(img.unbind(0))
 
-    def forward_events(self, xs, ys, ts, ps, offsets, H, W, crop, use_graph=True, slot=0):
+    def forward_events(self, xs, ys, ts, ps, offsets, H, W, crop, use_graph=True, slot=0, normalize=None, hot_mask=None):
         """Fused path: raw events -> frames (voxeliser writes the padded grids the UNet reads)."""
-        return self.forward_events_batch([(xs, ys, ts, ps, offsets)], H, W, crop, use_graph, slot)[0]
+        return self.forward_events_batch([(xs, ys, ts, ps, offsets)], H, W, crop, use_graph, slot, normalize, hot_mask)[0]
 
-    def forward_events_batch(self, seqs, H, W, crop, use_graph=True, slot=0):
+    def forward_events_batch(self, seqs, H, W, crop, use_graph=True, slot=0, normalize=None, hot_mask=None):
         """B independent sequences (each a tuple xs, ys, ts, ps, offsets with the same number of windows)
         processed as one batch: every kernel of the schedule runs once for all B sequences.  Returns a list
-        (per sequence) of T frames [1, 1, Hp, Wp]."""
+        (per sequence) of T frames [1, 1, Hp, Wp].  Event arrays: loader format (four float32 arrays) or the on-disk
+        dtypes (int16 x / y, float64 t, bool p).  ``normalize``: None | 'legacy' | 'robust' | ('robust', low, top)
+        (the loader's LegacyNorm / RobustNorm voxel transforms); ``hot_mask``: optional float32 [H, W] hot-pixel mask."""
         B = len(seqs)
         T = seqs[0][4].numel() - 1
         if any(s[4].numel() - 1 != T for s in seqs):
             raise ValueError("sequences batched together must have the same number of windows")
         Hp, Wp = crop.height_crop_size, crop.width_crop_size
         p = self.plan(T, B, Hp, Wp, slot)
-        p.set_events(seqs, H, W, crop.padding_top, crop.padding_left)
+        p.set_events(seqs, H, W, crop.padding_top, crop.padding_left, normalize, hot_mask)
         p.run(use_graph, from_events=True)
         img = p.img.clone().view(T, B, 1, 1, Hp, Wp)
         return [list(img[:, b].unbind(0)) for b in range(B)]
@@ -311,26 +392,38 @@ class _Plan:
         self.eng, self.T, self.B, self.Hp, self.Wp = eng, T, B, Hp, Wp
         dev, dt = eng.device, eng.dtype
         f32 = torch.float32
-        E = lambda *s, dtype=dt: torch.empty(*s, dtype=dtype, device=dev)  # noqa: E731
+        self.nbytes = 0
+
+        def E(*s, dtype=dt, zero=False):
+            t = (torch.zeros if zero else torch.empty)(*s, dtype=dtype, device=dev)
+            self.nbytes += t.numel() * t.element_size()
+            return t
+
         N = T * B
         self.vox_in = E(T, B, eng.bins, Hp, Wp, dtype=f32)
-        self.vox8 = E(N, Hp, Wp, VOX_CPAD)
+        self.vox8 = E(N, Hp, Wp, VOX_CPAD) if eng.head_direct is None else None
         self.head = E(N, Hp, Wp, eng.bc)
         self.img = E(N, Hp, Wp, dtype=f32)
         self.lv = []
+        mlp_fused = eng.fuse_mlp
         for l in range(eng.L):
             h, w, C = Hp >> (l + 1), Wp >> (l + 1), eng.bc * 2 ** (l + 1)
-            # merged forward / backward encoder conv: the ConvLSTM chains then read channel halves of one [.., 2C] map,
+            # merged forward / backward encoder conv: the recurrent chains then read channel halves of one [.., 2C] map,
             # which only the TMA conv kernel can do (it needs C % 64 == 0 and a map of at least 8 x 8)
             merged = ("fb_conv" in eng.enc[l] and C % 64 == 0 and h >= 8 and w >= 8
                       and os.environ.get("BDE2VID_CONV_TMA", "1") != "0")
             efb = E(N, h, w, 2 * C) if merged else None      # [.., :C] forward encoder conv, [.., C:] backward
             d = dict(h=h, w=w, C=C, efb=efb,
                      ef=None if merged else E(N, h, w, C), eb=None if merged else E(N, h, w, C),
-                     hf=E(N, h, w, C), hb=E(N, h, w, C),
-                     cf=[E(B, h, w, C, dtype=f32) for _ in range(2)], cb=[E(B, h, w, C, dtype=f32) for _ in range(2)],
-                     zero=torch.zeros(B, h, w, C, dtype=dt, device=dev),
                      feat=E(N, h, w, C, dtype=f32))
+            if eng.rec is not None:
+                # hf / hb: hidden state of every frame (the chains' output); cf / cb: fp32 ping-pong of the ConvLSTM cell
+                # state, or of the ConvGRU hidden state's fp32 master copy
+                d.update(hf=E(N, h, w, C), hb=E(N, h, w, C),
+                         cf=[E(B, h, w, C, dtype=f32) for _ in range(2)], cb=[E(B, h, w, C, dtype=f32) for _ in range(2)],
+                         zero=E(B, h, w, C, zero=True))
+            if eng.rec == "convgru":
+                d.update(uf=E(B, h, w, C, dtype=f32), ub=E(B, h, w, C, dtype=f32), hrf=E(B, h, w, C), hrb=E(B, h, w, C))
             d["feat_t"] = d["feat"] if dt == f32 else E(N, h, w, C)
             if eng.depths[l] > 0:
                 ws = eng.ws
@@ -343,12 +436,19 @@ class _Plan:
                 nwin = tm_plain.shape[0]
                 ntok = ws[0] * ws[1]
                 P = B * h * w
-                d.update(tm=[tm_plain, tm_dil], nwin=nwin, ntok=ntok,
-                         xs=E(P, C, dtype=f32), qn=E(nwin * ntok, C), kvn=E(nwin * eng.D * ntok, C),
-                         qb=E(nwin * ntok, C), kvb=E(nwin * eng.D * ntok, 2 * C), ob=E(nwin * ntok, C),
-                         qkv=E(nwin * eng.D * ntok, 3 * C),
-                         yn=E(P, C), hid=E(P, 4 * C))
                 blocks = eng.attn[l]
+                d.update(tm=[tm_plain, tm_dil], nwin=nwin, ntok=ntok, xs=E(P, C, dtype=f32), ob=E(nwin * ntok, C))
+                # scratch of the unfused forms, only where a block takes them
+                if any(b["tbl"] is None and b["qkv"] is not None for b in blocks):
+                    d["qkv"] = E(nwin * eng.D * ntok, 3 * C)
+                if any(b["qkv"] is None for b in blocks):
+                    n_kvf = ntok if eng.nwin is None else eng.nwin[0] * eng.nwin[1]
+                    d.update(qn=E(nwin * ntok, C), kvn=E(nwin * eng.D * n_kvf, C), qb=E(nwin * ntok, C),
+                             kvb=E(nwin * eng.D * n_kvf, 2 * C))
+                    if eng.nwin is not None:
+                        d["kvr"] = E(nwin * eng.D * n_kvf, C, dtype=f32)
+                if not (mlp_fused and ops.mlp_fused_supported(C, 4 * C) and all(b["fc1_ln"] is not None for b in blocks)):
+                    d.update(yn=E(P, C), hid=E(P, 4 * C))
                 if (C == 256 and eng.fuse_win256 and eng.kv_pre and nwin >= 64 and list(eng.buf) == [-1, 0, 1]
                         and eng.q_ind == 1 and blocks and "kv_all" in blocks[0]
                         and all(b["tbl"] is not None for b in blocks)):
@@ -358,6 +458,12 @@ class _Plan:
                     d["xn_all"] = E(T * P, C)          # LayerNorm'ed (no affine: folded into the weights) features, bf16
                     d["ln_one"] = torch.ones(C, dtype=f32, device=dev)
                     d["ln_zero"] = torch.zeros(C, dtype=f32, device=dev)
+            elif l == eng.L - 1 and eng.tail is not None:
+                P = B * h * w
+                # ResidualBlockNoBN tail: running x (fp32 + operand copy) and the conv1 output
+                d.update(tl_x=E(B, h, w, C, dtype=f32), tl_xb=E(B, h, w, C), tl_y=E(B, h, w, C),
+                         tl_zero=E(B, h, w, C, dtype=f32, zero=True))
+                d["tl_zerob"] = d["tl_zero"] if dt == f32 else E(B, h, w, C, zero=True)
             self.lv.append(d)
         Tc = min(eng.dec_chunk, T)
         self.Tc = Tc
@@ -365,79 +471,156 @@ class _Plan:
         for i in range(eng.L):
             l_in = eng.L - 1 - i                     # level whose resolution the decoder input has
             h, w, C = self.lv[l_in]["h"], self.lv[l_in]["w"], self.lv[l_in]["C"]
-            self.dec.append(dict(h=h, w=w, C=C, up=E(Tc * B, 2 * h, 2 * w, C), out=E(Tc * B, 2 * h, 2 * w, C // 2)))
+            dd = dict(h=h, w=w, C=C, up=E(Tc * B, 2 * h, 2 * w, C), out=E(Tc * B, 2 * h, 2 * w, C // 2))
+            if eng.concat:
+                dd["fus"] = E(Tc * B, h, w, C)
+            self.dec.append(dd)
         self.graphs = {}
         self.runs = {}
         self.ev = None
+        self.ev_kind = None
+        self.norm = (0, 0.0, 95.0)      # voxel normalisation of the fused events path: (mode, low_perc, top_perc)
+        self.hot_mask = None
+        self.oob = E(1, dtype=torch.int32, zero=True)
+        self.oob_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.oob_event = None
         self.side = torch.cuda.Stream(device=dev)
         # two-stream schedule (backward chain / decoders on `side`); False serialises everything on one stream
         self.overlap = os.environ.get("BDE2VID_OVERLAP", "1") != "0"
 
+    def release(self):
+        """Drop the CUDA graph and every buffer (LRU eviction)."""
+        self.graphs.clear()
+        self.lv, self.dec, self.ev = [], [], None
+        self.vox_in = self.vox8 = self.head = self.img = None
+
     # ------------------------------------------------------------------------------------
-    def set_events(self, seqs, H, W, pad_top, pad_left):
+    def check_oob(self):
+        """Events outside the sensor are dropped by the fused path (the reference's index_put_ raises IndexError).  The
+        count of the previous run is copied to pinned host memory asynchronously and examined here, at the next call:
+        BDE2VID_STRICT_OOB=1 waits for it and raises like the reference, otherwise a finished count != 0 warns."""
+        if self.oob_event is None:
+            return
+        strict = os.environ.get("BDE2VID_STRICT_OOB", "0") == "1"
+        if strict:
+            self.oob_event.synchronize()
+        if self.oob_event.query():
+            n = int(self.oob_host.item())
+            self.oob_event = None
+            if n:
+                msg = "%d events outside the sensor were dropped by the fused voxeliser" % n
+                if strict:
+                    raise IndexError(msg)
+                warnings.warn(msg)
+
+    def set_events(self, seqs, H, W, pad_top, pad_left, normalize=None, hot_mask=None):
         """Stage the events of the B sequences into static buffers (host or device sources; the copies are
-        asynchronous on the current stream) so that the captured graph can include the voxeliser."""
+        asynchronous on the current stream) so that the captured graph can include the voxeliser.  Event arrays are
+        either the loader format (four float32 arrays) or the on-disk dtypes (int16, int16, float64, bool / uint8)."""
         assert len(seqs) == self.B
+        self.check_oob()
         n = max(s[0].numel() for s in seqs)
         dev = self.eng.device
         geom = (H, W, pad_top, pad_left)
-        if self.ev is None or self.ev_cap < n or self.ev_geom != geom:
+        raw = seqs[0][0].dtype != torch.float32
+        dts = (torch.int16, torch.int16, torch.float64, torch.uint8) if raw else (torch.float32,) * 4
+        norm = (0, 0.0, 95.0)
+        if normalize is not None:
+            mode = {"legacy": ops.NORM_LEGACY, "LegacyNorm": ops.NORM_LEGACY, "robust": ops.NORM_ROBUST,
+                    "RobustNorm": ops.NORM_ROBUST}[normalize if isinstance(normalize, str) else normalize[0]]
+            lo, hi = (0.0, 95.0) if isinstance(normalize, str) else (float(normalize[1]), float(normalize[2]))
+            norm = (mode, lo, hi)
+        if (self.ev is None or self.ev_cap < n or self.ev_geom != geom or self.ev_kind != raw or self.norm != norm
+                or (hot_mask is None) != (self.hot_mask is None)):
             self.ev_cap = max(int(n * 1.25) + 16, 1024)
-            self.ev = [[torch.zeros(self.ev_cap, dtype=torch.float32, device=dev) for _ in range(4)]
-                       for _ in range(self.B)]
+            self.ev = [[torch.zeros(self.ev_cap, dtype=d, device=dev) for d in dts] for _ in range(self.B)]
             self.ev_off = [torch.zeros(self.T + 1, dtype=torch.int64, device=dev) for _ in range(self.B)]
-            self.oob = torch.zeros(1, dtype=torch.int32, device=dev)
-            self.ev_geom = geom
+            self.ev_geom, self.ev_kind, self.norm = geom, raw, norm
+            self.hot_mask = None if hot_mask is None else torch.empty(H, W, dtype=torch.float32, device=dev)
             self.graphs.pop(True, None)
             self.runs[True] = 0
+        if hot_mask is not None:
+            self.hot_mask.copy_(hot_mask, non_blocking=True)
         for b, (xs, ys, ts, ps, offsets) in enumerate(seqs):
             m = xs.numel()
             for dst, src in zip(self.ev[b], (xs, ys, ts, ps)):
-                dst[:m].copy_(src, non_blocking=True)
+                dst[:m].copy_(src.view(torch.uint8) if src.dtype == torch.bool else src, non_blocking=True)
             self.ev_off[b].copy_(offsets, non_blocking=True)
 
     def run(self, use_graph, from_events):
         self.runs[from_events] = self.runs.get(from_events, 0) + 1
         if not use_graph:
             self._enqueue(from_events)
-            return
-        if from_events not in self.graphs and self.runs[from_events] >= 2:
-            g = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize()
-            with torch.cuda.graph(g):
-                self._enqueue(from_events)
-            self.graphs[from_events] = g
-        if from_events in self.graphs:
-            self.graphs[from_events].replay()
         else:
-            self._enqueue(from_events)
+            if from_events not in self.graphs and self.runs[from_events] >= 2:
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    self._enqueue(from_events)
+                self.graphs[from_events] = g
+            if from_events in self.graphs:
+                self.graphs[from_events].replay()
+            else:
+                self._enqueue(from_events)
+        if from_events:
+            self.oob_host.copy_(self.oob, non_blocking=True)
+            self.oob_event = torch.cuda.Event()
+            self.oob_event.record()
 
     # ------------------------------------------------------------------------------------
+    def _chain_step(self, d, layer_key, e, xin, pitch, hbuf, cbuf, t, tprev, k, rev):
+        """One recurrent step of one direction: ConvLSTM (gates conv + pointwise update in one launch) or ConvGRU (two
+        launches: [update | reset] conv -> u, h * r;  out_gate conv -> h')."""
+        eng, B = self.eng, self.B
+        h, w, C = d["h"], d["w"], d["C"]
+        first = k == 0
+        hprev = d["zero"] if first else hbuf[tprev * B:(tprev + 1) * B]
+        if eng.rec == "convlstm":
+            eng._gemm(e[layer_key + "_lstm"], xin, hbuf[t * B:(t + 1) * B], B, h, w, C, a1=hprev, c1=C, epi=EPI_LSTM,
+                      c_prev=None if first else cbuf[(k + 1) & 1], c_out=cbuf[k & 1], **pitch)
+            self.launches += 1
+            return
+        ur, og = e[layer_key + "_gru"]
+        u, hr = (d["ub"], d["hrb"]) if rev else (d["uf"], d["hrf"])
+        hm_prev = None if first else cbuf[(k + 1) & 1]
+        eng._gemm(ur, xin, hr, B, h, w, C, a1=hprev, c1=C, epi=EPI_GRU_UR, c_prev=hm_prev, c_out=u, **pitch)
+        eng._gemm(og, xin, hbuf[t * B:(t + 1) * B], B, h, w, C, a1=hr, c1=C, epi=EPI_GRU_OUT, c_prev=hm_prev, residual=u,
+                  c_out=cbuf[k & 1], **pitch)
+        self.launches += 2
+
     def _enqueue(self, from_events):
         eng, T, B, Hp, Wp = self.eng, self.T, self.B, self.Hp, self.Wp
         N = T * B
         self.launches = 0
         if from_events:
             H, W, pt, pl = self.ev_geom
-            # sequence b writes windows t = 0..T-1 at vox_in[t, b]: window stride = B grids
+            self.oob.zero_()
+            # sequence b writes windows t = 0..T-1 at vox_in[t, b]: window stride = B grids.  min_events = 3 is the loader
+            # contract (h5_dataset.py:219-221): windows with fewer than 3 events give an all-zero grid
             for b in range(B):
                 xs, ys, ts, ps = self.ev[b]
                 ops.voxelize_seq_into(xs, ys, ts, ps, self.ev_off[b], eng.bins, H, W, pt, pl, Hp, Wp,
-                                      self.vox_in[0, b], B * eng.bins * Hp * Wp, oob_count=self.oob)
+                                      self.vox_in[0, b], B * eng.bins * Hp * Wp, oob_count=self.oob, min_events=3,
+                                      hot_mask=self.hot_mask)
                 self.launches += 1
-        # A: head conv + ReLU over all frames (...V5.py:116)
+            if self.norm[0]:
+                # LegacyNorm / RobustNorm of the loader (transform_voxel, h5_dataset.py:226), per window, in place
+                ops.voxel_normalize(self.vox_in, H, W, pt, pl, self.norm[0], self.norm[1], self.norm[2],
+                                    window_stride=eng.bins * Hp * Wp, n_windows=N)
+                self.launches += 1
+        # A: head conv + activation over all frames (...V5.py:116)
         if eng.head_direct is not None:
-            ops.head_conv(self.vox_in.view(N, eng.bins, Hp, Wp), eng.head_direct[0], eng.head_direct[1], self.head, act=ACT_RELU)
+            ops.head_conv(self.vox_in.view(N, eng.bins, Hp, Wp), eng.head_direct[0], eng.head_direct[1], self.head, act=eng.net_act)
             self.launches += 1
         else:
             ops.pack_voxel_nhwc(self.vox_in.view(N, eng.bins, Hp, Wp), VOX_CPAD, eng.dtype, out=self.vox8)
-            eng._gemm(eng.head, self.vox8, self.head, N, Hp, Wp, VOX_CPAD, act=ACT_RELU)
+            eng._gemm(eng.head, self.vox8, self.head, N, Hp, Wp, VOX_CPAD, act=eng.net_act)
             self.launches += 2
         x, xc, xh, xw = self.head, eng.bc, Hp, Wp
         for l in range(eng.L):
             d, e = self.lv[l], eng.enc[l]
             h, w, C = d["h"], d["w"], d["C"]
-            # the two ConvLSTM chains (sequential in t; gates conv + pointwise fused in one kernel) are independent
+            # the two recurrent chains (sequential in t; gates conv + pointwise fused in one kernel) are independent
             # of each other: the backward direction (conv + chain) runs on a second stream
             main = torch.cuda.current_stream()
             side = self.side if self.overlap else main
@@ -445,41 +628,69 @@ class _Plan:
             if merged:
                 # both directions' encoder convs in one launch over all T (same input, N doubled); each chain then reads
                 # its channel half of the [.., 2C] map through a pitched TMA descriptor
-                eng._gemm(e["fb_conv"], x, d["efb"], N, xh, xw, xc, act=ACT_RELU)
+                eng._gemm(e["fb_conv"], x, d["efb"], N, xh, xw, xc, act=eng.net_act)
                 self.launches += 1
             side.wait_stream(main)
-            for (strm, conv, src, hbuf, cbuf, layer, rev) in (
-                    (main, e["f_conv"], d["ef"], d["hf"], d["cf"], e["f_lstm"], False),
-                    (side, e["b_conv"], d["eb"], d["hb"], d["cb"], e["b_lstm"], True)):
+            for (strm, key, conv, src, rev) in ((main, "f", e["f_conv"], d["ef"], False), (side, "b", e["b_conv"], d["eb"], True)):
                 with torch.cuda.stream(strm):
                     if not merged:
                         # encoder conv is not recurrent: one launch over all T (...V5.py:129-130, conv part)
-                        eng._gemm(conv, x, src, N, xh, xw, xc, act=ACT_RELU)
+                        eng._gemm(conv, x, src, N, xh, xw, xc, act=eng.net_act)
                         self.launches += 1
+                    if eng.rec is None:
+                        continue                  # useRC=False: the encoder is the ConvLayer alone (...V5.py:255-257)
+                    hbuf, cbuf = (d["hb"], d["cb"]) if rev else (d["hf"], d["cf"])
                     for k in range(T):
                         t, tprev = (T - 1 - k, T - k) if rev else (k, k - 1)
-                        first = k == 0
                         if merged:
                             xin = d["efb"][t * B:(t + 1) * B, :, :, (C if rev else 0):(2 * C if rev else C)]
                             pitch = dict(a0_ld=2 * C)
                         else:
                             xin, pitch = src[t * B:(t + 1) * B], {}
-                        eng._gemm(layer, xin, hbuf[t * B:(t + 1) * B], B, h, w, C,
-                                  a1=d["zero"] if first else hbuf[tprev * B:(tprev + 1) * B], c1=C,
-                                  epi=EPI_LSTM, c_prev=None if first else cbuf[(k + 1) & 1], c_out=cbuf[k & 1], **pitch)
-                    self.launches += T
+                        self._chain_step(d, key, e, xin, pitch, hbuf, cbuf, t, tprev, k, rev)
             main.wait_stream(side)
             # merged = ff + fb (...V5.py:137-147)
-            ops.add(d["hf"], d["hb"], out_f32=d["feat"], out_t=None if eng.dtype == torch.float32 else d["feat_t"],
-                    dtype=eng.dtype)
+            ff, fb = (d["ef"], d["eb"]) if eng.rec is None else (d["hf"], d["hb"])
+            ops.add(ff, fb, out_f32=d["feat"], out_t=None if eng.dtype == torch.float32 else d["feat_t"], dtype=eng.dtype)
             self.launches += 1
+            last = l == eng.L - 1
             if eng.depths[l] > 0:
                 # the last level's frames are final as soon as their attention step is done: the decoders of a
                 # finished chunk of frames run on the side stream while the (latency-bound) chain continues
-                self._attention_level(l, self._decode_chunk_async if l == eng.L - 1 else None)
+                self._attention_level(l, self._decode_chunk_async if last else None)
+            elif last and eng.tail is not None:
+                self._tail_level(l, self._decode_chunk_async)
             x, xc, xh, xw = d["feat_t"], C, h, w
         if self.overlap:
             torch.cuda.current_stream().wait_stream(self.side)
+
+    def _tail_level(self, l, on_frame_done):
+        """Last level with depth 0 (...V5.py:77-80, 151-169, 261-282): per frame, in order, x = feats_buffer[0] (ParseLayer:
+        the frame at offset buffer_index[0], all-zero outside the sequence, already updated if it is a past frame --
+        quirk Q5 with Q1 / Q4), then num_res_blocks x (x = x + conv2(act(conv1(x)))), then merged[t] = x + merged[t]."""
+        eng, T, B = self.eng, self.T, self.B
+        d = self.lv[l]
+        h, w, C = d["h"], d["w"], d["C"]
+        P = B * h * w
+        feat = d["feat"].view(T, P * C)
+        feat_t = d["feat_t"].view(T, P * C)
+        lowp = eng.dtype != torch.float32
+        for t in range(T):
+            src_t = t + eng.buf[0]
+            if 0 <= src_t < T:
+                x32, xop = feat[src_t].view(B, h, w, C), feat_t[src_t].view(B, h, w, C)
+            else:
+                x32, xop = d["tl_zero"], d["tl_zerob"]
+            for (c1, c2) in eng.tail:
+                eng._gemm(c1, xop, d["tl_y"], B, h, w, C, act=eng.net_act)
+                # conv2 + bias + residual (fp32, after the absent activation): x = x + conv2(.)
+                eng._gemm(c2, d["tl_y"], d["tl_x"], B, h, w, C, out_f32=True, residual=x32,
+                          out2=d["tl_xb"] if lowp else None)
+                x32, xop = d["tl_x"], d["tl_xb"] if lowp else d["tl_x"]
+                self.launches += 2
+            ops.add(x32.view(-1), feat[t], out_f32=feat[t], out_t=feat_t[t] if lowp else None, dtype=eng.dtype)
+            self.launches += 1
+            on_frame_done(t)
 
     def _decode_chunk_async(self, t):
         """Called after frame t of the last level is final; launches the decoder of a completed chunk."""
@@ -503,15 +714,25 @@ class _Plan:
         for i in range(eng.L):
             dd = self.dec[i]
             l_in = eng.L - 1 - i
-            feat = self.lv[l_in]["feat"][s]
-            if i == 0:    # quirk Q2: the last level is appended twice -> decoder 0 sees feat + feat
-                ops.upsample2x_sum(None, feat, 2.0, n, dd["h"], dd["w"], dd["C"], dd["up"][:n])
+            if eng.concat:
+                # skip_concat: fusion conv1x1 over cat[skip, x] (two GEMM sources), then bilinear x2 + conv (...V5.py:86-93).
+                # Quirk Q2: decoder 0 sees cat[feat, feat]
+                skip = self.lv[l_in]["feat_t"][s]
+                xin = skip if i == 0 else cur
+                eng._gemm(eng.dec_fus[i], skip, dd["fus"][:n], n, dd["h"], dd["w"], dd["C"], a1=xin, c1=dd["C"])
+                ops.upsample2x_sum(None, dd["fus"][:n], 1.0, n, dd["h"], dd["w"], dd["C"], dd["up"][:n])
+                self.launches += 1
             else:
-                ops.upsample2x_sum(feat, cur, 1.0, n, dd["h"], dd["w"], dd["C"], dd["up"][:n])
+                feat = self.lv[l_in]["feat"][s]
+                if i == 0:    # quirk Q2: the last level is appended twice -> decoder 0 sees feat + feat
+                    ops.upsample2x_sum(None, feat, 2.0, n, dd["h"], dd["w"], dd["C"], dd["up"][:n])
+                else:
+                    ops.upsample2x_sum(feat, cur, 1.0, n, dd["h"], dd["w"], dd["C"], dd["up"][:n])
             eng._gemm(eng.dec[i], dd["up"][:n], dd["out"][:n], n, 2 * dd["h"], 2 * dd["w"], dd["C"], act=ACT_RELU6)
             cur = dd["out"][:n]
             self.launches += 2
-        ops.pred_sigmoid(cur, self.head[s], eng.pred_w, eng.pred_b, eng.bc, n * Hp * Wp, self.img[s])
+        ops.pred_sigmoid(cur, self.head[s], eng.pred_w, eng.pred_b, eng.bc, n * Hp * Wp, self.img[s], wt_head=eng.pred_wh,
+                         act=eng.out_act)
         self.launches += 1
 
     def _mlp(self, blk, d, xs, P, C, sum_io=None, sum_t=None):
@@ -608,20 +829,29 @@ class _Plan:
                     sum_done = self._mlp(blk, d, xs, P, C, *sum_args)
                     self.launches += 3
                     continue
-                if C in (64, 128, 256):
+                n_kvf = ntok
+                if blk["red"] is not None:
+                    # nwindow_size (DTransformer.py:172-175): q from the window's tokens, kv from the "feature reduction"
+                    # conv of every frame's window (raw tokens), then norm_kv
+                    rw, rb, n_kvf = blk["red"]
+                    ops.ln_gather([fr[eng.q_ind]], tm, nwin, ntok, C, blk["nq_g"], blk["nq_b"], d["qn"])
+                    ops.window_reduce(fr, tm.view(-1), nwin, ntok, C, n_kvf, rw, rb, d["kvr"])
+                    ops.layernorm(d["kvr"], nwin * D * n_kvf, C, blk["nkv_g"], blk["nkv_b"], d["kvn"])
+                    self.launches += 1
+                elif C in (64, 128, 256):
                     ops.ln_gather_qkv(fr, eng.q_ind, tm, nwin, ntok, C, blk["nkv_g"], blk["nkv_b"], blk["nq_g"],
                                       blk["nq_b"], d["kvn"], d["qn"])
                     self.launches -= 1
                 else:
-                    ops.ln_gather([xs], tm, nwin, ntok, C, blk["nq_g"], blk["nq_b"], d["qn"])
+                    ops.ln_gather([fr[eng.q_ind]], tm, nwin, ntok, C, blk["nq_g"], blk["nq_b"], d["qn"])
                     ops.ln_gather(fr, tm, nwin, ntok, C, blk["nkv_g"], blk["nkv_b"], d["kvn"])
                 eng._gemm(blk["q"], d["qn"], d["qb"], 1, nwin * ntok, 1, C)
-                eng._gemm(blk["kv"], d["kvn"], d["kvb"], 1, nwin * D * ntok, 1, C)
+                eng._gemm(blk["kv"], d["kvn"], d["kvb"], 1, nwin * D * n_kvf, 1, C)
                 if blk["bias_mma"] is not None:
                     ops.window_attention_mma(d["qb"], d["kvb"], blk["bias_mma"], nwin, ntok, D * ntok, C, eng.heads,
                                              d["ob"])
                 else:
-                    ops.window_attention(d["qb"], d["kvb"], blk["bias"], nwin, ntok, D * ntok, C, eng.heads, d["ob"])
+                    ops.window_attention(d["qb"], d["kvb"], blk["bias"], nwin, ntok, D * n_kvf, C, eng.heads, d["ob"])
                 # proj + window_reverse + crop + shortcut: x[pixel] += proj(o); uncovered pixels keep x
                 eng._gemm(blk["proj"], d["ob"], xs, 1, nwin * ntok, 1, C, epi=EPI_SCATTER, row_map=tm.view(-1))
                 ops.layernorm(xs, P, C, blk["n2_g"], blk["n2_b"], d["yn"])

@@ -27,10 +27,23 @@ from .registry import MODELS
 # --------------------------------------------------------------------------------------------
 
 
-class _ConvLayer(nn.Module):                      # submodules.py:85  (conv2d)
-    def __init__(self, cin, cout, k):
+def _norm_layer(norm, c):
+    """ConvLayer / UpsampleConvLayer norm (submodules.py:100-103, 133-136): eval-mode BatchNorm / InstanceNorm with
+    running statistics, folded into the convolution weights when the engine packs them."""
+    if norm == 'BN':
+        return nn.BatchNorm2d(c)
+    if norm == 'IN':
+        return nn.InstanceNorm2d(c, track_running_stats=True)
+    return None
+
+
+class _ConvLayer(nn.Module):                      # submodules.py:85  (conv2d [+ norm_layer])
+    def __init__(self, cin, cout, k, norm=None):
         super().__init__()
-        self.conv2d = nn.Conv2d(cin, cout, k, padding=k // 2)
+        self.conv2d = nn.Conv2d(cin, cout, k, padding=k // 2, bias=norm != 'BN')
+        nl = _norm_layer(norm, cout)
+        if nl is not None:
+            self.norm_layer = nl
 
 
 class _ConvLSTM(nn.Module):                       # submodules.py:278 (Gates)
@@ -39,21 +52,31 @@ class _ConvLSTM(nn.Module):                       # submodules.py:278 (Gates)
         self.Gates = nn.Conv2d(cin + hidden, 4 * hidden, k, padding=k // 2)
 
 
-class _RecurrentConv(nn.Module):                  # submodules.py:173 (conv, recurrent_block)
-    def __init__(self, cin, cout, k):
+class _ConvGRU(nn.Module):                        # submodules.py:337 (reset_gate, update_gate, out_gate)
+    def __init__(self, cin, hidden, k=3):
         super().__init__()
-        self.conv = _ConvLayer(cin, cout, k)
-        self.recurrent_block = _ConvLSTM(cout, cout, 3)
+        self.reset_gate = nn.Conv2d(cin + hidden, hidden, k, padding=k // 2)
+        self.update_gate = nn.Conv2d(cin + hidden, hidden, k, padding=k // 2)
+        self.out_gate = nn.Conv2d(cin + hidden, hidden, k, padding=k // 2)
+
+
+class _RecurrentConv(nn.Module):                  # submodules.py:173 (conv, recurrent_block)
+    def __init__(self, cin, cout, k, norm=None, recurrent_block_type='convlstm'):
+        super().__init__()
+        self.conv = _ConvLayer(cin, cout, k, norm)
+        self.recurrent_block = (_ConvLSTM if recurrent_block_type == 'convlstm' else _ConvGRU)(cout, cout, 3)
 
 
 class _WindowAttention(nn.Module):                # DTransformer.py:99
-    def __init__(self, dim, D, wh, ww, heads):
+    def __init__(self, dim, D, wh, ww, heads, nwin=None):
         super().__init__()
         from .synth import relative_position_index
         self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * D - 1) * (2 * wh - 1) * (2 * ww - 1), heads))
         self.register_buffer("relative_position_index", relative_position_index(D, wh, ww))
         self.norm_q = nn.LayerNorm(dim)
         self.norm_kv = nn.LayerNorm(dim)
+        if nwin is not None:                      # "feature reduction" (DTransformer.py:128-131)
+            self.reduction_conv = nn.Conv2d(dim, nwin[0] * nwin[1] * dim, kernel_size=(wh, ww), groups=dim)
         self.q = nn.Linear(dim, dim)
         self.kv = nn.Linear(dim, 2 * dim)
         self.proj = nn.Linear(dim, dim)
@@ -68,17 +91,24 @@ class _Mlp(nn.Module):                            # DTransformer.py:19
 
 
 class _SwinBlock(nn.Module):                      # DTransformer.py:213
-    def __init__(self, dim, D, wh, ww, heads):
+    def __init__(self, dim, D, wh, ww, heads, nwin=None):
         super().__init__()
-        self.attn = _WindowAttention(dim, D, wh, ww, heads)
+        self.attn = _WindowAttention(dim, D, wh, ww, heads, nwin)
         self.norm2 = nn.LayerNorm(dim)
         self.mlp = _Mlp(dim)
 
 
 class _DFrameAttention(nn.Module):                # DTransformer.py:309
-    def __init__(self, dim, depth, D, wh, ww, heads):
+    def __init__(self, dim, depth, D, wh, ww, heads, nwin=None):
         super().__init__()
-        self.blocks = nn.ModuleList([_SwinBlock(dim, D, wh, ww, heads) for _ in range(depth)])
+        self.blocks = nn.ModuleList([_SwinBlock(dim, D, wh, ww, heads, nwin) for _ in range(depth)])
+
+
+class _ResidualBlockNoBN(nn.Module):              # ...V5.py:261-275 (conv1, conv2)
+    def __init__(self, c):
+        super().__init__()
+        self.conv1 = nn.Conv2d(c, c, 3, padding=1)
+        self.conv2 = nn.Conv2d(c, c, 3, padding=1)
 
 
 def _unsupported(what):
@@ -86,9 +116,17 @@ def _unsupported(what):
                               "(there is no PyTorch/CPU fallback)" % what)
 
 
+_OUT_ACTS = {"Sigmoid": ops.ACT_SIGMOID, "Identity": ops.ACT_NONE}
+_NET_ACTS = {"default": ops.ACT_RELU, "ReLU": ops.ACT_RELU, "ReLU6": ops.ACT_RELU6}
+
+
 @MODELS.register_module()
 class BDE2VIDCrossscalePropogationV5(nn.Module):
-    """Generator.  Constructor signature = reference (...V5.py:19-23)."""
+    """Generator.  Constructor signature = reference (...V5.py:19-23).  Every architecture option of the reference
+    constructor is built from the same kernels: ``norm`` None / 'BN' / 'IN' (eval-mode statistics folded into the
+    convolution), ``recurrent_block_type`` 'convlstm' / 'convgru', ``useRC``, ``skip_type`` 'sum' / 'concat',
+    ``nwindow_size`` (reduction_conv), ``depths[-1] == 0`` (ParseLayer + ResidualBlockNoBN tail), output activation
+    'Sigmoid' / 'Identity'."""
 
     def __init__(self, num_bins, basechannels, num_encoders, ks, num_res_blocks, norm=None,
                  recurrent_block_type='convlstm', useRC=True, skip_type='sum', activation=None,
@@ -96,17 +134,22 @@ class BDE2VIDCrossscalePropogationV5(nn.Module):
                  window_size=(7, 7), nwindow_size=None, depths=[4, 0, 6], num_heads=16, drop_path_rate=0.2,
                  use_checkpoint=False, act_attn="default", losses=None, loss_inds=None, init_cfg=None):
         super().__init__()
-        if norm not in (None, "none"):
+        if norm in ("none", "None"):
+            norm = None
+        if norm not in (None, "BN", "IN"):
             _unsupported("norm=%r" % (norm,))
-        if recurrent_block_type != 'convlstm' or not useRC:
-            _unsupported("recurrent_block_type=%r / useRC=%r" % (recurrent_block_type, useRC))
-        if skip_type != 'sum':
-            _unsupported("skip_type=%r" % (skip_type,))
-        if nwindow_size is not None:
-            _unsupported("nwindow_size (reduction_conv)")
-        if activation is not None and dict(activation).get("type", "Sigmoid") != "Sigmoid":
+        if recurrent_block_type not in ('convlstm', 'convgru'):
+            raise AssertionError("recurrent_block_type must be 'convlstm' or 'convgru' (submodules.py:179)")
+        if skip_type in ('no_skip', None):
+            _unsupported("skip_type=%r (the reference itself fails on it: nn.Identity() returns the [skip, x] list, "
+                         "...V5.py:32-33,194)" % (skip_type,))
+        if skip_type not in ('sum', 'concat'):
+            raise KeyError('Could not identify skip_type, please add "skip_type": "sum", "concat" or "no_skip" '
+                           'to config["model"]')
+        act_name = "Sigmoid" if activation is None else dict(activation).get("type", "Sigmoid")
+        if act_name not in _OUT_ACTS:
             _unsupported("output activation %r" % (activation,))
-        if act_net not in ("default", "ReLU") or act_attn not in ("default", "GELU"):
+        if act_net not in _NET_ACTS or act_attn not in ("default", "GELU"):
             _unsupported("act_net=%r / act_attn=%r" % (act_net, act_attn))
         if num_output_channels != 1:
             _unsupported("num_output_channels != 1")
@@ -115,29 +158,43 @@ class BDE2VIDCrossscalePropogationV5(nn.Module):
         depths = list(depths)
         if len(depths) != num_encoders:
             raise ValueError("len(depths) must equal num_encoders")
-        if depths[-1] == 0:
-            _unsupported("depths[-1] == 0 (ParseLayer + ResidualBlockNoBN tail)")
         if len(buffer_index) > 8:
             _unsupported("more than 8 buffered frames")
+        nwin = None if nwindow_size is None else tuple(int(v) for v in nwindow_size)
         self.cfg = dict(num_bins=num_bins, basechannels=basechannels, num_encoders=num_encoders, ks=ks,
                         buffer_index=[int(b) for b in buffer_index], q_idx=int(q_idx),
-                        window_size=tuple(window_size), depths=depths, num_heads=num_heads)
+                        window_size=tuple(window_size), depths=depths, num_heads=num_heads, norm=norm,
+                        recurrent_block_type=recurrent_block_type if useRC else None, skip_type=skip_type,
+                        nwindow_size=nwin, num_res_blocks=num_res_blocks, out_act=_OUT_ACTS[act_name],
+                        net_act=_NET_ACTS[act_net])
         self.losses_cfg = losses          # accepted and ignored: training-only (...V5.py:37-38)
         self.num_encoders = num_encoders
         bc, ne = basechannels, num_encoders
         D = len(buffer_index)
         wh, ww = tuple(window_size)
-        self.head = _ConvLayer(num_bins, bc, ks)
-        self.forward_encoder = nn.ModuleList([_RecurrentConv(bc * 2 ** i, bc * 2 ** (i + 1), ks) for i in range(ne)])
-        self.backward_encoder = nn.ModuleList([_RecurrentConv(bc * 2 ** i, bc * 2 ** (i + 1), ks) for i in range(ne)])
+        self.head = _ConvLayer(num_bins, bc, ks, norm)
+
+        def encoder():                            # Encoder(), ...V5.py:244-259
+            if useRC:
+                return nn.ModuleList([_RecurrentConv(bc * 2 ** i, bc * 2 ** (i + 1), ks, norm, recurrent_block_type)
+                                      for i in range(ne)])
+            return nn.ModuleList([_ConvLayer(bc * 2 ** i, bc * 2 ** (i + 1), ks, norm) for i in range(ne)])
+
+        self.forward_encoder = encoder()
+        self.backward_encoder = encoder()
         # present in every reference checkpoint, never used by forward (quirk Q3)
         self.fusion_layers = nn.ModuleList([nn.Conv2d(bc * 2 ** (i + 2), bc * 2 ** (i + 1), 1) for i in range(ne)])
         self.feat_attns = nn.ModuleList([
-            _DFrameAttention(bc * 2 ** (i + 1), d, D, wh, ww, num_heads) if d > 0 else None
+            _DFrameAttention(bc * 2 ** (i + 1), d, D, wh, ww, num_heads, nwin) if d > 0 else None
             for i, d in enumerate(depths)])
+        if depths[-1] == 0:                       # ...V5.py:77-80: ParseLayer + ResidualBlockNoBN x num_res_blocks
+            self.feat_attns[-1] = nn.Sequential(nn.Identity(), *[_ResidualBlockNoBN(bc * 2 ** ne) for _ in range(num_res_blocks)])
+        concat = skip_type == 'concat'
         self.decoders = nn.ModuleList([
-            nn.Sequential(nn.Identity(), _ConvLayer(bc * 2 ** (ne - i), bc * 2 ** (ne - i - 1), ks)) for i in range(ne)])
-        self.predI = nn.Sequential(nn.Identity(), nn.Conv2d(bc, num_output_channels, 1))
+            nn.Sequential(nn.Conv2d(bc * 2 ** (ne - i + 1), bc * 2 ** (ne - i), 1) if concat else nn.Identity(),
+                          _ConvLayer(bc * 2 ** (ne - i), bc * 2 ** (ne - i - 1), ks, norm)) for i in range(ne)])
+        self.predI = nn.Sequential(nn.Conv2d(bc * 2, bc, 1) if concat else nn.Identity(),
+                                   nn.Conv2d(bc, num_output_channels, 1))
         self._engine = None
         self.precision = os.environ.get("BDE2VID_PRECISION", "bf16")
         self.use_cuda_graph = os.environ.get("BDE2VID_CUDA_GRAPH", "1") != "0"
@@ -196,20 +253,24 @@ class BDE2VID(nn.Module):
         _unsupported("forward mode %r (only 'tensor' is on the inference path)" % (mode,))
 
     # fused entry point: raw events -> frames without materialising voxel grids on the host
-    def reconstruct_events(self, xs, ys, ts, ps, offsets, sensor_size, num_encoders=None, slot=0):
-        """events (float32 loader format; CUDA or pinned host) + CSR offsets -> list of T cropped frames
-        [1,1,H,W].  ``slot`` picks an independent buffer set so that several sequences can run
-        concurrently on different CUDA streams."""
+    def reconstruct_events(self, xs, ys, ts, ps, offsets, sensor_size, num_encoders=None, slot=0, normalize=None,
+                           hot_mask=None):
+        """events + CSR offsets (CUDA or pinned host) -> list of T cropped frames [1,1,H,W].  Events are either the
+        loader format (four float32 arrays, h5_dataset.py:222-225) or the on-disk dtypes (int16 x / y, float64 t, bool p:
+        event_packagers.py:44-47), converted in the voxeliser.  The loader contract is kept: windows with fewer than 3
+        events give zero grids (h5_dataset.py:219-221); ``normalize`` ('legacy' | 'robust' | ('robust', low, top)) and
+        ``hot_mask`` apply the loader's voxel transforms (h5_dataset.py:226, :364) on the device.  ``slot`` picks an
+        independent buffer set so that several sequences can run concurrently on different CUDA streams."""
         from .croper import Croper
         H, W = sensor_size
         crop = Croper(self.generator.num_encoders if num_encoders is None else num_encoders)
         crop.update_params(W, H)
         eng = self.generator.engine()
         frames = eng.forward_events(xs, ys, ts, ps, offsets, H, W, crop, use_graph=self.generator.use_cuda_graph,
-                                    slot=slot)
+                                    slot=slot, normalize=normalize, hot_mask=hot_mask)
         return [crop.crop(f) for f in frames]
 
-    def reconstruct_events_batch(self, seqs, sensor_size, num_encoders=None, slot=0):
+    def reconstruct_events_batch(self, seqs, sensor_size, num_encoders=None, slot=0, normalize=None, hot_mask=None):
         """Several independent event sequences (same window count) reconstructed as ONE batch: ``seqs`` is a
         list of (xs, ys, ts, ps, offsets) tuples; returns a list (per sequence) of T cropped frames."""
         from .croper import Croper
@@ -217,7 +278,8 @@ class BDE2VID(nn.Module):
         crop = Croper(self.generator.num_encoders if num_encoders is None else num_encoders)
         crop.update_params(W, H)
         eng = self.generator.engine()
-        out = eng.forward_events_batch(seqs, H, W, crop, use_graph=self.generator.use_cuda_graph, slot=slot)
+        out = eng.forward_events_batch(seqs, H, W, crop, use_graph=self.generator.use_cuda_graph, slot=slot,
+                                       normalize=normalize, hot_mask=hot_mask)
         return [[crop.crop(f) for f in frames] for frames in out]
 
 

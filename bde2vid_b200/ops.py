@@ -9,12 +9,13 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_RELU6, ACT_SIGMOID, BDE_DTYPE, BF16, ENGINE_SIMT,  # noqa: F401
-                   ENGINE_TCGEN05, EPI_LSTM, EPI_SCATTER, EPI_STORE, F32, TORCH_DTYPE, check, ptr, stream_ptr)
+                   ENGINE_TCGEN05, EPI_GRU_OUT, EPI_GRU_UR, EPI_LSTM, EPI_SCATTER, EPI_STORE, F32, TORCH_DTYPE, check, ptr, stream_ptr)
 
 
 def voxelize_seq(xs, ys, ts, ps, offsets, num_bins, H, W, pad_top=0, pad_left=0, Hp=None, Wp=None, out=None,
-                 oob_count=None, algo=0):
-    """float32 event arrays + int64 CSR offsets [T+1] -> float32 [T, bins, Hp, Wp]."""
+                 oob_count=None, algo=0, min_events=1):
+    """float32 event arrays + int64 CSR offsets [T+1] -> float32 [T, bins, Hp, Wp].  ``min_events``: windows with fewer
+    events give zeros (1 = the bare reference function, 3 = the loader contract h5_dataset.py:219-221)."""
     lib = _lib.require_device()
     Hp = H + pad_top if Hp is None else Hp
     Wp = W + pad_left if Wp is None else Wp
@@ -26,19 +27,73 @@ def voxelize_seq(xs, ys, ts, ps, offsets, num_bins, H, W, pad_top=0, pad_left=0,
         out = torch.empty((T, num_bins, Hp, Wp), dtype=torch.float32, device=xs.device)
     assert out.shape == (T, num_bins, Hp, Wp) and out.dtype == torch.float32
     check(lib.bde_voxelize_seq(ptr(xs), ptr(ys), ptr(ts), ptr(ps), ptr(offsets), T, num_bins, H, W, pad_top, pad_left,
-                               Hp, Wp, ptr(out), ptr(oob_count), algo, stream_ptr()), "bde_voxelize_seq")
+                               Hp, Wp, ptr(out), ptr(oob_count), algo, min_events, stream_ptr()), "bde_voxelize_seq")
     return out
 
 
 def voxelize_seq_into(xs, ys, ts, ps, offsets, num_bins, H, W, pad_top, pad_left, Hp, Wp, out_view, window_stride,
-                      oob_count=None, algo=0):
+                      oob_count=None, algo=0, min_events=1, hot_mask=None):
     """Voxelise one sequence into a strided destination: ``out_view`` is the tensor element where window 0's grid
-    starts and consecutive windows are ``window_stride`` floats apart (batch buffers [T, B, bins, Hp, Wp])."""
+    starts and consecutive windows are ``window_stride`` floats apart (batch buffers [T, B, bins, Hp, Wp]).
+    Event arrays: four float32 tensors (loader format) or the on-disk dtypes int16 / int16 / float64 / bool|uint8
+    (bde_voxelize_raw_strided)."""
     lib = _lib.require_device()
     T = offsets.numel() - 1
-    check(lib.bde_voxelize_seq_strided(ptr(xs), ptr(ys), ptr(ts), ptr(ps), ptr(offsets), T, num_bins, H, W, pad_top,
-                                       pad_left, Hp, Wp, C.c_void_p(out_view.data_ptr()), window_stride, ptr(oob_count),
-                                       algo, stream_ptr()), "bde_voxelize_seq_strided")
+    if xs.dtype == torch.float32:
+        assert ys.dtype == ts.dtype == ps.dtype == torch.float32
+        fn, name = lib.bde_voxelize_seq_strided, "bde_voxelize_seq_strided"
+    else:
+        assert xs.dtype == torch.int16 and ys.dtype == torch.int16 and ts.dtype == torch.float64 \
+            and ps.dtype in (torch.bool, torch.uint8), "raw events must be int16 / int16 / float64 / bool"
+        fn, name = lib.bde_voxelize_raw_strided, "bde_voxelize_raw_strided"
+    assert hot_mask is None or (hot_mask.dtype == torch.float32 and hot_mask.shape == (H, W))
+    check(fn(ptr(xs), ptr(ys), ptr(ts), ptr(ps), ptr(offsets), T, num_bins, H, W, pad_top, pad_left, Hp, Wp,
+             C.c_void_p(out_view.data_ptr()), window_stride, ptr(oob_count), algo, min_events, ptr(hot_mask), stream_ptr()), name)
+
+
+def voxelize_raw(xs, ys, ts, ps, offsets, num_bins, H, W, pad_top=0, pad_left=0, Hp=None, Wp=None, out=None,
+                 oob_count=None, algo=0, min_events=3, hot_mask=None):
+    """On-disk event dtypes (int16 x / y, float64 t, bool p) + CSR offsets -> float32 [T, bins, Hp, Wp]; the loader's
+    conversions (h5_dataset.py:222-225, :414) happen in the kernel."""
+    Hp = H + pad_top if Hp is None else Hp
+    Wp = W + pad_left if Wp is None else Wp
+    T = offsets.numel() - 1
+    if out is None:
+        out = torch.empty((T, num_bins, Hp, Wp), dtype=torch.float32, device=xs.device)
+    voxelize_seq_into(xs, ys, ts, ps, offsets, num_bins, H, W, pad_top, pad_left, Hp, Wp, out, num_bins * Hp * Wp,
+                      oob_count=oob_count, algo=algo, min_events=min_events, hot_mask=hot_mask)
+    return out
+
+
+NORM_LEGACY, NORM_ROBUST = 1, 2
+
+
+def voxel_normalize(grids, H, W, pad_top, pad_left, mode, low_perc=0.0, top_perc=95.0, window_stride=None, n_windows=None,
+                    stats=None):
+    """In-place LegacyNorm / RobustNorm of every window's sensor area (see bde_voxel_normalize).  ``grids``: float32
+    [T, bins, Hp, Wp] contiguous, or any float32 view whose window 0 starts at its first element when ``window_stride`` /
+    ``n_windows`` (floats between windows, number of windows) are given with bins / Hp / Wp taken from its last 3 dims."""
+    lib = _lib.require_device()
+    bins, Hp, Wp = grids.shape[-3:]
+    if window_stride is None:
+        assert grids.is_contiguous()
+        window_stride = bins * Hp * Wp
+        n_windows = grids.numel() // window_stride
+    assert grids.dtype == torch.float32
+    check(lib.bde_voxel_normalize(C.c_void_p(grids.data_ptr()), window_stride, n_windows, bins, H, W, pad_top, pad_left, Hp, Wp,
+                                  mode, float(low_perc), float(top_perc), ptr(stats), stream_ptr()), "bde_voxel_normalize")
+    return grids
+
+
+def hot_pixel_mask(xs, ys, ps, H, W, num_hot):
+    """get_hot_event_mask (event_utils.py:100-116) on the device: float32 [H, W] of {0, 1}."""
+    lib = _lib.require_device()
+    assert xs.dtype == torch.int16 and ys.dtype == torch.int16 and ps.dtype in (torch.bool, torch.uint8)
+    mask = torch.empty(H, W, dtype=torch.float32, device=xs.device)
+    scratch = torch.empty(H, W, dtype=torch.float32, device=xs.device)
+    check(lib.bde_hot_pixel_mask(ptr(xs), ptr(ys), ptr(ps), xs.numel(), H, W, int(num_hot), ptr(mask), ptr(scratch),
+                                 stream_ptr()), "bde_hot_pixel_mask")
+    return mask
 
 
 def pack_voxel_nhwc(vox, c_pad, dtype, out=None):
@@ -52,7 +107,7 @@ def pack_voxel_nhwc(vox, c_pad, dtype, out=None):
     return out
 
 
-def frame_metrics(pred, gt, y0, x0, data_range=1.0):
+def frame_metrics(pred, gt, y0, x0, data_range):
     """pred float32 [n, Hp, Wp] (padded model output), gt float32 [n, H, W] -> float64 [n, 2] = (mse, ssim) per frame
     of pred[:, y0:y0+H, x0:x0+W] vs gt (evaluate/metrics.py:42-65)."""
     lib = _lib.require_device()
@@ -125,11 +180,21 @@ def upsample2x_sum(skip, x, x_scale, n_img, h, w, c, dst):
     return dst
 
 
-def pred_sigmoid(x, head, wt, bias, c, n_pix, img):
+def pred_sigmoid(x, head, wt, bias, c, n_pix, img, wt_head=None, act=ACT_SIGMOID):
     lib = _lib.require_device()
-    check(lib.bde_pred_sigmoid(ptr(x), ptr(head), ptr(wt), ptr(bias), c, n_pix, ptr(img), BDE_DTYPE[x.dtype],
-                               stream_ptr()), "bde_pred_sigmoid")
+    check(lib.bde_pred_sigmoid(ptr(x), ptr(head), ptr(wt), ptr(wt_head), ptr(bias), c, n_pix, ptr(img), BDE_DTYPE[x.dtype],
+                               act, stream_ptr()), "bde_pred_sigmoid")
     return img
+
+
+def window_reduce(frames, tok_map, n_win, n_tok, c, X, w, b, out):
+    """Depthwise whole-window "feature reduction" (nwindow_size) -> float32 [n_win, D, X, c]; see bde_window_reduce."""
+    lib = _lib.require_device()
+    D = len(frames)
+    arr = (C.c_void_p * D)(*[None if f is None else f.data_ptr() for f in frames])
+    check(lib.bde_window_reduce(arr, D, ptr(tok_map), n_win, n_tok, c, X, ptr(w), ptr(b), ptr(out), stream_ptr()),
+          "bde_window_reduce")
+    return out
 
 
 def ln_gather(frames, tok_map, n_win, n_tok, c, gamma, beta, out):

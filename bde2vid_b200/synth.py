@@ -153,3 +153,57 @@ def init_state_dict(cfg, seed=0, stress=False):
         elif kind == "index":
             sd[key] = relative_position_index(D, wh, ww)
     return sd
+
+
+def random_state_dict_like(template, seed=0):
+    """Seeded random checkpoint with the key set / shapes of ``template`` (a state_dict of the reference model or of the
+    drop-in container -- they have the same keys).  Every tensor is drawn from a generator seeded by (crc32(key), seed),
+    so the result does not depend on key order.  Used for the architecture variants (ConvGRU, BN / IN, concat skips,
+    nwindow_size, residual tail, FireNet ...) whose key sets differ from ``state_dict_spec``."""
+    import zlib
+    out = {}
+    for key, v in template.items():
+        g = torch.Generator().manual_seed((zlib.crc32(key.encode()) + 7919 * int(seed)) & 0x7fffffff)
+        shape = tuple(v.shape)
+        if not torch.is_floating_point(v):
+            out[key] = v.clone()                                   # relative_position_index, num_batches_tracked
+        elif key.endswith("running_var"):
+            out[key] = 0.5 + torch.rand(shape, generator=g)
+        elif key.endswith("running_mean"):
+            out[key] = 0.2 * torch.randn(shape, generator=g)
+        elif key.endswith("relative_position_bias_table"):
+            out[key] = 0.5 * torch.randn(shape, generator=g).clamp_(-2, 2)
+        elif ("norm" in key.rsplit(".", 2)[-2]) and key.endswith(".weight"):
+            out[key] = 1.0 + 0.2 * torch.randn(shape, generator=g)
+        elif ("norm" in key.rsplit(".", 2)[-2]) and key.endswith(".bias"):
+            out[key] = 0.2 * torch.randn(shape, generator=g)
+        elif v.dim() >= 2:
+            fan_in = 1
+            for s_ in shape[1:]:
+                fan_in *= s_
+            out[key] = (torch.rand(shape, generator=g) * 2 - 1) / fan_in ** 0.5
+        else:
+            out[key] = (torch.rand(shape, generator=g) * 2 - 1) * 0.1
+    return out
+
+
+def gen_events_clustered(seq_id, T, H, W, N, blobs=24, sigma=6.0):
+    """Like ``gen_events`` but spatially clustered: every window's events fall around ``blobs`` moving Gaussian blobs
+    (sigma pixels), the way real event streams concentrate on moving edges.  Same dtypes / CSR layout."""
+    g = torch.Generator().manual_seed(5000 + int(seq_id))
+    cx = torch.rand(blobs, generator=g) * W
+    cy = torch.rand(blobs, generator=g) * H
+    vx = (torch.rand(blobs, generator=g) - 0.5) * 8
+    vy = (torch.rand(blobs, generator=g) - 0.5) * 8
+    xs, ys = [], []
+    for t in range(T):
+        which = torch.randint(0, blobs, (N,), generator=g)
+        x = (cx + vx * t)[which] + sigma * torch.randn(N, generator=g)
+        y = (cy + vy * t)[which] + sigma * torch.randn(N, generator=g)
+        xs.append(x.remainder(W).floor().clamp_(0, W - 1).to(torch.int16))
+        ys.append(y.remainder(H).floor().clamp_(0, H - 1).to(torch.int16))
+    ps = torch.rand(T, N, generator=g) < 0.5
+    u, _ = torch.sort(torch.rand(T, N, generator=g, dtype=torch.float64), dim=1)
+    ts = u * WINDOW_DT + torch.arange(T, dtype=torch.float64).view(T, 1) * WINDOW_DT
+    return dict(xs=torch.cat(xs).numpy(), ys=torch.cat(ys).numpy(), ts=ts.reshape(-1).numpy(), ps=ps.reshape(-1).numpy(),
+                offsets=np.arange(T + 1, dtype=np.int64) * N, H=H, W=W)

@@ -15,12 +15,13 @@ def _as_cuda_f32(t, device):
     return t.to(device=device, dtype=torch.float32).contiguous()
 
 
-def events_to_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240), temporal_bilinear=True):
+def events_to_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240), temporal_bilinear=True, check_bounds=True):
     """Turn one window of events into a voxel grid with temporal bilinear interpolation.
 
     Same arguments as the reference.  ``device`` (or the events' device) must be a CUDA device:
     this implementation has no CPU path.  Events outside the sensor raise IndexError like the
-    reference's ``index_put_`` does."""
+    reference's ``index_put_`` does; that check reads one counter back from the device (a stream
+    synchronisation per call) -- ``check_bounds=False`` (an extension) skips it and drops such events."""
     if not temporal_bilinear:
         raise NotImplementedError("temporal_bilinear=False is broken in the reference itself "
                                   "(event_utils.py:500-503 uses undefined names) and is not provided")
@@ -35,19 +36,22 @@ def events_to_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240)
     if n == 0:
         raise IndexError("events_to_voxel_torch: empty event window (the reference fails on ts[-1] too)")
     offsets = torch.tensor([0, n], dtype=torch.int64, device=device)
-    oob = torch.zeros(1, dtype=torch.int32, device=device)
     H, W = sensor_size
+    if not check_bounds:
+        return ops.voxelize_seq(xs, ys, ts, ps, offsets, B, H, W)[0]
+    oob = torch.zeros(1, dtype=torch.int32, device=device)
     out = ops.voxelize_seq(xs, ys, ts, ps, offsets, B, H, W, oob_count=oob)
-    if int(oob.item()) != 0:
-        raise IndexError("events_to_voxel_torch: %d events outside the %dx%d sensor" % (int(oob.item()), H, W))
+    n_oob = int(oob.item())
+    if n_oob != 0:
+        raise IndexError("events_to_voxel_torch: %d events outside the %dx%d sensor" % (n_oob, H, W))
     return out[0]
 
 
-def voxelize_sequence(xs, ys, ts, ps, offsets, num_bins, sensor_size, crop=None, algo=0, out=None, oob_count=None):
+def voxelize_sequence(xs, ys, ts, ps, offsets, num_bins, sensor_size, crop=None, algo=0, out=None, oob_count=None, min_events=1):
     """All windows of a sequence in one launch.  ``crop`` (a ``Croper`` with params set) selects the
     zero-padded output geometry; returns float32 [T, num_bins, Hp, Wp]."""
     H, W = sensor_size
     if crop is None:
-        return ops.voxelize_seq(xs, ys, ts, ps, offsets, num_bins, H, W, out=out, oob_count=oob_count, algo=algo)
+        return ops.voxelize_seq(xs, ys, ts, ps, offsets, num_bins, H, W, out=out, oob_count=oob_count, algo=algo, min_events=min_events)
     return ops.voxelize_seq(xs, ys, ts, ps, offsets, num_bins, H, W, crop.padding_top, crop.padding_left,
-                            crop.height_crop_size, crop.width_crop_size, out=out, oob_count=oob_count, algo=algo)
+                            crop.height_crop_size, crop.width_crop_size, out=out, oob_count=oob_count, algo=algo, min_events=min_events)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define BDE_ABI_VERSION 1
+#define BDE_ABI_VERSION 2
 
 /* element types of activation / weight buffers */
 enum { BDE_F32 = 0, BDE_BF16 = 1 };
@@ -35,7 +35,13 @@ enum { BDE_ACT_NONE = 0, BDE_ACT_RELU = 1, BDE_ACT_RELU6 = 2, BDE_ACT_GELU = 3, 
 enum {
   BDE_EPI_STORE = 0,   /* out[m,n] = act(acc + bias[n]) (+ residual[m,n])                       */
   BDE_EPI_LSTM = 1,    /* N = 4*hidden, gate-interleaved rows; ConvLSTM pointwise update         */
-  BDE_EPI_SCATTER = 2  /* out_f32[row_map[m], n] += acc + bias[n]   (rows with map < 0 dropped)  */
+  BDE_EPI_SCATTER = 2, /* out_f32[row_map[m], n] += acc + bias[n]   (rows with map < 0 dropped)  */
+  /* ConvGRU (model/BDE2VID/submodules.py:337-375, model/e2vid/submodules.py ConvGRU) as two fused convolutions:    */
+  BDE_EPI_GRU_UR = 3,  /* N = 2*hidden, rows interleaved n = 2*c + g (g = 0 update_gate, 1 reset_gate):           */
+                       /*   c_out[m,c] = u = sigmoid(update)  (fp32);  out[m,c] = h_prev[m,c] * sigmoid(reset)    */
+                       /*   (`dtype`; the second source of the out_gate convolution).  h_prev = c_prev (fp32).    */
+  BDE_EPI_GRU_OUT = 4  /* N = hidden: o = tanh(acc + bias);  h' = h_prev * (1 - u) + o * u;  h_prev = c_prev     */
+                       /*   (fp32, NULL = zeros), u = residual (fp32); c_out = h' (fp32 master), out = h' (`dtype`) */
 };
 
 /* GEMM engines */
@@ -58,20 +64,61 @@ int bde_device_ok(void);
  *                    pad_left); every byte of `out` is written (padding = 0)
  *   oob_count      : optional int32[1], incremented for every event outside the sensor (the
  *                    reference raises IndexError from index_put_; such events are dropped here)
- *   algo           : 0 = auto, 1 = shared-memory row-band accumulation, 2 = global atomics
- * Windows with fewer than 1 event produce zeros; dt == 0 reproduces the reference's NaNs.
+ *   algo           : 0 = auto (= 2), 1 = shared-memory row-band tiles + warp aggregation, 2 = memset + global
+ *                    RED.ADD.F32 (L2 executes the reductions; 128-bit event loads; windows processed in L2-sized
+ *                    chunks), 3 = cluster / distributed-shared-memory grid, 4 = cluster zero + global reductions,
+ *                    5 = algorithm 2 with a warp-level pre-reduction of lanes that hit the same cell
+ *   min_events     : windows with fewer events produce an all-zero grid.  1 reproduces the bare function
+ *                    (dt == 0 gives the reference's NaNs); 3 is the loader contract (h5_dataset.py:219-221:
+ *                    `if len(xs) < 3: voxel = zeros`) that the fused events -> frames path must keep.
  */
 int bde_voxelize_seq(const float* xs, const float* ys, const float* ts, const float* ps,
                      const int64_t* offsets, int T, int num_bins, int H, int W,
                      int pad_top, int pad_left, int Hp, int Wp,
-                     float* out, int* oob_count, int algo, void* stream);
+                     float* out, int* oob_count, int algo, int min_events, void* stream);
 
 /* Same, with `out_window_stride` floats between the grids of consecutive windows (>= bins*Hp*Wp).  Lets B
- * sequences be voxelised straight into one [T, B, bins, Hp, Wp] batch buffer (stride B*bins*Hp*Wp). */
+ * sequences be voxelised straight into one [T, B, bins, Hp, Wp] batch buffer (stride B*bins*Hp*Wp).
+ *   hot_mask : optional float32 [H, W] of {0, 1}: the loader's hot-pixel mask (h5_dataset.py:163-172, :364
+ *              `voxel_grid * self.hot_events_mask`, the same mask for every bin); events on masked pixels are
+ *              dropped (algorithms 2 / 5). */
 int bde_voxelize_seq_strided(const float* xs, const float* ys, const float* ts, const float* ps,
                              const int64_t* offsets, int T, int num_bins, int H, int W,
                              int pad_top, int pad_left, int Hp, int Wp,
-                             float* out, size_t out_window_stride, int* oob_count, int algo, void* stream);
+                             float* out, size_t out_window_stride, int* oob_count, int algo, int min_events,
+                             const float* hot_mask, void* stream);
+
+/* Event ingest in the reference's ON-DISK dtypes (events_contrast_maximization/tools/event_packagers.py:44-47:
+ * events/xs, ys int16; events/ts float64 seconds; events/ps bool), 13 bytes per event instead of 16.  The loader's
+ * conversions (data_loader/h5_dataset.py:204-226, :410-415) happen in registers, bit-exactly:
+ *   x, y -> float32;  t -> float32(ts - ts[first event of the window]) (float64 subtraction, then the cast);
+ *   p -> ps * 2.0 - 1.0.   `offsets` are the per-frame event_idx windows (h5_dataset.py:448-455) as CSR.
+ * Replaces DynamicH5Dataset.__getitem__'s voxelisation on DataLoader workers + the per-window H2D of dense grids
+ * (eval_models_seq.py:204).  algo: 0 / 2 / 5 as above. */
+int bde_voxelize_raw_strided(const int16_t* xs, const int16_t* ys, const double* ts, const uint8_t* ps,
+                             const int64_t* offsets, int T, int num_bins, int H, int W,
+                             int pad_top, int pad_left, int Hp, int Wp,
+                             float* out, size_t out_window_stride, int* oob_count, int algo, int min_events,
+                             const float* hot_mask, void* stream);
+
+/* Voxel normalisation variants of the loader, applied per window on the sensor area of the padded grids, in place
+ * (the padding ring stays zero: the reference normalises before Croper.pad).
+ *   mode 1 = LegacyNorm (utils_func/data_augmentation.py:311-330): mean / std over the NON-ZERO cells,
+ *            x = (x != 0) * (x - mean) / std   (unchanged when there are no non-zero cells or std == 0)
+ *   mode 2 = RobustNorm(low_perc, top_perc) (utils_func/utils.py:7-51): t = k-th smallest value with
+ *            k = 1 + round(.01 * q * (numel - 1)) (exact order statistic over the bins*H*W cells, radix select);
+ *            unchanged when t_max == t_min == 0, else x = (clamp(x, t_min, t_max) - t_min) / (t_max + 1e-6)
+ *   grids: float32, window w at grids + w * window_stride, [bins, Hp, Wp] with the sensor at (pad_top, pad_left)
+ *   stats: optional float32 [T, 4] receiving (mean, std, count, 0) or (t_min, t_max, 0, 0) per window */
+int bde_voxel_normalize(float* grids, size_t window_stride, int T, int num_bins, int H, int W, int pad_top, int pad_left,
+                        int Hp, int Wp, int mode, float low_perc, float top_perc, float* stats, void* stream);
+
+/* Hot-pixel mask of the loader (events_contrast_maximization/utils/event_utils.py:100-116 get_hot_event_mask,
+ * h5_dataset.py:163-172): accumulate the polarities of the first n events into an image, then clear the num_hot
+ * largest pixels one argmax at a time (first index wins ties, as np.argmax).  Event formats as bde_voxelize_raw_strided
+ * (ps in {0,1} -> +-1).  mask: float32 [H, W] output of {0, 1};  scratch: float32 [H, W]. */
+int bde_hot_pixel_mask(const int16_t* xs, const int16_t* ys, const uint8_t* ps, int64_t n, int H, int W, int num_hot,
+                       float* mask, float* scratch, void* stream);
 
 /* Head convolution straight from the voxeliser's planar grid (model/BDE2VID/bde2vid_cross_scale_propogation_V5.py:116,
  * ConvLayer model/BDE2VID/submodules.py:85-114):  out = act(conv5x5(vox) + bias)
@@ -183,10 +230,22 @@ int bde_add(const void* a, int a_f32, const void* b, int b_f32, float* out_f32, 
 int bde_upsample2x_sum(const void* skip, int skip_f32, const void* x, int x_f32, float x_scale,
                        int n_img, int h, int w, int c, void* dst, int dtype, void* stream);
 
-/* img[p] = sigmoid(bias + sum_c wt[c] * (x[p,c] + head[p,c]))  (predI + Sigmoid, ...V5.py:195-197)
- * x, head NHWC [P, c] of `dtype`; img float32[P]. */
-int bde_pred_sigmoid(const void* x, const void* head, const float* wt, const float* bias, int c,
-                     size_t n_pix, float* img, int dtype, void* stream);
+/* img[p] = act(bias + sum_c wt[c] * x[p,c] + wt_head[c] * head[p,c])  (predI + output activation, ...V5.py:195-197)
+ * x, head NHWC [P, c] of `dtype`; img float32[P].  wt_head = NULL means wt (skip_type 'sum': w . (x + head)); with
+ * skip_type 'concat' the two 1x1 convolutions of predI (...V5.py:92-97: fusion 2c -> c, then c -> 1, no activation in
+ * between) are folded by the caller into one [2c] vector (wt | wt_head) and one bias.  act: BDE_ACT_SIGMOID or BDE_ACT_NONE
+ * (ACTIVATION registry 'Sigmoid' / 'Identity', model/BDE2VID/activaions.py). */
+int bde_pred_sigmoid(const void* x, const void* head, const float* wt, const float* wt_head, const float* bias, int c,
+                     size_t n_pix, float* img, int dtype, int act, void* stream);
+
+/* "Feature reduction" of WindowAttention3D when nwindow_size is set (DTransformer.py:128-131, 172-175): the depthwise
+ * whole-window convolution Conv2d(C, X*C, kernel = window, groups = C) that turns the n_tok tokens of every (window,
+ * frame) into X tokens, including the reference's reinterpretation of the [C*X] output vector as [X, C].
+ *   frames_host : HOST array of D device pointers float32 [P, c] (NULL = all-zero frame);  tok_map int32 [n_win * n_tok]
+ *   w float32 [c*X, n_tok] (reduction_conv.weight [C*X, 1, wh, ww] flattened), b float32 [c*X]
+ *   out float32 [n_win, D, X, c]  (kv token index d*X + j', before norm_kv) */
+int bde_window_reduce(const float* const* frames_host, int D, const int* tok_map, int n_win, int n_tok, int c, int X,
+                      const float* w, const float* b, float* out, void* stream);
 
 /* Window-token gather + LayerNorm (DTransformer.py:41-60 window_partition, :183-184 norm_q/kv).
  *   frames[d]  : float32 NHWC [h*w, c] feature map of buffer slot d, or NULL (= all-zero frame)

@@ -34,6 +34,27 @@ MODEL_CASES = {
 }
 
 
+# architecture variants of the generator constructor (...V5.py:19-98); weights = synth.random_state_dict_like(template, seed)
+# name: (H, W, T, N, cfg overrides, weight seed, event seq_id)
+VARIANT_CASES = {
+    "var_gru_64x96_T4": (64, 96, 4, 2500, dict(recurrent_block_type="convgru", depths=[1, 0, 1]), 21, 41),
+    "var_concat_64x96_T3": (64, 96, 3, 2500, dict(skip_type="concat", depths=[1, 0, 1]), 22, 42),
+    "var_bn_64x96_T3": (64, 96, 3, 2500, dict(norm="BN", depths=[1, 0, 1]), 23, 43),
+    "var_in_56x80_T3": (56, 80, 3, 2000, dict(norm="IN", depths=[1, 0, 1]), 24, 44),
+    "var_nwin_64x96_T3": (64, 96, 3, 2500, dict(nwindow_size=(3, 3), depths=[2, 0, 2]), 25, 45),
+    "var_tail_64x96_T4": (64, 96, 4, 2500, dict(depths=[1, 0, 0]), 26, 46),
+    "var_norc_64x96_T3": (64, 96, 3, 2500, dict(useRC=False, depths=[1, 0, 1]), 27, 47),
+    "var_all_64x96_T3": (64, 96, 3, 2500, dict(recurrent_block_type="convgru", skip_type="concat", norm="BN",
+                                               nwindow_size=(2, 2), depths=[2, 0, 0], buffer_index=[-1, 0], q_idx=1,
+                                               activation=dict(type="Identity")), 28, 48),
+}
+
+
+def gen_cfg(over):
+    """Constructor kwargs of the generator for a variant (type + every argument of DEFAULT_CFG)."""
+    return O.full_cfg(over)
+
+
 def voxel_inputs(seq_id, T, H, W, N, num_encoders=3):
     """Voxel grids of a synthetic sequence via the oracle voxeliser, padded like the driver does."""
     ev = synth.gen_events(seq_id, T, H, W, N)
@@ -135,6 +156,71 @@ def main():
                               oracle_vs_reference_maxabs=err,
                               frame_mean=float(torch.cat(ref, 0).mean()))
         print(name, "ok", arrays["ref_frames"].shape, manifest[name]["frame_mean"])
+
+    # ---- BDE2VID architecture variants ---------------------------------------------------
+    for name, (H, W, T, N, over, wseed, sid) in VARIANT_CASES.items():
+        cfg = gen_cfg(over)
+        model = R.BDE2VID(generator=dict(cfg)).eval()
+        sd = synth.random_state_dict_like(model.state_dict(), wseed)
+        model.load_state_dict(sd, strict=True)
+        vox, prm = voxel_inputs(sid, T, H, W, N)
+        with ref_shim.cpu_mode(), torch.no_grad():
+            ref = model([{"events": v} for v in vox])
+            mine = O.bde2vid_forward(sd, cfg, vox)
+        err = max(float((a - b).abs().max()) for a, b in zip(ref, mine))
+        assert err == 0.0, (name, err)
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), ref_frames=torch.cat(ref, 0).numpy())
+        manifest[name] = dict(H=H, W=W, T=T, N=N, cfg_overrides={k: (list(v) if isinstance(v, tuple) else v) for k, v in over.items()},
+                              weight_seed=wseed, seq_id=sid, oracle_vs_reference_maxabs=err, n_keys=len(sd),
+                              keys_sha256=hashlib.sha256("\n".join(sorted(sd.keys())).encode()).hexdigest(),
+                              frame_mean=float(torch.cat(ref, 0).mean()))
+        print(name, "ok", manifest[name]["frame_mean"])
+
+    # ---- E2VIDRecurrent with ConvGRU, FireNet --------------------------------
+    from model.e2vid.model import FireNet
+    g = torch.Generator().manual_seed(6)
+    e = R.E2VIDRecurrent({"num_bins": 5, "recurrent_block_type": "convgru", "num_encoders": 3}).eval()
+    esd = synth.random_state_dict_like(e.state_dict(), 31)
+    e.load_state_dict(esd, strict=True)
+    xs = [torch.randn(2, 5, 64, 96, generator=g) for _ in range(3)]
+    frames, st = [], None
+    with torch.no_grad():
+        for x in xs:
+            r = e({"events": x})["image"]
+            a, st = O.e2vid_recurrent_forward(esd, x, st, num_encoders=3)
+            assert float((r - a).abs().max()) == 0.0
+            frames.append(r)
+    np.savez_compressed(os.path.join(GOLD, "e2vid_gru_64x96_B2_T3.npz"), ref_frames=torch.stack(frames).numpy())
+    manifest["e2vid_gru_64x96_B2_T3"] = dict(seed=31, input_seed=6, n_keys=len(esd))
+    fn = FireNet().eval()
+    fsd = synth.random_state_dict_like(fn.state_dict(), 32)
+    fn.load_state_dict(fsd, strict=True)
+    frames, st = [], None
+    with torch.no_grad():
+        for x in xs:
+            r = fn({"events": x})["image"]
+            a, st = O.firenet_forward(fsd, x, st)
+            assert float((r - a).abs().max()) == 0.0
+            frames.append(r)
+    np.savez_compressed(os.path.join(GOLD, "firenet_64x96_B2_T3.npz"), ref_frames=torch.stack(frames).numpy())
+    manifest["firenet_64x96_B2_T3"] = dict(seed=32, input_seed=6, n_keys=len(fsd), keys=sorted(fsd.keys()))
+
+    # ---- loader-side transforms: LegacyNorm / RobustNorm / hot-pixel mask -------
+    from utils_func.data_augmentation import LegacyNorm
+    from utils_func.utils import RobustNorm
+    import events_contrast_maximization.utils.event_utils as EU
+    ev = synth.gen_events(51, 2, 48, 64, 3000)
+    for w in range(2):
+        xs_, ys_, ts_, ps_ = synth.to_loader_format(ev, w)
+        v = torch.from_numpy(O.voxel_grid(xs_, ys_, ts_, ps_, 5, (48, 64)))
+        assert torch.equal(LegacyNorm()(v.clone()), O.legacy_norm(v.clone()))
+        for lo, hi in ((0, 95), (1, 99), (5, 50)):
+            assert torch.equal(RobustNorm(lo, hi)(v.clone()), O.robust_norm(v.clone(), lo, hi))
+    a0, a1 = int(ev["offsets"][0]), int(ev["offsets"][1])
+    pm = ev["ps"][a0:a1] * 2.0 - 1.0
+    ref_mask = EU.get_hot_event_mask(ev["xs"][a0:a1].astype(np.int64), ev["ys"][a0:a1].astype(np.int64), pm, (48, 64), num_hot=30)
+    assert np.array_equal(ref_mask, O.hot_event_mask(ev["xs"][a0:a1], ev["ys"][a0:a1], pm, (48, 64), 30))
+    manifest["loader_transforms"] = "LegacyNorm / RobustNorm / get_hot_event_mask: oracle bit-equal to the reference classes"
 
     # ---- E2VIDRecurrent (config 3 twin) ----------------------------------------------
     torch.manual_seed(0)

@@ -42,6 +42,8 @@ DEFAULT_CFG = dict(
     buffer_index=[-1, 0, 1], q_idx=1, window_size=(7, 7), nwindow_size=None,
     depths=[4, 0, 6], num_heads=16, losses=[],
 )
+# keys of DEFAULT_CFG that are constructor arguments of the generator (everything but 'type')
+GEN_KEYS = [k for k in DEFAULT_CFG if k != "type"]
 
 
 def full_cfg(cfg=None):
@@ -132,10 +134,20 @@ def _act(x, name):
     raise NotImplementedError(name)
 
 
+def _norm(sd, prefix, x):
+    """norm_layer of ConvLayer / UpsampleConvLayer in eval mode (submodules.py:100-111, 133-145): BatchNorm2d, or
+    InstanceNorm2d(track_running_stats=True) which then also normalises with its running statistics (no affine)."""
+    if prefix + ".norm_layer.running_mean" not in sd:
+        return x
+    return F.batch_norm(x, sd[prefix + ".norm_layer.running_mean"], sd[prefix + ".norm_layer.running_var"],
+                        sd.get(prefix + ".norm_layer.weight"), sd.get(prefix + ".norm_layer.bias"), False, 0.1, 1e-5)
+
+
 def conv_layer(sd, prefix, x, stride, act):
-    """ConvLayer (submodules.py:85-114), norm=None."""
+    """ConvLayer (submodules.py:85-114): conv2d (no bias with BN) -> optional norm -> activation."""
     w = sd[prefix + ".conv2d.weight"]
-    return _act(F.conv2d(x, w, sd[prefix + ".conv2d.bias"], stride=stride, padding=w.shape[-1] // 2), act)
+    y = F.conv2d(x, w, sd.get(prefix + ".conv2d.bias"), stride=stride, padding=w.shape[-1] // 2)
+    return _act(_norm(sd, prefix, y), act)
 
 
 def convlstm_step(sd, prefix, x, state):
@@ -153,11 +165,35 @@ def convlstm_step(sd, prefix, x, state):
     return h, c
 
 
+def convgru_step(sd, prefix, x, state):
+    """ConvGRU (submodules.py:355-375; model/submodules.py and model/e2vid/submodules.py hold the same cell)."""
+    wu = sd[prefix + ".update_gate.weight"]
+    pad = wu.shape[-1] // 2
+    if state is None:
+        state = torch.zeros(x.shape[0], wu.shape[0], x.shape[2], x.shape[3], dtype=x.dtype)
+    stacked = torch.cat([x, state], 1)
+    update = torch.sigmoid(F.conv2d(stacked, wu, sd[prefix + ".update_gate.bias"], padding=pad))
+    reset = torch.sigmoid(F.conv2d(stacked, sd[prefix + ".reset_gate.weight"], sd[prefix + ".reset_gate.bias"], padding=pad))
+    out = torch.tanh(F.conv2d(torch.cat([x, state * reset], 1), sd[prefix + ".out_gate.weight"],
+                              sd[prefix + ".out_gate.bias"], padding=pad))
+    return state * (1 - update) + out * update
+
+
+def recurrent_step(sd, prefix, x, state):
+    """recurrent_block of a RecurrentConv / RecurrentConvLayer: returns (output, new state)."""
+    if prefix + ".Gates.weight" in sd:
+        st = convlstm_step(sd, prefix, x, state)
+        return st[0], st
+    st = convgru_step(sd, prefix, x, state)
+    return st, st
+
+
 def upsample_conv(sd, prefix, x, act):
-    """UpsampleConvLayer (submodules.py:137-147): bilinear x2 (align_corners=False) then conv."""
+    """UpsampleConvLayer (submodules.py:137-147): bilinear x2 (align_corners=False), conv, optional norm, activation."""
     x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
     w = sd[prefix + ".conv2d.weight"]
-    return _act(F.conv2d(x, w, sd[prefix + ".conv2d.bias"], padding=w.shape[-1] // 2), act)
+    y = F.conv2d(x, w, sd.get(prefix + ".conv2d.bias"), padding=w.shape[-1] // 2)
+    return _act(_norm(sd, prefix, y), act)
 
 
 # --------------------------------------------------------------------------------------
@@ -204,14 +240,15 @@ def window_token_map(H, W, dilated, ws=(7, 7)):
     return idx.reshape(nH * nW, wh * ww), ok.reshape(nH * nW, wh * ww), g
 
 
-def rel_pos_bias(sd, prefix, D, wh, ww, q_ind, num_heads):
+def rel_pos_bias(sd, prefix, D, wh, ww, q_ind, num_heads, n_kv=None):
     """relative_position_bias_table gathered for the query frame's tokens
-    (DTransformer.py:139-152, 195-199) -> [nH, wh*ww, D*wh*ww]."""
+    (DTransformer.py:139-152, 195-199) -> [nH, wh*ww, N]; N = D*wh*ww, or the first N columns with nwindow_size."""
     table = sd[prefix + ".relative_position_bias_table"]
     index = sd[prefix + ".relative_position_index"]
     n = wh * ww
-    idx = index[q_ind * n:(q_ind + 1) * n, :D * n].reshape(-1)
-    return table[idx].reshape(n, D * n, num_heads).permute(2, 0, 1).contiguous()
+    N = D * n if n_kv is None else n_kv
+    idx = index[q_ind * n:(q_ind + 1) * n, :N].reshape(-1)
+    return table[idx].reshape(n, N, num_heads).permute(2, 0, 1).contiguous()
 
 
 def attention_block(sd, prefix, frames, q_ind, num_heads, dilated, ws=(7, 7)):
@@ -231,16 +268,29 @@ def attention_block(sd, prefix, frames, q_ind, num_heads, dilated, ws=(7, 7)):
 
     tok = [tokens(fr) for fr in frames]
     q_in = tok[q_ind]
-    kv_in = torch.cat(tok, dim=2)                                   # [B, nWin, D*n, C], index d*n + a*ww + b
+    if ap + ".reduction_conv.weight" in sd:
+        # "feature reduction" (DTransformer.py:128-131, 172-175): depthwise whole-window conv Conv2d(C, X*C, window, groups=C)
+        # on every (frame, window); the [C*X, 1, 1] result is VIEWED as [X, C] (index j*C + c), as the reference does
+        rw, rb = sd[ap + ".reduction_conv.weight"], sd[ap + ".reduction_conv.bias"]
+        X = rw.shape[0] // C
+        # one conv over all D frames' windows, contiguous NCHW like the reference's x.view(-1, C, H, W) (same batch layout,
+        # so that the CPU conv takes the same code path and the port stays bit-equal)
+        img = torch.stack([t.reshape(B * nWin, g["wh"], g["ww"], C).permute(0, 3, 1, 2) for t in tok], 0).contiguous()
+        red = F.conv2d(img.view(-1, C, g["wh"], g["ww"]), rw, rb, groups=C).view(D, B, nWin, X, C)
+        kv_in = red.permute(1, 2, 0, 3, 4).reshape(B, nWin, D * X, C)   # [B, nWin, D*X, C], index d*X + j
+        n_kv = D * X
+    else:
+        kv_in = torch.cat(tok, dim=2)                              # [B, nWin, D*n, C], index d*n + a*ww + b
+        n_kv = D * n
     qn = F.layer_norm(q_in, (C,), sd[ap + ".norm_q.weight"], sd[ap + ".norm_q.bias"], 1e-5)
     kvn = F.layer_norm(kv_in, (C,), sd[ap + ".norm_kv.weight"], sd[ap + ".norm_kv.bias"], 1e-5)
     q = F.linear(qn, sd[ap + ".q.weight"], sd[ap + ".q.bias"])
     kv = F.linear(kvn, sd[ap + ".kv.weight"], sd[ap + ".kv.bias"])
     q = q.reshape(B, nWin, n, num_heads, hd).permute(0, 1, 3, 2, 4) * (hd ** -0.5)
-    k = kv[..., :C].reshape(B, nWin, D * n, num_heads, hd).permute(0, 1, 3, 2, 4)
-    v = kv[..., C:].reshape(B, nWin, D * n, num_heads, hd).permute(0, 1, 3, 2, 4)
+    k = kv[..., :C].reshape(B, nWin, n_kv, num_heads, hd).permute(0, 1, 3, 2, 4)
+    v = kv[..., C:].reshape(B, nWin, n_kv, num_heads, hd).permute(0, 1, 3, 2, 4)
     attn = q @ k.transpose(-2, -1)
-    attn = attn + rel_pos_bias(sd, ap, D, g["wh"], g["ww"], q_ind, num_heads).view(1, 1, num_heads, n, D * n)
+    attn = attn + rel_pos_bias(sd, ap, D, g["wh"], g["ww"], q_ind, num_heads, n_kv).view(1, 1, num_heads, n, n_kv)
     attn = torch.softmax(attn, dim=-1)
     o = (attn @ v).permute(0, 1, 3, 2, 4).reshape(B, nWin, n, C)
     o = F.linear(o, sd[ap + ".proj.weight"], sd[ap + ".proj.bias"])
@@ -273,22 +323,20 @@ def dframe_attention(sd, prefix, frames, depth, q_ind, num_heads, ws=(7, 7)):
 # --------------------------------------------------------------------------------------
 
 def _check_cfg(cfg):
-    if cfg["norm"] not in (None, "none"):
+    if cfg["norm"] not in (None, "none", "BN", "IN"):
         raise NotImplementedError("norm=%r" % (cfg["norm"],))
-    if cfg["recurrent_block_type"] != "convlstm" or not cfg["useRC"]:
-        raise NotImplementedError("only useRC=True with convlstm is restated")
-    if cfg["skip_type"] != "sum":
-        raise NotImplementedError("skip_type=%r" % (cfg["skip_type"],))
-    if cfg["nwindow_size"] is not None:
-        raise NotImplementedError("nwindow_size")
-    if cfg["depths"][-1] == 0:
-        raise NotImplementedError("last-level depth 0 (ParseLayer path)")
+    if cfg["recurrent_block_type"] not in ("convlstm", "convgru"):
+        raise NotImplementedError("recurrent_block_type=%r" % (cfg["recurrent_block_type"],))
+    if cfg["skip_type"] not in ("sum", "concat"):
+        raise NotImplementedError("skip_type=%r (no_skip crashes in the reference too)" % (cfg["skip_type"],))
 
 
 def bde2vid_forward(sd, cfg, voxels, prefix="generator", taps=None):
     """voxels: list over time of [B, num_bins, Hp, Wp] fp32.  Returns list of [B, 1, Hp, Wp].
 
-    ``taps`` (optional dict) receives intermediate tensors for stage-level parity tests."""
+    ``taps`` (optional dict) receives intermediate tensors for stage-level parity tests.  The architecture variant
+    (norm layers, ConvGRU, useRC=False, reduction conv, residual tail, concat skips) is read off the state_dict keys, as
+    SURVEY.md appendix B describes; ``cfg`` supplies what has no parameters (buffer_index, q_idx, depths, heads, ...)."""
     cfg = full_cfg(cfg)
     _check_cfg(cfg)
     T = len(voxels)
@@ -297,6 +345,8 @@ def bde2vid_forward(sd, cfg, voxels, prefix="generator", taps=None):
     q_ind = cfg["q_idx"]
     act = "ReLU" if cfg["act_net"] == "default" else cfg["act_net"]
     p = prefix + "." if prefix else ""
+    use_rc = cfg.get("useRC", True)
+    concat = cfg["skip_type"] == "concat"
 
     head = [conv_layer(sd, p + "head", v, 1, act) for v in voxels]                     # :116
     if taps is not None:
@@ -308,22 +358,33 @@ def bde2vid_forward(sd, cfg, voxels, prefix="generator", taps=None):
         sf = sb = None
         for k in range(T):                                                              # :122-135
             kb = T - 1 - k
-            ef = conv_layer(sd, p + "forward_encoder.%d.conv" % l, x_seq[k], 2, act)
-            sf = convlstm_step(sd, p + "forward_encoder.%d.recurrent_block" % l, ef, sf)
-            fwd[k] = sf[0]
-            eb = conv_layer(sd, p + "backward_encoder.%d.conv" % l, x_seq[kb], 2, act)
-            sb = convlstm_step(sd, p + "backward_encoder.%d.recurrent_block" % l, eb, sb)
-            bwd[kb] = sb[0]
+            if use_rc:
+                ef = conv_layer(sd, p + "forward_encoder.%d.conv" % l, x_seq[k], 2, act)
+                fwd[k], sf = recurrent_step(sd, p + "forward_encoder.%d.recurrent_block" % l, ef, sf)
+                eb = conv_layer(sd, p + "backward_encoder.%d.conv" % l, x_seq[kb], 2, act)
+                bwd[kb], sb = recurrent_step(sd, p + "backward_encoder.%d.recurrent_block" % l, eb, sb)
+            else:                                                                       # Encoder(), :255-257: ConvLayer only
+                fwd[k] = conv_layer(sd, p + "forward_encoder.%d" % l, x_seq[k], 2, act)
+                bwd[kb] = conv_layer(sd, p + "backward_encoder.%d" % l, x_seq[kb], 2, act)
         merged = [fwd[t] + bwd[t] for t in range(T)]                                    # :137-147
         if taps is not None:
             taps["merged%d" % l] = list(merged)
         depth = cfg["depths"][l]
-        if depth > 0:                                                                   # :151-169
+        tail = l == L - 1 and depth == 0                                                # :77-80
+        if depth > 0 or tail:                                                           # :151-169
             zero = torch.zeros_like(merged[0])
             for t in range(T):
                 frames = [merged[t + o] if 0 <= t + o < T else zero for o in buf]       # Q1/Q4
-                x = dframe_attention(sd, p + "feat_attns.%d" % l, frames, depth, q_ind, cfg["num_heads"],
-                                     tuple(cfg["window_size"]))
+                if tail:
+                    # ParseLayer (x[0]) + ResidualBlockNoBN x num_res_blocks (:261-282), quirk Q5
+                    x = frames[0]
+                    for r in range(cfg["num_res_blocks"]):
+                        rp = p + "feat_attns.%d.%d" % (l, r + 1)
+                        y = _act(F.conv2d(x, sd[rp + ".conv1.weight"], sd[rp + ".conv1.bias"], padding=1), act)
+                        x = x + F.conv2d(y, sd[rp + ".conv2.weight"], sd[rp + ".conv2.bias"], padding=1)
+                else:
+                    x = dframe_attention(sd, p + "feat_attns.%d" % l, frames, depth, q_ind, cfg["num_heads"],
+                                         tuple(cfg["window_size"]))
                 merged[t] = x + merged[t]
         if taps is not None:
             taps["level%d" % l] = list(merged)
@@ -335,9 +396,19 @@ def bde2vid_forward(sd, cfg, voxels, prefix="generator", taps=None):
     for t in range(T):                                                                  # :183-197
         x = skips[-1][t]
         for i in range(L):
-            x = upsample_conv(sd, p + "decoders.%d.1" % i, skips[-2 - i][t] + x, "ReLU6")
-        x = x + head[t]
-        img = torch.sigmoid(F.conv2d(x, sd[p + "predI.1.weight"], sd[p + "predI.1.bias"]))
+            if concat:                                                                  # skip_concat + fusion conv (:86-93)
+                x = torch.cat([skips[-2 - i][t], x], 1)
+                x = F.conv2d(x, sd[p + "decoders.%d.0.weight" % i], sd[p + "decoders.%d.0.bias" % i])
+            else:
+                x = skips[-2 - i][t] + x
+            x = upsample_conv(sd, p + "decoders.%d.1" % i, x, "ReLU6")
+        if concat:
+            x = F.conv2d(torch.cat([x, head[t]], 1), sd[p + "predI.0.weight"], sd[p + "predI.0.bias"])
+        else:
+            x = x + head[t]
+        img = F.conv2d(x, sd[p + "predI.1.weight"], sd[p + "predI.1.bias"])
+        if dict(cfg["activation"] or {}).get("type", "Sigmoid") == "Sigmoid":
+            img = torch.sigmoid(img)
         out.append(img)
     return out
 
@@ -347,7 +418,7 @@ def bde2vid_forward(sd, cfg, voxels, prefix="generator", taps=None):
 # --------------------------------------------------------------------------------------
 
 def e2vid_recurrent_forward(sd, x, prev_states, num_encoders=4, num_residual_blocks=2, prefix="unetrecurrent"):
-    """One step: x [B, bins, H, W], prev_states list of (h, c) or None -> (img, states)."""
+    """One step: x [B, bins, H, W], prev_states list of states (ConvLSTM (h, c) / ConvGRU h) or None -> (img, states)."""
     p = prefix + "." if prefix else ""
     x = conv_layer(sd, p + "head", x, 1, "relu")
     head = x
@@ -356,19 +427,101 @@ def e2vid_recurrent_forward(sd, x, prev_states, num_encoders=4, num_residual_blo
     blocks, states = [], []
     for i in range(num_encoders):
         x = conv_layer(sd, p + "encoders.%d.conv" % i, x, 2, "relu")
-        st = convlstm_step(sd, p + "encoders.%d.recurrent_block" % i, x, prev_states[i])
-        x = st[0]
+        x, st = recurrent_step(sd, p + "encoders.%d.recurrent_block" % i, x, prev_states[i])
         blocks.append(x)
         states.append(st)
     for r in range(num_residual_blocks):                       # ResidualBlock e2vid/submodules.py:212-247
-        rp = p + "resblocks.%d" % r
-        y = F.relu(F.conv2d(x, sd[rp + ".conv1.weight"], sd[rp + ".conv1.bias"], padding=1))
-        y = F.conv2d(y, sd[rp + ".conv2.weight"], sd[rp + ".conv2.bias"], padding=1)
-        x = F.relu(y + x)
+        x = residual_block(sd, p + "resblocks.%d" % r, x)
     for i in range(num_encoders):
         x = upsample_conv(sd, p + "decoders.%d" % i, x + blocks[num_encoders - 1 - i], "relu")
     img = torch.sigmoid(F.conv2d(x + head, sd[p + "pred.conv2d.weight"], sd[p + "pred.conv2d.bias"]))
     return img, states
+
+
+def residual_block(sd, prefix, x):
+    """ResidualBlock with norm=None (model/submodules.py / model/e2vid/submodules.py:212-247): relu(conv2(relu(conv1 x)) + x)."""
+    y = F.relu(F.conv2d(x, sd[prefix + ".conv1.weight"], sd[prefix + ".conv1.bias"], padding=1))
+    y = F.conv2d(y, sd[prefix + ".conv2.weight"], sd[prefix + ".conv2.bias"], padding=1)
+    return F.relu(y + x)
+
+
+def firenet_forward(sd, x, states):
+    """FireNet.forward (model/e2vid/model.py:119-172): head -> G1 (ConvGRU) -> R1 -> G2 -> R2 -> pred (1x1, no activation)."""
+    if states is None:
+        states = [None, None]
+    x = conv_layer(sd, "head", x, 1, "relu")
+    s1 = convgru_step(sd, "G1", x, states[0])
+    x = residual_block(sd, "R1", s1)
+    s2 = convgru_step(sd, "G2", x, states[1])
+    x = residual_block(sd, "R2", s2)
+    img = F.conv2d(x, sd["pred.conv2d.weight"], sd["pred.conv2d.bias"])
+    return img, [s1, s2]
+
+
+# --------------------------------------------------------------------------------------
+# loader-side voxel transforms (SURVEY.md 8(f2), 8(f3))
+# --------------------------------------------------------------------------------------
+
+def loader_window(xs_i16, ys_i16, ts_f64, ps_bool):
+    """DynamicH5Dataset.get_events + __getitem__ conversions (h5_dataset.py:410-415, :222-225) of one window given in the
+    on-disk dtypes: ps * 2.0 - 1.0, float32 casts, ts - ts[0] in float64 before the cast."""
+    ps = ps_bool * 2.0 - 1.0
+    ts0 = ts_f64[0]
+    return (xs_i16.astype(np.float32), ys_i16.astype(np.float32), (ts_f64 - ts0).astype(np.float32), ps.astype(np.float32))
+
+
+def loader_voxel(xs_i16, ys_i16, ts_f64, ps_bool, num_bins, sensor_size, hot_mask=None):
+    """__getitem__'s voxel (h5_dataset.py:219-226, :357-364): fewer than 3 events -> zeros; else the voxel grid times the
+    hot-pixel mask."""
+    if len(xs_i16) < 3:
+        return np.zeros((num_bins,) + tuple(sensor_size), dtype=np.float32)
+    g = voxel_grid(*loader_window(xs_i16, ys_i16, ts_f64, ps_bool), num_bins, sensor_size)
+    if hot_mask is not None:
+        g = g * hot_mask[None].astype(np.float32)
+    return g
+
+
+def legacy_norm(x):
+    """LegacyNorm.__call__ (utils_func/data_augmentation.py:316-330) on a float32 tensor."""
+    x = torch.as_tensor(x)
+    nonzero = (x != 0)
+    num_nonzeros = nonzero.sum()
+    if num_nonzeros > 0:
+        mean = x.sum() / num_nonzeros
+        stddev = torch.sqrt((x ** 2).sum() / num_nonzeros - mean ** 2)
+        if stddev != 0:
+            mask = nonzero.float()
+            x = mask * (x - mean) / stddev
+    return x
+
+
+def robust_norm(x, low_perc=0, top_perc=95):
+    """RobustNorm.__call__ (utils_func/utils.py:17-51): nearest-rank percentiles via kthvalue, clamp, rescale."""
+    x = torch.as_tensor(x)
+
+    def percentile(t, q):
+        k = 1 + round(.01 * float(q) * (t.numel() - 1))
+        return t.reshape(-1).kthvalue(k).values.item()
+
+    t_max = percentile(x, top_perc)
+    t_min = percentile(x, low_perc)
+    if t_max == 0 and t_min == 0:
+        return x
+    normed = torch.clamp(x, min=t_min, max=t_max)
+    return (normed - torch.min(normed)) / (torch.max(normed) + 1e-6)
+
+
+def hot_event_mask(xs, ys, ps, sensor_size, num_hot):
+    """get_hot_event_mask (event_utils.py:100-116) with events_to_image's bincount accumulation (:155-174); ps = +-1."""
+    H, W = sensor_size
+    img = np.bincount(np.asarray(ys, dtype=np.int64) * W + np.asarray(xs, dtype=np.int64), weights=np.asarray(ps, dtype=np.float64),
+                      minlength=H * W).reshape(H, W)
+    mask = np.ones_like(img)
+    for _ in range(num_hot):
+        idx = np.unravel_index(np.argmax(img), img.shape)
+        mask[idx] = 0
+        img[idx] = 0
+    return mask
 
 
 # --------------------------------------------------------------------------------------

@@ -40,14 +40,51 @@ def test_checkpoint_loading_path_and_key_compat():
 
 
 def test_unsupported_configs_raise_not_fallback():
+    """What the sm_100a path does not build raises at construction (never a CPU path); every architecture option of
+    the reference constructor that IS built constructs."""
     base = dict(Config.fromstring(synth.ASSUMED_CFG_STR, ".py").model["generator"])
-    for bad in (dict(norm="BN"), dict(recurrent_block_type="convgru"), dict(skip_type="concat"),
-                dict(nwindow_size=(3, 3)), dict(depths=[4, 0, 0])):
+    for bad in (dict(norm="GN"), dict(skip_type="no_skip"), dict(num_output_channels=3), dict(act_net="ELU"),
+                dict(activation=dict(type="LReLU"))):
         with pytest.raises(NotImplementedError):
             BDE2VID(generator=dict(base, **bad))
+    for ok in (dict(norm="BN"), dict(norm="IN"), dict(recurrent_block_type="convgru"), dict(skip_type="concat"),
+               dict(nwindow_size=(3, 3)), dict(depths=[4, 0, 0]), dict(useRC=False), dict(activation=dict(type="Identity"))):
+        BDE2VID(generator=dict(base, **ok))
     m = BDE2VID(generator=base)
     with pytest.raises(NotImplementedError):
         m([], mode="loss")
+
+
+def test_plan_cache_is_bounded():
+    """Engine.plans is an LRU bounded in bytes (the driver with subseq_L=None calls the model with a new T per file)."""
+    from collections import OrderedDict
+    from bde2vid_b200.engine import Engine
+
+    class P:
+        def __init__(self, n):
+            self.nbytes, self.released = n, False
+
+        def release(self):
+            self.released = True
+
+    eng = Engine.__new__(Engine)
+    eng.plans, eng.plan_cache_bytes = OrderedDict(), 250
+    made = []
+    import bde2vid_b200.engine as E
+    orig = E._Plan
+    E._Plan = lambda e, T, B, Hp, Wp: made.append(P(100)) or made[-1]
+    try:
+        a = eng.plan(1, 1, 8, 8)
+        b = eng.plan(2, 1, 8, 8)
+        assert eng.plan(1, 1, 8, 8) is a                     # hit: moves to the MRU end
+        c = eng.plan(3, 1, 8, 8)                             # 300 bytes > 250: evicts the LRU entry (b)
+        assert b.released and not a.released and not c.released
+        assert list(eng.plans.keys()) == [(1, 1, 8, 8, 0), (3, 1, 8, 8, 0)]
+        eng.plan_cache_bytes = 50
+        d = eng.plan(4, 1, 8, 8)                             # a single plan larger than the budget still lives
+        assert list(eng.plans.values()) == [d] and a.released and c.released
+    finally:
+        E._Plan = orig
 
 
 @pytest.mark.parametrize("H,W", [(12, 20), (9, 13), (7, 30), (33, 44), (132, 176)])

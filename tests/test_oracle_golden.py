@@ -8,7 +8,7 @@ import torch
 from bde2vid_b200 import synth
 from conftest import load_golden
 from oracle import oracle_torch as O
-from oracle.make_golden import MODEL_CASES, sub, voxel_inputs
+from oracle.make_golden import MODEL_CASES, VARIANT_CASES, gen_cfg, sub, voxel_inputs
 
 
 def test_voxel_small_bit_exact():
@@ -86,3 +86,68 @@ def test_e2vid_forward_matches_reference(manifest):
         for i, x in enumerate(xs):
             img, st = O.e2vid_recurrent_forward(sd, x, st)
             assert np.abs(img.numpy() - g["ref_frames"][i]).max() <= 2e-6
+
+
+@pytest.mark.parametrize("name", list(VARIANT_CASES))
+def test_variant_forward_matches_reference(manifest, name):
+    """Architecture variants (ConvGRU, concat skips, BN / IN, nwindow_size, residual tail, useRC=False): the oracle on
+    weights regenerated from the seed against the frames the unmodified reference produced; the drop-in container must
+    expose exactly the reference's state_dict key set (sha256 of the sorted keys recorded by make_golden)."""
+    from bde2vid_b200.model import BDE2VID
+    H, W, T, N, over, wseed, sid = VARIANT_CASES[name]
+    g = load_golden(name)
+    cfg = gen_cfg(over)
+    model = BDE2VID(generator=dict(cfg))
+    sd = synth.random_state_dict_like(model.state_dict(), wseed)
+    model.load_state_dict(sd, strict=True)
+    assert len(sd) == manifest[name]["n_keys"]
+    assert hashlib.sha256("\n".join(sorted(sd.keys())).encode()).hexdigest() == manifest[name]["keys_sha256"]
+    vox, _ = voxel_inputs(sid, T, H, W, N)
+    with torch.no_grad():
+        frames = torch.cat(O.bde2vid_forward(sd, cfg, vox), 0).numpy()
+    assert np.abs(frames - g["ref_frames"]).max() <= 2e-6
+
+
+def test_e2vid_gru_and_firenet_match_reference(manifest):
+    from bde2vid_b200.e2vid import E2VIDRecurrent, FireNet
+    gen = torch.Generator().manual_seed(manifest["e2vid_gru_64x96_B2_T3"]["input_seed"])
+    xs = [torch.randn(2, 5, 64, 96, generator=gen) for _ in range(3)]
+    e = E2VIDRecurrent({"num_bins": 5, "recurrent_block_type": "convgru", "num_encoders": 3})
+    esd = synth.random_state_dict_like(e.state_dict(), manifest["e2vid_gru_64x96_B2_T3"]["seed"])
+    e.load_state_dict(esd, strict=True)
+    g = load_golden("e2vid_gru_64x96_B2_T3")
+    st = None
+    with torch.no_grad():
+        for i, x in enumerate(xs):
+            img, st = O.e2vid_recurrent_forward(esd, x, st, num_encoders=3)
+            assert np.abs(img.numpy() - g["ref_frames"][i]).max() <= 2e-6
+    f = FireNet()
+    fsd = synth.random_state_dict_like(f.state_dict(), manifest["firenet_64x96_B2_T3"]["seed"])
+    f.load_state_dict(fsd, strict=True)
+    assert sorted(fsd.keys()) == manifest["firenet_64x96_B2_T3"]["keys"]
+    g = load_golden("firenet_64x96_B2_T3")
+    st = None
+    with torch.no_grad():
+        for i, x in enumerate(xs):
+            img, st = O.firenet_forward(fsd, x, st)
+            assert np.abs(img.numpy() - g["ref_frames"][i]).max() <= 2e-6
+
+
+def test_loader_contract_and_transforms():
+    """h5_dataset.py:219-226: fewer than 3 events -> zeros; raw dtypes converted like the loader; LegacyNorm / RobustNorm
+    known answers (the oracle functions are bit-equal to the reference classes: make_golden asserts it)."""
+    ev = synth.gen_events(5, 1, 20, 30, 50)
+    a, b = 0, 50
+    raw = (ev["xs"][a:b], ev["ys"][a:b], ev["ts"][a:b], ev["ps"][a:b])
+    v = O.loader_voxel(*raw, 5, (20, 30))
+    assert np.array_equal(v, O.voxel_grid(*synth.to_loader_format(ev, 0), 5, (20, 30)))
+    for n in (0, 1, 2):
+        assert not O.loader_voxel(*(r[:n] for r in raw), 5, (20, 30)).any()
+    assert O.loader_voxel(*(r[:3] for r in raw), 5, (20, 30)).any()
+    x = torch.tensor([0., 2., 0., 4.])
+    assert torch.allclose(O.legacy_norm(x), torch.tensor([0., -1., 0., 1.]))
+    assert torch.equal(O.legacy_norm(torch.zeros(4)), torch.zeros(4))
+    y = O.robust_norm(torch.arange(101, dtype=torch.float32), 0, 95)
+    assert float(y.max()) == pytest.approx(95.0 / (95.0 + 1e-6)) and float(y.min()) == 0.0
+    m = O.hot_event_mask(np.array([1, 1, 2]), np.array([0, 0, 1]), np.array([1., 1., 1.]), (2, 3), 1)
+    assert m[0, 1] == 0 and m.sum() == 5

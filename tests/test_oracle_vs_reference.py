@@ -31,3 +31,33 @@ def test_bde2vid_vs_reference_and_strict_load():
         ref = model([{"events": v} for v in vox])
         mine = O.bde2vid_forward(sd, cfg, vox)
     assert max(float((a - b).abs().max()) for a, b in zip(ref, mine)) == 0.0
+
+
+@pytest.mark.parametrize("over", [dict(recurrent_block_type="convgru", skip_type="concat", depths=[1, 0, 0], num_res_blocks=1),
+                                  dict(norm="BN", nwindow_size=(2, 3), depths=[1, 0, 1], useRC=False)])
+def test_variants_vs_reference_live(over):
+    """Fresh variant cfgs (not the ones in tests/golden): strict load of our container's keys into the reference model,
+    oracle bit-equal to the reference forward."""
+    from bde2vid_b200.model import BDE2VID
+    R = ref_shim.reference_modules()
+    cfg = O.full_cfg(over)
+    ours = BDE2VID(generator=dict(cfg))
+    sd = synth.random_state_dict_like(ours.state_dict(), 77)
+    model = R.BDE2VID(generator=dict(cfg)).eval()
+    model.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(4)
+    vox = [torch.randn(1, 5, 56, 64, generator=g) for _ in range(3)]
+    with ref_shim.cpu_mode(), torch.no_grad():
+        ref = model([{"events": v} for v in vox])
+        mine = O.bde2vid_forward(sd, cfg, vox)
+    assert max(float((a - b).abs().max()) for a, b in zip(ref, mine)) == 0.0
+
+
+def test_loader_transforms_vs_reference_live():
+    ref_shim.install()
+    from utils_func.data_augmentation import LegacyNorm
+    from utils_func.utils import RobustNorm
+    ev = synth.gen_events(61, 1, 40, 56, 2500)
+    v = torch.from_numpy(O.voxel_grid(*synth.to_loader_format(ev, 0), 5, (40, 56)))
+    assert torch.equal(LegacyNorm()(v.clone()), O.legacy_norm(v.clone()))
+    assert torch.equal(RobustNorm(2, 98)(v.clone()), O.robust_norm(v.clone(), 2, 98))
