@@ -550,7 +550,7 @@ static int launch_atomic(const Src& src, bool agg, const int64_t* offsets, int T
     const long v = atol(e);
     if (v > 0) chunk_mb = (size_t)v;
   }
-  int per_chunk = (int)((chunk_mb << 20) / (out_window_stride * sizeof(float)));
+  int per_chunk = (int)((chunk_mb << 20) / (grid_elems * sizeof(float)));   // L2 footprint of a window = its grid, not the stride
   per_chunk = per_chunk < 1 ? 1 : (per_chunk > T ? T : per_chunk);
   int n_sm = kNumSMs;
   {

@@ -30,6 +30,9 @@ H, W, NEV, BINS = 260, 346, 31500, 5
 # are executed by the implicit-GEMM kernel, bmm FLOPs by the window-attention kernel.
 GF_CONV, GF_LINEAR, GF_BMM = 125.79, 32.36, 5.19
 VOXEL_BYTES_PER_WINDOW = 16 * NEV + 4 * BINS * H * W
+# dram__bytes_read.sum + dram__bytes_write.sum of the voxeliser (memset + reduction kernels) from the committed ncu capture;
+# filled in from profiles/ once measured (None = not captured for this build)
+VOXEL_TRAFFIC = {}
 
 
 def cfg_dict():
@@ -97,48 +100,91 @@ class ClockSampler:
 # CPU arm: the oracle port of the reference path on the host cores (bounded sample)
 # ------------------------------------------------------------------------------------------------
 
-def cpu_reference_fps(T_sample, seq_id=0, threads=None):
-    """frames/s of voxelise (numpy restatement) + oracle forward (functional torch, fp32) for T_sample
-    windows of the bench workload.  This is the reference algorithm on the CPU ('port')."""
+def reference_model_or_none(cfg):
+    """The UNMODIFIED reference (BDE2VID from /root/reference or baseline/_ref, imported through oracle/ref_shim.py) when
+    its tree is reachable at run time -- it is in the build container, it is not on the GPU box -- else None."""
+    for root in (os.environ.get("BDE2VID_REFERENCE"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if root and os.path.isdir(os.path.join(root, "model", "BDE2VID")):
+            try:
+                os.environ["BDE2VID_REFERENCE"] = root
+                from oracle import ref_shim
+                ref_shim.REFERENCE_ROOT = root
+                R = ref_shim.reference_modules()
+                return R, ref_shim
+            except Exception as e:          # missing third-party import etc.: fall back to the port, say why
+                sys.stderr.write("reference at %s not importable (%s); timing the oracle port\n" % (root, e))
+    return None, None
+
+
+def cpu_reference_fps(T_sample, seq_id=0, threads=None, h=H, w=W, nev=NEV, return_frames=False):
+    """frames/s of voxelise + forward on the host cores for T_sample windows of the bench workload: the reference's own
+    code when its tree is present ('reference'), else the oracle port of the same algorithm ('port': numpy voxeliser +
+    functional torch fp32)."""
     from oracle import oracle_torch as O
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
     cfg = O.full_cfg(cfg_dict()["generator"])
     sd = synth.init_state_dict(cfg, 0)
-    ev = synth.gen_events(seq_id, T_sample, H, W, NEV)
-    prm = O.croper_params(W, H, 3)
+    ev = synth.gen_events(seq_id, T_sample, h, w, nev)
+    prm = O.croper_params(w, h, 3)
+    R, shim = reference_model_or_none(cfg)
+    kind = "port"
+    if R is not None:
+        kind = "reference"
+        model = R.BDE2VID(generator=dict(cfg)).eval()
+        model.load_state_dict(sd, strict=True)
+        crop = R.Croper(3)
+        crop.update_params(w, h)
     t0 = time.perf_counter()
     vox = []
-    for w in range(T_sample):
-        xs, ys, ts, ps = synth.to_loader_format(ev, w)
-        vox.append(O.pad_voxel(torch.from_numpy(O.voxel_grid(xs, ys, ts, ps, BINS, (H, W)))[None], prm))
+    for wi in range(T_sample):
+        xs, ys, ts, ps = synth.to_loader_format(ev, wi)
+        if R is not None:
+            v = R.events_to_voxel_torch(*(torch.from_numpy(a) for a in (xs, ys, ts, ps)), BINS, sensor_size=(h, w))
+            vox.append(crop.pad(v[None]))
+        else:
+            vox.append(O.pad_voxel(torch.from_numpy(O.voxel_grid(xs, ys, ts, ps, BINS, (h, w)))[None], prm))
     with torch.no_grad():
-        out = O.bde2vid_forward(sd, cfg, vox)
-    _ = [O.crop_image(o, prm) for o in out]
+        if R is not None:
+            with shim.cpu_mode():
+                out = model([{"events": v} for v in vox])
+        else:
+            out = O.bde2vid_forward(sd, cfg, vox)
+    frames = [O.crop_image(o, prm) for o in out]
     dt = time.perf_counter() - t0
-    return T_sample / dt, dt, threads
+    if return_frames:
+        return T_sample / dt, dt, threads, kind, torch.cat(frames, 0)
+    return T_sample / dt, dt, threads, kind
 
 
 def run_reference_arm(args, rank, world):
+    """`--impl reference`: the reference's CPU implementation of the path on the box's host cores (all threads), on a
+    bounded sample of the same workload.  Rank 0 alone works; the other ranks exit."""
     if rank != 0:
         return
-    T_s = args.ref_windows
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_fps(2)
-    times = []
-    for _ in range(max(1, min(args.steps, 3))):
-        fps, dt, threads = cpu_reference_fps(T_s)
-        times.append(dt)
+    if args.full_cpu:
+        # SURVEY 8(d) C1: one 240x180 sequence, T = 100, voxelise + model end to end
+        fps, dt, threads, kind = cpu_reference_fps(100, h=180, w=240, nev=15000)
+        T_s, times, sample = 100, [dt], "C1: 100 of 100 windows of one 240x180 sequence (BASELINE.json configs[0])"
+    else:
+        T_s = args.ref_windows
+        for _ in range(max(0, min(args.warmup, 1))):
+            cpu_reference_fps(2)
+        times = []
+        for _ in range(max(1, min(args.steps, 3))):
+            fps, dt, threads, kind = cpu_reference_fps(T_s)
+            times.append(dt)
+        sample = "%d of %d windows of one 346x260 sequence" % (T_s, args.windows)
     dt = float(np.mean(times))
     val = T_s / dt
+    what = ("the unmodified reference imported from its tree" if kind == "reference"
+            else "oracle port of the reference path; the reference tree is not on this box")
     line = {
         "impl": "reference", "metric": "reconstructed frames/s (346x260, 5-bin)", "value": val, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, T_s, note="CPU arm: bounded sample of the same workload"),
-        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": "%d of %d windows of one 346x260 sequence (oracle port of the reference path; the "
-                                   "reference itself cannot travel to the GPU box)" % (T_s, args.windows)},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": threads, "kind": kind, "sample": "%s (%s)" % (sample, what)},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -173,6 +219,10 @@ def main():
     ap.add_argument("--windows", type=int, default=100, help="T: windows (= frames) per sequence")
     ap.add_argument("--ref-windows", type=int, default=6, help="windows of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-cpu", action="store_true", help="CPU arm / cpu_baseline on SURVEY's C1: 240x180, T=100, whole sequence")
+    ap.add_argument("--config", default="default", choices=["default", "e2vid16", "gen4", "shard64"],
+                    help="default = BASELINE.json configs[1] (the headline); e2vid16 = configs[2]; shard64 = configs[3]; gen4 = configs[4]")
+    ap.add_argument("--no-single", action="store_true", help="skip the extra one-sequence-in-flight measurement")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--concurrent", type=int, default=3, help="CUDA streams (independent model calls in flight) per GPU")
     ap.add_argument("--batch", type=int, default=4, help="independent sequences batched into each model call")
@@ -201,6 +251,14 @@ def main():
 
     warm = max(3, args.warmup)
     T = args.windows
+    if args.config != "default":
+        import bench_configs
+        line = getattr(bench_configs, "run_" + args.config)(args, rank, world, dev)
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     model = MODELS.build(cfg_dict())
     model.load_state_dict(synth.init_state_dict(cfg_dict()["generator"], 0), strict=True)
     model = model.eval().to(dev)
@@ -348,16 +406,51 @@ def main():
         torch.cuda.synchronize()
         vms = s.elapsed_time(e) / 10
         vach = VOXEL_BYTES_PER_WINDOW * T / (vms * 1e-3) / 1e9
-        voxel_roof = {"kernel": "voxel_atomic_kernel (grid memset + global RED.ADD.F32, executed by L2)", "bound": "hbm", "achieved": vach, "peak": pk["hbm"], "unit": "GB/s",
-                      "frac": vach / pk["hbm"], "traffic": None, "ms_per_launch": vms,
+        voxel_roof = {"kernel": "voxel_atomic_kernel (grid memset + global RED.ADD.F32 executed by L2, in L2-sized chunks of "
+                                "windows; 128-bit event loads)", "bound": "hbm", "achieved": vach, "peak": pk["hbm"], "unit": "GB/s",
+                      "frac": vach / pk["hbm"], "traffic": VOXEL_TRAFFIC.get("bytes_per_100_windows"),
+                      "traffic_source": VOXEL_TRAFFIC.get("source"), "ms_per_launch": vms,
                       "bytes_per_launch": VOXEL_BYTES_PER_WINDOW * T}
 
+    # one sequence in flight (BASELINE.json configs[1] says "batch 1"): the strict single-sequence rate, reported beside
+    # the batched headline
+    single = None
+    if not args.no_single and (S, NB) != (1, 1):
+        def step_single(i):
+            return model.reconstruct_events_batch([resident[i % n_seq]], (H, W), slot=0)
+        with torch.no_grad():
+            for i in range(3):
+                step_single(i)
+            ms1 = timed(step_single, 3)
+        single = {"value": world * 3 * T / (ms1 * 1e-3), "unit": "frames/s", "streams": 1, "sequences_per_call": 1,
+                  "ms_per_sequence": ms1 / 3}
+
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, threads = cpu_reference_fps(args.ref_windows)
-        cpu = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": "%d of %d windows of the same 346x260 sequence, oracle port (numpy voxeliser + functional torch "
-                         "fp32), %.1f s" % (args.ref_windows, T, dt)}
+        if args.full_cpu:
+            v, dt, threads, kind = cpu_reference_fps(100, h=180, w=240, nev=15000)
+            cpu = {"value": v, "unit": "frames/s", "cores": threads, "kind": kind,
+                   "sample": "SURVEY C1: 100 of 100 windows of one 240x180 sequence, voxelise + model, %.1f s" % dt}
+        else:
+            Ts = args.ref_windows
+            v, dt, threads, kind, ref_frames = cpu_reference_fps(Ts, seq_id=0, return_frames=True)
+            cpu = {"value": v, "unit": "frames/s", "cores": threads, "kind": kind,
+                   "sample": "%d of %d windows of the same 346x260 sequence, %s, %.1f s"
+                             % (Ts, T, "the unmodified reference" if kind == "reference" else
+                                "oracle port (numpy voxeliser + functional torch fp32)", dt)}
+            # parity of the TIMED path in the same run: the same Ts windows through reconstruct_events_batch with the bench's
+            # batch size (same kernels / dispatch as the timed steps: B = NB sequences, CUDA graph) vs the CPU frames
+            seqs = []
+            for b in range(NB):
+                evb = synth.gen_events(b, Ts, H, W, NEV)
+                seqs.append([torch.from_numpy(a).to(dev) for a in synth.to_loader_format_seq(evb)])
+            with torch.no_grad():
+                for _ in range(3):
+                    outp = model.reconstruct_events_batch(seqs, (H, W), slot=0)
+            got = torch.cat(outp[0], 0).cpu()
+            parity = {"max_abs": float((got - ref_frames).abs().max()), "mse": float(((got - ref_frames) ** 2).mean()),
+                      "frames": Ts, "batch": NB, "vs": kind, "gate": 2e-3}
 
     if rank == 0:
         line = {
@@ -371,6 +464,8 @@ def main():
             "clocks": clocks, "roofline": roofline, "roofline_voxeliser": voxel_roof, "cpu_baseline": cpu,
             "tflops_algorithmic": fps / world * (GF_CONV + GF_LINEAR + GF_BMM) / 1e3,
             "frame_checksum": chk, "precision": args.precision,
+            "single_sequence": single, "parity": parity,
+            "parity_max_abs": None if parity is None else parity["max_abs"],
         }
         print(json.dumps(line))
     if world > 1:

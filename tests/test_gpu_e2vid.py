@@ -75,7 +75,62 @@ def test_e2vid_states_and_reset(manifest, precision):
 def test_e2vid_rejects_cpu_and_unsupported():
     from bde2vid_b200.e2vid import E2VIDRecurrent
     with pytest.raises(NotImplementedError):
-        E2VIDRecurrent({"num_bins": 5, "recurrent_block_type": "convgru"})
+        E2VIDRecurrent({"num_bins": 5, "norm": "BN"})
     m = E2VIDRecurrent({"num_bins": 5}).eval()
     with pytest.raises(RuntimeError):
         m({"events": torch.zeros(1, 5, 32, 32)})
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_e2vid_convgru_golden_frames(manifest, precision):
+    """E2VIDRecurrent with recurrent_block_type='convgru' (model/e2vid/model.py:89-92): ConvGRU as two fused convolutions
+    (BDE_EPI_GRU_UR / BDE_EPI_GRU_OUT) against the frames of the unmodified reference; states round-trip in the reference's
+    layout (a single NCHW tensor per level)."""
+    from bde2vid_b200 import synth
+    from bde2vid_b200.e2vid import E2VIDRecurrent
+    rec = manifest["e2vid_gru_64x96_B2_T3"]
+    g = load_golden("e2vid_gru_64x96_B2_T3")
+    gen = torch.Generator().manual_seed(rec["input_seed"])
+    xs = [torch.randn(2, 5, 64, 96, generator=gen) for _ in range(3)]
+    model = E2VIDRecurrent({"num_bins": 5, "recurrent_block_type": "convgru", "num_encoders": 3})
+    sd = synth.random_state_dict_like(model.state_dict(), rec["seed"])
+    model.load_state_dict(sd, strict=True)
+    model = model.eval().to(DEV)
+    model.unetrecurrent.precision = precision
+    st = None
+    with torch.no_grad():
+        for i, x in enumerate(xs):
+            if i == 2:
+                st = [s.h for s in st]                      # hand the states back as reference-layout tensors
+            img, st = model.unetrecurrent(x.to(DEV), st)
+            err = np.abs(img.cpu().numpy() - g["ref_frames"][i]).max()
+            print("e2vid gru step", i, precision, "max-abs", float(err))
+            assert err <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_firenet_golden_frames(manifest, precision):
+    """FireNet (model/e2vid/model.py:119-172) on the same kernels against the reference's frames."""
+    from bde2vid_b200 import synth
+    from bde2vid_b200.e2vid import FireNet
+    rec = manifest["firenet_64x96_B2_T3"]
+    g = load_golden("firenet_64x96_B2_T3")
+    gen = torch.Generator().manual_seed(rec["input_seed"])
+    xs = [torch.randn(2, 5, 64, 96, generator=gen) for _ in range(3)]
+    model = FireNet()
+    sd = synth.random_state_dict_like(model.state_dict(), rec["seed"])
+    model.load_state_dict(sd, strict=True)
+    model = model.eval().to(DEV)
+    model.precision = precision
+    model.reset_states()
+    with torch.no_grad():
+        for i, x in enumerate(xs):
+            img = model({"events": x.to(DEV)})["image"]
+            assert img.shape == (2, 1, 64, 96)
+            err = np.abs(img.cpu().numpy() - g["ref_frames"][i]).max()
+            scale = max(1.0, float(np.abs(g["ref_frames"][i]).max()))
+            print("firenet step", i, precision, "max-abs", float(err), "scale", scale)
+            assert err <= (2e-4 if precision == "fp32" else 1e-2) * scale     # raw (no sigmoid) output
+        model.reset_states()
+        again = model({"events": xs[0].to(DEV)})["image"]
+        assert np.abs(again.cpu().numpy() - g["ref_frames"][0]).max() <= (2e-4 if precision == "fp32" else 1e-2) * scale
