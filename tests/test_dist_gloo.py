@@ -33,3 +33,37 @@ def test_two_rank_shard_and_metric_reduce():
     assert abs(a[1]["n"] - sum(costs)) < 1e-9
     assert abs(a[1]["mse"] - sum(0.01 * (i + 1) * c for i, c in enumerate(costs))) < 1e-9
     assert abs(finalize_means(a[1])["mse"] - a[1]["mse"] / a[1]["n"]) < 1e-12
+
+
+def _eval_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bde2vid_b200.eval_seq import eval_files
+    files = ["HQF/a.npz", "HQF/b.npz", "ECD/c.npz", "ECD/d.npz", "ECD/e.npz"]
+    seen = []
+
+    def fake_eval(f):           # per-file "metrics" that depend only on the file name: the gathered table is checkable
+        seen.append(f)
+        n = 2 + files.index(f)
+        d = {"mse": [0.1 * files.index(f)] * n, "ssim": [0.5] * n}
+        return {k: sum(v) / len(v) for k, v in d.items()}, d
+
+    results, details, overall = eval_files(files, fake_eval, costs=[5, 4, 3, 2, 1])
+    ret[rank] = (seen, results, overall)
+    dist.destroy_process_group()
+
+
+def test_two_rank_headless_driver_sharding_and_gather():
+    """eval_seq.eval_files: files sharded over 2 ranks, every rank ends with the full {dataset: {file: row}} table
+    (reference schema, eval_models_seq.py:122-135) and the frame-weighted overall means from ONE all-reduce."""
+    world, port = 2, 29543
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_eval_worker, args=(world, port, ret), nprocs=world, join=True)
+    (s0, r0, o0), (s1, r1, o1) = ret[0], ret[1]
+    assert sorted(s0 + s1) == sorted(["HQF/a.npz", "HQF/b.npz", "ECD/c.npz", "ECD/d.npz", "ECD/e.npz"]) and s0 and s1
+    assert r0 == r1 and set(r0) == {"HQF", "ECD"} and set(r0["ECD"]) == {"c", "d", "e"}
+    assert abs(r0["ECD"]["d"]["mse"] - 0.3) < 1e-12
+    n = [2, 3, 4, 5, 6]
+    want = sum(0.1 * i * n[i] for i in range(5)) / sum(n)
+    assert abs(o0["mse"] - want) < 1e-12 and abs(o1["mse"] - want) < 1e-12 and abs(o0["ssim"] - 0.5) < 1e-12
