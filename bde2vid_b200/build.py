@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbde2vid_sm100.so")
-SOURCES = ["api.cu", "voxel.cu", "voxel_norm.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_conv.cu", "head_conv.cu", "metrics.cu", "elementwise.cu", "attn.cu", "attn_mma.cu", "attn_fused.cu", "mlp_fused.cu"]
+SOURCES = ["api.cu", "voxel.cu", "voxel_norm.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_conv.cu", "head_conv.cu", "metrics.cu", "elementwise.cu", "attn.cu", "attn_mma.cu", "attn_fused.cu", "attn_tc256.cu", "mlp_fused.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

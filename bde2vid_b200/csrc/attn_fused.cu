@@ -14,10 +14,14 @@
 // of the expanded [heads, 49, D*49] tensor, which would not fit in shared memory next to the operands.
 #include "common.cuh"
 
+#include <stdlib.h>
 namespace bde {
 namespace tc {
 extern long long* g_dbg;   // bring-up cycle-counter buffer owned by gemm_tc.cu (bde_tc_debug_enable)
 extern size_t g_dbg_ctas;
+int attn_win256_tc_launch(const float* const* frames, int D, int q_slot, const int* tok_map, int n_win, const void* wqkv,
+                          const float* bqkv, const float* bias_tbl, const void* wproj, const float* bproj, float* xs,
+                          cudaStream_t s);
 }  // namespace tc
 namespace {
 
@@ -1138,6 +1142,10 @@ extern "C" int bde_window_attention_fused(const float* const* frames_host, int D
   }
   if (c == 64) { BDE_FUSED(64, 4) }
   if (with_proj) {   // c == 256 with the projection fused: whole-window kernel
+    // default: projections on tcgen05 (attn_tc256.cu); BDE2VID_ATTN_TC256=0 selects the mma.sync form below
+    const char* e = getenv("BDE2VID_ATTN_TC256");
+    if (!(e != nullptr && e[0] == '0') && (((uintptr_t)wqkv) & 127) == 0 && (((uintptr_t)wproj) & 127) == 0)
+      return tc::attn_win256_tc_launch(frames_host, D, q_slot, tok_map, n_win, wqkv, bqkv, bias_tbl, wproj, bproj, xs, s);
     switch (D) {
       case 1: return launch_win256<7, false>(p, s);
       case 2: return launch_win256<13, false>(p, s);

@@ -144,6 +144,10 @@ class Engine:
         self.fuse_attn = os.environ.get("BDE2VID_FUSED_ATTN", "1") != "0"
         self.fuse_mlp = os.environ.get("BDE2VID_FUSED_MLP", "1") != "0"
         self.fuse_win256 = os.environ.get("BDE2VID_ATTN_WIN256", "1") != "0"
+        # the whole-window C = 256 kernel (tcgen05 projections, attn_tc256.cu) is used from this many windows up; the mma.sync
+        # form it replaced only paid off from 64 windows (one CTA per window), the tcgen05 form wins at every size measured
+        # (35 windows: 31.7 us vs 64.5 us per launch; tools/attn_tc256_probe.py)
+        self.win256_min = int(os.environ.get("BDE2VID_WIN256_MIN", "1" if os.environ.get("BDE2VID_ATTN_TC256", "1") != "0" else "64"))
         # precomputed neighbour k | v for the level-3 attention (bde_window_attention_fused_kvpre): OFF by default.
         # Measured on B200 (round 1): the attention kernel stays at 66 us per launch with 60 % fewer MMAs and a 5-deep
         # weight prefetch (it is bound by barrier / shared-memory latency at 16 warps per SM, not by the projections),
@@ -776,7 +780,7 @@ class _Plan:
             # the first block (plain windows: every pixel belongs to exactly one window) of the fused-projection kernels
             # reads the query frame / shortcut straight from feat[t] and writes x: no copy of feat[t] into xs
             direct0 = (qsrc is not None and blk0["tbl"] is not None
-                       and (C == 64 or pre or (eng.fuse_win256 and nwin >= 64)))
+                       and (C == 64 or pre or (eng.fuse_win256 and nwin >= eng.win256_min)))
             if not direct0:
                 if qsrc is None:
                     xs.zero_()
@@ -804,7 +808,7 @@ class _Plan:
                     continue
                 if blk["tbl"] is not None:
                     # one kernel for the attention half; C == 64 also projects and scatters into xs
-                    if C == 64 or (eng.fuse_win256 and nwin >= 64):
+                    if C == 64 or (eng.fuse_win256 and nwin >= eng.win256_min):
                         # C = 256: whole-window kernel (gather + LN once per window, projection + scatter fused) once
                         # there are enough windows to fill the SMs with one CTA each; below that (a single sequence
                         # has 35 level-3 windows) the per-head-group kernel's 4 CTAs per window finish sooner

@@ -29,7 +29,7 @@ def to_loader_format(ev, w):
     xs = ev["xs"][a:b].astype(np.float32)
     ys = ev["ys"][a:b].astype(np.float32)
     ts = ev["ts"][a:b]
-    ts = (ts - ts[0]).astype(np.float32)
+    ts = (ts - ts[0]).astype(np.float32) if b > a else ts.astype(np.float32)    # (empty window: nothing to shift)
     ps = ev["ps"][a:b].astype(np.float32) * 2.0 - 1.0
     return xs, ys, ts, ps
 

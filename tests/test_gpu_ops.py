@@ -271,7 +271,9 @@ def test_window_attention_whole_window_kernel_c256(dilated, zero_frame):
     frames = [(torch.randn(P, C, generator=g) * 1.5 + 0.2).to(DEV) for _ in range(D)]
     if zero_frame is not None:
         frames[zero_frame] = None
-    wqkv = (torch.randn(3 * C, C, generator=g) / C ** 0.5).to(torch.bfloat16).to(DEV)
+    wq_f = torch.randn(3 * C, C, generator=g) / C ** 0.5
+    wq_f[:C] *= (C // heads) ** -0.5            # the engine folds the q scale head_dim^-0.5 into the q rows (engine.py)
+    wqkv = wq_f.to(torch.bfloat16).to(DEV)
     bqkv = (torch.randn(3 * C, generator=g) * 0.1).to(DEV)
     table = torch.randn((2 * D - 1) * 169, heads, generator=g) * 0.5
     rows = [table[((q_ind - d) + D - 1) * 169:((q_ind - d) + D) * 169] for d in range(D)]
@@ -315,14 +317,17 @@ def test_window_attention_whole_window_kernel_c256(dilated, zero_frame):
     torch.cuda.synchronize()
     err = float((xs - ref).abs().max())
     print("win256", dilated, zero_frame, err, float((ref - xs0).abs().max()))
-    assert err <= 2e-2                                # bf16 operands on inputs of magnitude ~1.5, fp32 reference
-    assert float((ref - xs0).abs().max()) > 0.1      # the attention path really contributes
+    upd = float((ref - xs0).abs().max())
+    # pure fp32 reference, bf16 operands in the kernel (xhat, q, k, o rounded to bf16, p / v to fp16, two chained K = 256
+    # products): gate relative to the size of the update the attention half makes
+    assert err <= 1.5e-2 * max(1.0, upd), (err, upd)
+    assert upd > 0.1                                  # the attention path really contributes
     # the per-head-group kernel (o only; used below 64 windows) against the same fp32 reference
     ob = torch.zeros(nwin * 49, C, dtype=torch.bfloat16, device=DEV)
     fr[q_ind] = xs0
     ops.window_attention_fused(fr, q_ind, tm.view(-1), nwin, C, heads, wqkv, bqkv, tbl, o_out=ob)
     torch.cuda.synchronize()
-    assert float((ob.float() - o).abs().max()) <= 2e-2
+    assert float((ob.float() - o).abs().max()) <= 1.5e-2 * max(1.0, float(o.abs().max()))
     # same kernel fed with precomputed neighbour k | v (LayerNorm + rows [C, 3C) of wqkv, bf16), as the executor does
     if zero_frame != q_ind:
         kv = []
@@ -340,4 +345,4 @@ def test_window_attention_whole_window_kernel_c256(dilated, zero_frame):
         torch.cuda.synchronize()
         err2 = float((xs2 - ref).abs().max())
         print("win256 kvpre", dilated, zero_frame, err2)
-        assert err2 <= 2e-2
+        assert err2 <= 1.5e-2 * max(1.0, upd)
