@@ -13,6 +13,7 @@
 //              (TMEM -> +b2 + residual -> coalesced fp32 store through a smem transpose)
 //   warp 8     one thread: TMA loads of W1 [256 x 64] and W2 [64 x 256] (SWIZZLE_128B), then both MMA chains
 // Shared memory ~100 KB and 256 TMEM columns (accumulator 2 reuses accumulator 1's columns) -> 2 CTAs / SM.
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -264,8 +265,36 @@ struct Mlp3Params {
   __nv_bfloat16* sum_t;
 };
 
+// CL > 1: a thread-block CLUSTER of CL CTAs shares one 128-row tile and splits the HIDDEN dimension: CTA `rank` runs the
+// chunks rank, rank + CL, ... (fc1 + GELU + its K-slice of fc2), so every CTA streams only 1 / CL of the 1 MB of weights
+// and does 1 / CL of the GELU work, and CL x as many SMs are busy (46 tiles -> 92 CTAs for four 33 x 44 maps; the single-CTA
+// form ran on 46 of the 148 SMs).  The partial fc2 accumulators are then exchanged through distributed shared memory:
+// CTA r finalises output columns [256 r / CL, 256 (r + 1) / CL) = its own TMEM partial + the peers' partials in a FIXED
+// order (deterministic, no atomics), + bias + residual.
+__device__ __forceinline__ uint32_t m3_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void m3_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t m3_mapa(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void m3_st_cluster_v4(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int CL>
 __global__ void __launch_bounds__(kM3Threads, 1)
 mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2, const Mlp3Params p) {
+  constexpr int NL = kM3NChunks / CL;          // hidden chunks of this CTA: rank, rank + CL, ...
+  constexpr int NC = kM3C / CL;                // output columns this CTA finalises
+  static_assert(CL == 1 || CL == 2 || CL == 4, "cluster sizes 1, 2, 4");
+  const int rank = CL > 1 ? (int)m3_cluster_rank() : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sb - smem_u32(smem_raw));
@@ -282,7 +311,7 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
   const uint32_t tmem_slot = bar0 + 128;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
+  const int m0 = (blockIdx.x / CL) * BM;
 
   if (threadIdx.x == 0) {
     mbar_init(bar_xn, kNumProducerThreads);
@@ -368,8 +397,9 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
 #pragma unroll 1
-    for (int jc = 0; jc < kM3NChunks; ++jc) {
-      const uint32_t a = jc & 1, ph = (jc >> 1) & 1;
+    for (int jl = 0; jl < NL; ++jl) {
+      const int jc = rank + CL * jl;            // global hidden chunk
+      const uint32_t a = jl & 1, ph = (jl >> 1) & 1;
       mbar_wait(bar_a1full + 8 * a, ph);
       tcgen05_fence_after();
       uint32_t raw0[32], raw1[32];
@@ -398,43 +428,8 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
       fence_proxy_async_smem();
       mbar_arrive(bar_hfull + 8 * a);
     }
-    // ---------------- final epilogue: x += acc2 + b2, coalesced through a per-warp smem transpose (XN region is free) ---
-    mbar_wait(bar_a2full, 0);
+    mbar_wait(bar_a2full, 0);     // this CTA's (partial) fc2 accumulator is complete: all its MMAs have retired
     tcgen05_fence_after();
-    float* stg = reinterpret_cast<float*>(sgen + kM3OffXn) + warp * 1024;
-    const int rq = lane >> 3, cq4 = lane & 7;
-#pragma unroll 1
-    for (int cb = half * 32; cb < kM3C; cb += 64) {
-      uint32_t raw[32];
-      tmem_ld_32x32b_x32(acc2 + lane_off + (uint32_t)cb, raw);
-      tmem_ld_wait();
-      __syncwarp();
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4)
-        *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
-            make_float4(__uint_as_float(raw[4 * j4]), __uint_as_float(raw[4 * j4 + 1]), __uint_as_float(raw[4 * j4 + 2]),
-                        __uint_as_float(raw[4 * j4 + 3]));
-      __syncwarp();
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + cb + cq4 * 4));
-      float4 cur[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int mm = m0 + q * 32 + it * 4 + rq;
-        cur[it] = mm < p.P ? *reinterpret_cast<const float4*>(p.x + (size_t)mm * kM3C + cb + cq4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + rq;
-        const int mm = m0 + q * 32 + r;
-        const float4 acc = *reinterpret_cast<const float4*>(stg + r * 32 + ((cq4 ^ (r & 7)) << 2));
-        if (mm < p.P) {
-          const float4 xnew = make_float4(cur[it].x + acc.x + bb.x, cur[it].y + acc.y + bb.y, cur[it].z + acc.z + bb.z, cur[it].w + acc.w + bb.w);
-          *reinterpret_cast<float4*>(p.x + (size_t)mm * kM3C + cb + cq4 * 4) = xnew;
-          if (p.sum_io != nullptr) mlp_fused_sum(p.sum_io, p.sum_t, (size_t)mm * kM3C + cb + cq4 * 4, xnew);
-        }
-      }
-    }
-    tcgen05_fence_before();
   } else if (warp == kTmaWarp) {
     // ---------------- weight loads, in the order the MMA warp consumes them ----------------------------------------------
     {
@@ -460,11 +455,12 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
         __syncwarp();
         ++it;
       };
-      load_w1(0, 0); load_w1(0, 1);
-      load_w1(1, 0); load_w1(1, 1);
-      for (int jc = 0; jc < kM3NChunks; ++jc) {
+      load_w1(rank, 0); load_w1(rank, 1);
+      if (NL > 1) { load_w1(rank + CL, 0); load_w1(rank + CL, 1); }
+      for (int jl = 0; jl < NL; ++jl) {
+        const int jc = rank + CL * jl;
         load_w2(jc, 0); load_w2(jc, 1);
-        if (jc + 2 < kM3NChunks) { load_w1(jc + 2, 0); load_w1(jc + 2, 1); }
+        if (jl + 2 < NL) { load_w1(jc + 2 * CL, 0); load_w1(jc + 2 * CL, 1); }
       }
     }
     __syncwarp();
@@ -473,7 +469,7 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
     {
       constexpr uint32_t idesc1 = make_idesc(kM3Chunk), idesc2 = make_idesc(kM3C);
       uint32_t it = 0;
-      auto fc1 = [&](int chunk) {
+      auto fc1 = [&](int chunk) {   // chunk = LOCAL chunk index (the weights of the global chunk arrive through the ring)
         const uint32_t a = chunk & 1;
         mbar_wait(bar_a1empty + 8 * a, ((chunk >> 1) & 1u) ^ 1u);   // the epilogue drained this accumulator (chunk - 2)
         tcgen05_fence_after();
@@ -497,8 +493,8 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
       };
       mbar_wait(bar_xn, 0);
       fc1(0);
-      fc1(1);
-      for (int jc = 0; jc < kM3NChunks; ++jc) {
+      if (NL > 1) fc1(1);
+      for (int jc = 0; jc < NL; ++jc) {
         const uint32_t a = jc & 1;
         mbar_wait(bar_hfull + 8 * a, (jc >> 1) & 1u);
         tcgen05_fence_after();
@@ -514,14 +510,93 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
             umma_commit(bar_wempty + 8 * s);
             if (i == 1) {
               umma_commit(bar_hempty + 8 * a);   // H[a] may be rewritten once these MMAs have read it
-              if (jc == kM3NChunks - 1) umma_commit(bar_a2full);
+              if (jc == NL - 1) umma_commit(bar_a2full);
             }
           }
           __syncwarp();
         }
-        if (jc + 2 < kM3NChunks) fc1(jc + 2);
+        if (jc + 2 < NL) fc1(jc + 2);
       }
     }
+  }
+
+  // ---------------- exchange of the partial accumulators (CL > 1) and final epilogue -------------------------------------
+  // staging slots (fp32 [128 rows][NC cols], 16-byte chunks XOR-swizzled by row) live in the XN / H regions, which are free
+  // in EVERY CTA of the cluster once all of them have passed the first cluster barrier (their MMAs have retired)
+  constexpr int kSlotBytes = BM * NC * 4;
+  const int q = warp & 3, half = warp >> 2;
+  const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+  if (CL > 1) {
+    m3_cluster_sync();
+    if (warp < kNumProducerWarps) {
+      const int row = q * 32 + lane;
+      for (int pr = 0; pr < CL; ++pr) {
+        if (pr == rank) continue;
+        const int slot = rank < pr ? rank : rank - 1;            // my slot in peer pr (its peers in rank order)
+        const uint32_t dst_row = m3_mapa(sb + slot * kSlotBytes + (uint32_t)row * (NC * 4), (uint32_t)pr);
+#pragma unroll 1
+        for (int c0 = half * (NC / 2); c0 < (half + 1) * (NC / 2); c0 += 32) {      // my partial of the peer's columns
+          uint32_t raw[32];
+          tmem_ld_32x32b_x32(acc2 + lane_off + (uint32_t)(pr * NC + c0), raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const int chunk = (c0 >> 2) + j4;
+            m3_st_cluster_v4(dst_row + (uint32_t)(((chunk & ~7) | ((chunk ^ row) & 7)) << 4),
+                             make_float4(__uint_as_float(raw[4 * j4]), __uint_as_float(raw[4 * j4 + 1]),
+                                         __uint_as_float(raw[4 * j4 + 2]), __uint_as_float(raw[4 * j4 + 3])));
+          }
+        }
+      }
+    }
+    m3_cluster_sync();   // every peer's partial of my columns has landed in my staging slots
+  }
+  if (warp < kNumProducerWarps) {
+    // x += (sum of the partial accumulators) + b2 for my columns, coalesced through a per-warp smem transpose
+    float* stg = reinterpret_cast<float*>(sgen + 98304) + warp * 1024;      // above the (CL - 1) staging slots (<= 96 KB)
+    const int rq = lane >> 3, cq4 = lane & 7;
+#pragma unroll 1
+    for (int cl = half * 32; cl < NC; cl += 64) {      // local column offset inside my NC columns
+      const int cb = rank * NC + cl;
+      uint32_t raw[32];
+      tmem_ld_32x32b_x32(acc2 + lane_off + (uint32_t)cb, raw);
+      tmem_ld_wait();
+      __syncwarp();
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
+            make_float4(__uint_as_float(raw[4 * j4]), __uint_as_float(raw[4 * j4 + 1]), __uint_as_float(raw[4 * j4 + 2]),
+                        __uint_as_float(raw[4 * j4 + 3]));
+      __syncwarp();
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + cb + cq4 * 4));
+      float4 cur[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int mm = m0 + q * 32 + it * 4 + rq;
+        cur[it] = mm < p.P ? *reinterpret_cast<const float4*>(p.x + (size_t)mm * kM3C + cb + cq4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + rq;
+        const int trow = q * 32 + r;
+        const int mm = m0 + trow;
+        float4 acc = *reinterpret_cast<const float4*>(stg + r * 32 + ((cq4 ^ (r & 7)) << 2));
+        if (CL > 1) {
+          const int chunk = (cl >> 2) + cq4;
+#pragma unroll
+          for (int sl = 0; sl < CL - 1; ++sl) {
+            const float4 pv = *reinterpret_cast<const float4*>(sgen + sl * kSlotBytes + trow * (NC * 4) + (((chunk & ~7) | ((chunk ^ trow) & 7)) << 4));
+            acc.x += pv.x; acc.y += pv.y; acc.z += pv.z; acc.w += pv.w;
+          }
+        }
+        if (mm < p.P) {
+          const float4 xnew = make_float4(cur[it].x + acc.x + bb.x, cur[it].y + acc.y + bb.y, cur[it].z + acc.z + bb.z, cur[it].w + acc.w + bb.w);
+          *reinterpret_cast<float4*>(p.x + (size_t)mm * kM3C + cb + cq4 * 4) = xnew;
+          if (p.sum_io != nullptr) mlp_fused_sum(p.sum_io, p.sum_t, (size_t)mm * kM3C + cb + cq4 * 4, xnew);
+        }
+      }
+    }
+    tcgen05_fence_before();
   }
 
   __syncthreads();
@@ -566,16 +641,41 @@ extern "C" int bde_mlp_fused_sum(float* x, size_t rows, int c, int hidden, const
     if (rc3 != 0) return rc3;
     rc3 = get_weight_tmap(w2, kM3C, kM3H, kM3C, &t2);           // boxes [64 k x 256 n]
     if (rc3 != 0) return rc3;
-    static bool configured3 = false;
-    if (!configured3) {
-      cudaError_t e = cudaFuncSetAttribute(mlp_fused256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kM3Smem);
-      BDE_REQUIRE(e == cudaSuccess, "bde_mlp_fused: smem attribute: %s", cudaGetErrorString(e));
-      configured3 = true;
-    }
     Mlp3Params p3;
     p3.x = x; p3.b1 = b1; p3.b2 = b2; p3.P = (int)rows;
     p3.sum_io = sum_io; p3.sum_t = (__nv_bfloat16*)sum_t;
-    mlp_fused256_kernel<<<(unsigned)ceil_div(rows, BM), kM3Threads, kM3Smem, (cudaStream_t)stream>>>(t1, t2, p3);
+    // cluster size: split the hidden dimension over 2 (or 4) CTAs while the grid still fits one wave of SMs
+    const int tiles = (int)ceil_div(rows, BM);
+    int n_sm = kNumSMs;
+    {
+      int dev = 0;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    // (measured on B200, tools/mlp_probe.py: 46 tiles 29.1 -> 24.8 us with 2 CTAs per tile; 4 per tile is not faster even for 12 tiles)
+    int cl = tiles * 2 <= n_sm ? 2 : 1;
+    if (const char* e = getenv("BDE2VID_MLP256_CLUSTER")) {
+      const int f = atoi(e);
+      if (f == 1 || f == 2 || f == 4) cl = f;
+    }
+    void (*kern)(const CUtensorMap, const CUtensorMap, const Mlp3Params) =
+        cl == 4 ? mlp_fused256_kernel<4> : (cl == 2 ? mlp_fused256_kernel<2> : mlp_fused256_kernel<1>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kM3Smem);
+    BDE_REQUIRE(e == cudaSuccess, "bde_mlp_fused: smem attribute: %s", cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)(tiles * cl));
+    cfg.blockDim = dim3(kM3Threads);
+    cfg.dynamicSmemBytes = kM3Smem;
+    cfg.stream = (cudaStream_t)stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, t1, t2, p3);
+    BDE_REQUIRE(e == cudaSuccess, "bde_mlp_fused: launch (cluster %d): %s", cl, cudaGetErrorString(e));
     return check_launch("mlp_fused256_kernel");
   }
   int rc = get_weight_tmap(w1, kMlpH, kMlpC, kMlpH, &t1);   // one box [64 k x 256 n]

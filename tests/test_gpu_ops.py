@@ -216,6 +216,25 @@ def test_mlp_fused(rows, C):
     assert torch.equal(x2, xd)
     assert float((sm.cpu() - (xd.cpu() + merged)).abs().max()) <= 1e-5
     assert torch.equal(st, sm.to(torch.bfloat16))
+    if C == 256:
+        # hidden dimension split over a thread-block cluster (BDE2VID_MLP256_CLUSTER = 1 / 2 / 4): partial fc2 accumulators
+        # are exchanged through distributed shared memory and summed in a fixed order -> deterministic; the split only
+        # changes the fp32 summation order of the K = 1024 product
+        import os
+        outs = {}
+        for cl in ("1", "2", "4"):
+            os.environ["BDE2VID_MLP256_CLUSTER"] = cl
+            for rep in range(2):
+                xc = x.to(DEV).contiguous()
+                ops.mlp_fused(xc, rows, C, Hd, w1f.to(DEV).contiguous(), b1f.to(DEV), w2f.to(DEV).contiguous(), b2.to(DEV))
+                torch.cuda.synchronize()
+                if rep == 0:
+                    outs[cl] = xc
+                else:
+                    assert torch.equal(outs[cl], xc), "cluster %s not deterministic" % cl
+            assert float((outs[cl].cpu() - ref).abs().max()) <= 2e-2
+            assert float((outs[cl] - outs["1"]).abs().max()) <= 1e-4
+        del os.environ["BDE2VID_MLP256_CLUSTER"]
 
 
 @pytest.mark.parametrize("shape", [(3, 5, 40, 56), (2, 5, 33, 47), (1, 3, 16, 32), (2, 6, 19, 70)])
