@@ -395,7 +395,130 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
   constexpr int NUNITS = HG * MTN + (HD == 4 ? 1 : 0);
   constexpr uint32_t kOnes = 0x3C003C00u;              // fp16x2 (1, 1)
   constexpr float kLog2e = 1.4426950408889634f;
-  for (int unit = warp; unit < NUNITS; unit += kThreadsF / 32) {
+  if (HD == 4) {
+    // ---- head_dim 4, normal units: TWO units per warp in flight, softmax over three key segments ------------------------
+    // The unit is a long dependent chain (bias + QK^T -> row max -> exp -> P.V) and only 16 warps fit on an SM, so the
+    // kernel was issue-latency bound (warps active 24 %, no pipe above 60 %).  Interleaving two independent units doubles
+    // the instruction-level parallelism per warp; the online softmax over three key segments (6 / 6 / 7 tiles for D = 3)
+    // keeps 2 x 7 score tiles alive instead of 2 x 19, so both fit the 128-register budget of two CTAs per SM.
+    constexpr int NPAIR_UNITS = HG * MTN;                         // 48 normal units: (head, 16-row query tile)
+    constexpr int SEG = ((NT + 2) / 3) & ~1;                      // even segment size: 19 -> 6, 13 -> 4, 7 -> 2
+    constexpr int LAST = NT - 2 * SEG;                            // 7 / 5 / 3
+    constexpr int kMaxT = LAST > SEG ? LAST : SEG;
+    for (int u0 = warp; u0 < NPAIR_UNITS; u0 += 2 * (kThreadsF / 32)) {
+      int hl[2], row0[2], row1[2];
+      uint32_t r0a[2], r1a[2], qa0[2], qa1[2], vaddr[2];
+      bool ones_lane[2], live[2];
+      float oa[2][4], ob[2][4], m0s[2], m1s[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int unit = u0 + u * (kThreadsF / 32);
+        live[u] = unit < NPAIR_UNITS;                             // (48 units over 8 warps: always true; kept for other shapes)
+        const int un = live[u] ? unit : u0;
+        hl[u] = un / MTN;
+        const int mt = un - hl[u] * MTN;
+        row0[u] = mt * 16 + g; row1[u] = row0[u] + 8;
+        r0a[u] = tbl_u32 + (uint32_t)(hl[u] * tbl_ld * 4 + roff[row0[u]]);
+        r1a[u] = tbl_u32 + (uint32_t)(hl[u] * tbl_ld * 4 + roff[row1[u]]);
+        qa0[u] = qa1[u] = 0u;
+        if (2 * t < HD) {
+          qa0[u] = *reinterpret_cast<const uint32_t*>(qs + row0[u] * PQ + hl[u] * HD + 2 * t);
+          qa1[u] = *reinterpret_cast<const uint32_t*>(qs + row1[u] * PQ + hl[u] * HD + 2 * t);
+        }
+        // one 8-channel V tile holds a head pair; the other head's columns are replaced by ones -> row sums
+        ones_lane[u] = (g >> 2) != (hl[u] & 1);
+        vaddr[u] = vs_u32 + (uint32_t)(((lane & 15) * PQ + (hl[u] >> 1) * 8) * 2);
+        oa[u][0] = oa[u][1] = oa[u][2] = oa[u][3] = 0.f;
+        ob[u][0] = ob[u][1] = ob[u][2] = ob[u][3] = 0.f;
+        m0s[u] = m1s[u] = -INFINITY;                              // running row maxima times log2(e)
+      }
+#pragma unroll
+      for (int seg = 0; seg < 3; ++seg) {
+        const int j0 = seg * SEG, nj = seg < 2 ? SEG : LAST;
+        float s[2][kMaxT][4];
+#pragma unroll
+        for (int jj = 0; jj < kMaxT; ++jj) {
+          if (jj < nj) {
+            const int j = j0 + jj;
+            const uint2 cp = lds_u64(coff_u32 + (uint32_t)((j * 8 + 2 * t) * 4));
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              s[u][jj][0] = lds_f32(r0a[u] + cp.x); s[u][jj][1] = lds_f32(r0a[u] + cp.y);
+              s[u][jj][2] = lds_f32(r1a[u] + cp.x); s[u][jj][3] = lds_f32(r1a[u] + cp.y);
+              if (j == NT - 1) {  // only the last key tile can hold padding keys
+                if (j * 8 + 2 * t >= n_kv) s[u][jj][0] = s[u][jj][2] = -1e30f;
+                if (j * 8 + 2 * t + 1 >= n_kv) s[u][jj][1] = s[u][jj][3] = -1e30f;
+              }
+              uint32_t kb0 = 0u;
+              if (2 * t < HD) kb0 = *reinterpret_cast<const uint32_t*>(ks + (j * 8 + g) * PQ + hl[u] * HD + 2 * t);
+              const uint32_t qa[4] = {qa0[u], qa1[u], 0u, 0u};
+              mma16816(s[u][jj], qa, kb0, 0u);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+          for (int jj = 0; jj < kMaxT; ++jj) {
+            if (jj < nj) {
+              mx0 = fmaxf(mx0, fmaxf(s[u][jj][0], s[u][jj][1]));
+              mx1 = fmaxf(mx1, fmaxf(s[u][jj][2], s[u][jj][3]));
+            }
+          }
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+          const float n0s = fmaxf(m0s[u], mx0 * kLog2e), n1s = fmaxf(m1s[u], mx1 * kLog2e);
+          if (seg > 0) {   // rescale what the earlier segments accumulated (values and ones-column row sums alike)
+            float c0, c1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(c0) : "f"(m0s[u] - n0s));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(c1) : "f"(m1s[u] - n1s));
+            oa[u][0] = (oa[u][0] + ob[u][0]) * c0; oa[u][1] = (oa[u][1] + ob[u][1]) * c0;
+            oa[u][2] = (oa[u][2] + ob[u][2]) * c1; oa[u][3] = (oa[u][3] + ob[u][3]) * c1;
+            ob[u][0] = ob[u][1] = ob[u][2] = ob[u][3] = 0.f;
+          }
+          m0s[u] = n0s; m1s[u] = n1s;
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < (kMaxT + 1) / 2; ++k2) {
+          if (2 * k2 < nj) {
+            const int kk = j0 / 2 + k2;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              uint32_t pa[4];
+              pa[0] = ex2_h2(fmaf(s[u][2 * k2][0], kLog2e, -m0s[u]), fmaf(s[u][2 * k2][1], kLog2e, -m0s[u]));
+              pa[1] = ex2_h2(fmaf(s[u][2 * k2][2], kLog2e, -m1s[u]), fmaf(s[u][2 * k2][3], kLog2e, -m1s[u]));
+              if (2 * k2 + 1 < nj) {
+                pa[2] = ex2_h2(fmaf(s[u][2 * k2 + 1][0], kLog2e, -m0s[u]), fmaf(s[u][2 * k2 + 1][1], kLog2e, -m0s[u]));
+                pa[3] = ex2_h2(fmaf(s[u][2 * k2 + 1][2], kLog2e, -m1s[u]), fmaf(s[u][2 * k2 + 1][3], kLog2e, -m1s[u]));
+              } else {
+                pa[2] = pa[3] = 0u;
+              }
+              uint32_t vb0, vb1;
+              ldsm_x2_trans(vb0, vb1, vaddr[u] + (uint32_t)(kk * 16 * PQ * 2));
+              if (ones_lane[u]) { vb0 = kOnes; vb1 = kOnes; }
+              if (k2 & 1) mma16816_f16(ob[u], pa, vb0, vb1); else mma16816_f16(oa[u], pa, vb0, vb1);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oa[u][e] += ob[u][e];
+        const float l0 = __shfl_xor_sync(0xffffffffu, oa[u][0], 2), l1 = __shfl_xor_sync(0xffffffffu, oa[u][2], 2);
+        if (live[u] && (t >> 1) == (hl[u] & 1)) {
+          const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+          const int col = (hl[u] >> 1) * 8 + 2 * t;
+          *reinterpret_cast<uint32_t*>(os + row0[u] * PQ + col) = pack2(oa[u][0] * inv0, oa[u][1] * inv0);
+          *reinterpret_cast<uint32_t*>(os + row1[u] * PQ + col) = pack2(oa[u][2] * inv1, oa[u][3] * inv1);
+        }
+      }
+    }
+  }
+  for (int unit = HD == 4 ? HG * MTN + warp : warp; unit < NUNITS; unit += kThreadsF / 32) {
     const bool special = HD == 4 && unit == HG * MTN;
     const int hl = unit / MTN, mt = unit - hl * MTN;
     const int row0 = mt * 16 + g, row1 = row0 + 8;
@@ -585,6 +708,22 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
   if (dbg) { const long long c = clock64(); t_attn = c - t_mark; t_mark = c; }
   if (C == 64) {
     // ---- output projection + window_reverse + shortcut: x[pix] += proj(o) + b (DTransformer.py:204,294-299) ----
+    // shortcut = the query frame (DTransformer.py:294-299; xs itself when the block runs in place): this thread's eight
+    // float2 values are fetched BEFORE the projection GEMM -- inside the store loop every load waited behind the previous
+    // store (xs and the frame may alias), eight global round trips in a row
+    const float* shortcut = p.frames[p.q_slot];
+    float2 sc[2][2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const int r = (mh * 2 + i) * 16 + g + hrow * 8;
+        const int pix = r < kTok ? pix_s[r] : -1;
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+          sc[i][hrow][n] = pix >= 0 ? __ldg(reinterpret_cast<const float2*>(shortcut + (size_t)pix * C + npair * 16 + n * 8 + 2 * t))
+                                    : make_float2(0.f, 0.f);
+      }
     __syncthreads();
     float acc[2][2][4];
     warp_gemm<C, PQ, 2>(acc, 2, sb + Cfg::OFF_OS, [&](int i, int r) { return (mh * 2 + i) * 16 + r; }, sb + Cfg::OFF_WP, npair, lane);
@@ -600,12 +739,10 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
           for (int n = 0; n < 2; ++n) {
             const int col = npair * 16 + n * 8 + 2 * t;
             const float2 bb = __ldg(reinterpret_cast<const float2*>(p.bproj + col));
-            float2* dst = reinterpret_cast<float2*>(p.xs + (size_t)pix * C + col);
-            // shortcut = the query frame (DTransformer.py:294-299); it is xs itself when the block runs in place
-            float2 cur = *reinterpret_cast<const float2*>(p.frames[p.q_slot] + (size_t)pix * C + col);
+            float2 cur = sc[i][hrow][n];
             cur.x += acc[i][n][hrow * 2 + 0] + bb.x;
             cur.y += acc[i][n][hrow * 2 + 1] + bb.y;
-            *dst = cur;
+            *reinterpret_cast<float2*>(p.xs + (size_t)pix * C + col) = cur;
           }
         }
       }
