@@ -15,6 +15,32 @@ void set_error(const char* fmt, ...) {
 
 }  // namespace bde
 
+#include <mutex>
+#include <set>
+#include <utility>
+namespace bde {
+bool first_use_on_device(const void* key) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> seen;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  return seen.insert(std::make_pair(dev, key)).second;
+}
+int device_sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return kNumSMs;
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+    cache[dev] = n;     // (a benign race: every writer stores the same value)
+  }
+  return cache[dev];
+}
+}  // namespace bde
+
 using namespace bde;
 
 extern "C" const char* bde_last_error(void) { return g_err; }
@@ -28,13 +54,17 @@ extern "C" int bde_device_ok(void) {
     set_error("cudaGetDevice: %s", cudaGetErrorString(e));
     return -2;
   }
-  int major = 0;
+  int major = 0, minor = 0;
   e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
   if (e != cudaSuccess) {
     set_error("cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
     return -2;
   }
-  return major == 10 ? 1 : 0;
+  // the library holds sm_100a code only (arch-specific: not forward compatible, e.g. with sm_103)
+  if (major == 10 && minor == 0) return 1;
+  set_error("device is compute capability %d.%d; libbde2vid_sm100.so holds sm_100a code only", major, minor);
+  return 0;
 }
 
 // ---- optional per-launch timing of the tcgen05 GEMM kernel (used by bench.py's roofline measurement) ----

@@ -760,11 +760,9 @@ int launch_fused(const FusedAttnParams& p, cudaStream_t s) {
   using Cfg = FusedCfg<C, HD, NT>;
   static_assert(C != 64 || Cfg::PQ == Cfg::PX, "C == 64 shares one pitch between token and q/k/v tiles");
   auto kern = attn_fused_kernel<C, HD, NT>;
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device((const void*)kern)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     BDE_REQUIRE(e == cudaSuccess, "bde_window_attention_fused: smem attribute (%d bytes): %s", Cfg::SMEM, cudaGetErrorString(e));
-    configured = true;
   }
   FusedAttnParams q = p;
   q.dbg = (tc::g_dbg != nullptr && (size_t)p.n_win * (C / 64) <= tc::g_dbg_ctas) ? tc::g_dbg : nullptr;
@@ -1220,11 +1218,9 @@ template <int NT, bool kPre>
 int launch_win256(const FusedAttnParams& p, cudaStream_t s) {
   using Cfg = WinCfg<NT, kPre>;
   auto kern = attn_win256_kernel<NT, kPre>;
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device((const void*)kern)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     BDE_REQUIRE(e == cudaSuccess, "bde_window_attention_fused: smem attribute (%d bytes): %s", Cfg::SMEM, cudaGetErrorString(e));
-    configured = true;
   }
   FusedAttnParams q = p;
   q.dbg = (tc::g_dbg != nullptr && (size_t)p.n_win <= tc::g_dbg_ctas) ? tc::g_dbg : nullptr;

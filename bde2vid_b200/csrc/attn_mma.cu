@@ -237,14 +237,12 @@ int launch_mma(const void* q, const void* kv, const float* bias, int n_win, int 
   constexpr int KS = 2 * HD + 8;
   const size_t smem = (size_t)2 * 64 * SM::kBiasStride * sizeof(float) + (size_t)4 * SM::kRows * KS * 2;
   auto kern = window_attention_mma_kernel<HD, NT>;
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device((const void*)kern)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     BDE_REQUIRE(e == cudaSuccess, "bde_window_attention(mma): smem attribute: %s", cudaGetErrorString(e));
-    configured = true;
   }
   // two CTAs per SM: (heads/2) head pairs x window groups ~ one wave of 2 x 148 CTAs
-  int groups = (2 * kNumSMs) / (heads / 2);
+  int groups = (2 * device_sm_count()) / (heads / 2);
   if (groups < 1) groups = 1;
   if (groups > n_win) groups = n_win;
   dim3 grid(heads / 2, groups);

@@ -647,8 +647,10 @@ template <int NT>
 int launch_tc256(const CUtensorMap& tq, const CUtensorMap& tp, const TcAttnParams& p, cudaStream_t s) {
   using Cfg = TCfg<NT>;
   auto kern = attn_win256_tc_kernel<NT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-  BDE_REQUIRE(e == cudaSuccess, "bde_window_attention_fused: smem attribute (%d bytes): %s", Cfg::SMEM, cudaGetErrorString(e));
+  if (first_use_on_device((const void*)kern)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    BDE_REQUIRE(e == cudaSuccess, "bde_window_attention_fused: smem attribute (%d bytes): %s", Cfg::SMEM, cudaGetErrorString(e));
+  }
   TcAttnParams q = p;
   q.dbg = (g_dbg != nullptr && (size_t)2 * p.n_win <= g_dbg_ctas) ? g_dbg : nullptr;   // rows [n_win, 2 n_win): MMA-warp timeline
   kern<<<p.n_win, kThreadsT, Cfg::SMEM, s>>>(tq, tp, q);

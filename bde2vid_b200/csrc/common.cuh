@@ -89,6 +89,11 @@ __device__ __forceinline__ void lstm_update(float gi, float gf, float go, float 
   h = sigmoid_f(go) * tanh_f(c);
 }
 
+// true exactly once per (current device, key): guards the per-device cudaFuncSetAttribute calls (api.cu, mutex-protected)
+bool first_use_on_device(const void* key);
+// multiProcessorCount of the current device (cached per ordinal)
+int device_sm_count();
+
 // implemented per translation unit
 int gemm_simt(const bde_gemm_desc* d, cudaStream_t s);
 int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s);

@@ -419,11 +419,9 @@ template <int BN, bool kBTma, bool kDeep, int kLn = 0>
 int launch(const CUtensorMap& tmap, const TcParams& p, cudaStream_t s) {
   using Cfg = TileCfg<BN, kDeep, kLn>;
   auto kern = gemm_tc_kernel<BN, kBTma, kDeep, kLn>;
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device((const void*)kern)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     BDE_REQUIRE(e == cudaSuccess, "bde_gemm(tcgen05): smem attribute: %s", cudaGetErrorString(e));
-    configured = true;
   }
   const size_t m_tiles = p.tiles_x > 0 ? (size_t)p.n_img * p.tiles_x * p.tiles_y : ceil_div(p.M, BM);
   dim3 grid((unsigned)m_tiles, (unsigned)(p.N / BN));
@@ -535,7 +533,7 @@ int gemm_tcgen05(const bde_gemm_desc* d, cudaStream_t s) {
     bn = (p.N % 256 == 0) ? 256 : (p.N % 192 == 0) ? 192 : (p.N % 128 == 0) ? 128 : (p.N % 64 == 0) ? 64 : 32;
   }
   // grids of at most one CTA per SM cannot overlap two CTAs' phases: give the single CTA a deeper pipeline instead
-  const bool small_grid = !ln && m_tiles * (size_t)(p.N / bn) <= (size_t)kNumSMs && p.num_kb >= 8;
+  const bool small_grid = !ln && m_tiles * (size_t)(p.N / bn) <= (size_t)device_sm_count() && p.num_kb >= 8;
   const bool deep = (p.tiles_x > 0 && env_flag("BDE2VID_TC_DEEP", false)) || (small_grid && env_flag("BDE2VID_TC_DEEP_SMALL", true));
   if (g_dbg != nullptr) {
     const size_t mt = p.tiles_x > 0 ? (size_t)p.n_img * p.tiles_x * p.tiles_y : ceil_div(p.M, BM);

@@ -630,7 +630,6 @@ static int launch_conv(const CUtensorMap& ta0, const CUtensorMap& ta1, const CUt
   using Cfg = CvCfg<BN, kHalo, kPair, NSUB>;
   constexpr int CS = kPair ? 2 : 1;
   auto kern = conv_tma_kernel<BN, kHalo, EPI, kPair, NSUB>;
-  static int max_clusters = 0;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[1];
@@ -643,17 +642,18 @@ static int launch_conv(const CUtensorMap& ta0, const CUtensorMap& ta1, const CUt
   cfg.stream = s;
   cfg.attrs = attr;
   cfg.numAttrs = kPair ? 1 : 0;
-  if (max_clusters == 0) {
+  if (first_use_on_device((const void*)kern)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     BDE_REQUIRE(e == cudaSuccess, "bde_gemm(tcgen05 conv): smem attribute: %s", cudaGetErrorString(e));
-    int n = kNumSMs / CS;
-    if (kPair) {
-      cfg.gridDim = dim3(kNumSMs / CS * CS);
-      e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
-      BDE_REQUIRE(e == cudaSuccess && n > 0, "bde_gemm(tcgen05 conv): cluster occupancy query: %s", cudaGetErrorString(e));
-      if (n > kNumSMs / CS) n = kNumSMs / CS;
-    }
-    max_clusters = n;
+  }
+  const int n_sm = device_sm_count();
+  int max_clusters = n_sm / CS;     // persistent: one CTA (or CTA pair) per SM
+  if (kPair) {
+    cfg.gridDim = dim3(n_sm / CS * CS);
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    BDE_REQUIRE(e == cudaSuccess && n > 0, "bde_gemm(tcgen05 conv): cluster occupancy query: %s", cudaGetErrorString(e));
+    if (n < max_clusters) max_clusters = n;
   }
   const int clusters = cp.num_groups < max_clusters ? cp.num_groups : max_clusters;
   cfg.gridDim = dim3((unsigned)(clusters * CS));
@@ -724,7 +724,7 @@ int conv_tma_launch(const bde_gemm_desc* d, const TcParams& p0, cudaStream_t s) 
   // keep every SM busy and a map at least two tiles wide
   int nsub = 1;
   if (halo && bn_max <= 128 && env_flag("BDE2VID_CONV_DUAL", true) && d2_out > kCvD2 &&
-      (size_t)p.n_img * ceil_div(d1_out, kCvD1) * ceil_div(d2_out, 2 * kCvD2) * (p.N / bn_max) >= (size_t)kNumSMs)
+      (size_t)p.n_img * ceil_div(d1_out, kCvD1) * ceil_div(d2_out, 2 * kCvD2) * (p.N / bn_max) >= (size_t)device_sm_count())
     nsub = 2;
   cp.t1_tiles = (int)ceil_div(d1_out, kCvD1);
   cp.t2_tiles = (int)ceil_div(d2_out, kCvD2 * nsub);
@@ -736,7 +736,7 @@ int conv_tma_launch(const bde_gemm_desc* d, const TcParams& p0, cudaStream_t s) 
   // every shape of the path (the main loop is bound by the tensor pipe at ~700 cycles per 128x256x64 block either way)
   const bool pair = env_flag("BDE2VID_CONV_PAIR", false) && cp.num_m_tiles >= 2 && halo && bn_max == 256 && nsub == 1;
   const int cs = pair ? 2 : 1;
-  const int units = kNumSMs / cs;   // CTAs or CTA pairs that run concurrently
+  const int units = device_sm_count() / cs;   // CTAs or CTA pairs that run concurrently
   // tile width: the widest N tile that divides N, narrowed while the grid would leave SMs idle
   int bn = bn_max;
   while (nsub == 1 && !pair && bn > 64 && ceil_div(cp.num_m_tiles, cs) * (size_t)(p.N / bn) < (size_t)units) bn /= 2;
@@ -748,7 +748,7 @@ int conv_tma_launch(const bde_gemm_desc* d, const TcParams& p0, cudaStream_t s) 
   const size_t groups = (size_t)cp.groups_per_n * (p.N / bn);
   BDE_REQUIRE(groups < ((size_t)1 << 30), "bde_gemm(tcgen05 conv): too many tiles");
   cp.num_groups = (int)groups;
-  if (g_dbg != nullptr && (size_t)kNumSMs <= g_dbg_ctas) cp.p.dbg = g_dbg;
+  if (g_dbg != nullptr && (size_t)device_sm_count() <= g_dbg_ctas) cp.p.dbg = g_dbg;
   // epilogue specialisation
   int epi = kEpiGeneric;
   if (env_flag("BDE2VID_CONV_EPI_SPEC", true)) {

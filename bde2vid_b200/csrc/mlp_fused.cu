@@ -646,11 +646,7 @@ extern "C" int bde_mlp_fused_sum(float* x, size_t rows, int c, int hidden, const
     p3.sum_io = sum_io; p3.sum_t = (__nv_bfloat16*)sum_t;
     // cluster size: split the hidden dimension over 2 (or 4) CTAs while the grid still fits one wave of SMs
     const int tiles = (int)ceil_div(rows, BM);
-    int n_sm = kNumSMs;
-    {
-      int dev = 0;
-      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int n_sm = device_sm_count();
     // (measured on B200, tools/mlp_probe.py: 46 tiles 29.1 -> 24.8 us with 2 CTAs per tile; 4 per tile is not faster even for 12 tiles)
     int cl = tiles * 2 <= n_sm ? 2 : 1;
     if (const char* e = getenv("BDE2VID_MLP256_CLUSTER")) {
@@ -659,7 +655,8 @@ extern "C" int bde_mlp_fused_sum(float* x, size_t rows, int c, int hidden, const
     }
     void (*kern)(const CUtensorMap, const CUtensorMap, const Mlp3Params) =
         cl == 4 ? mlp_fused256_kernel<4> : (cl == 2 ? mlp_fused256_kernel<2> : mlp_fused256_kernel<1>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kM3Smem);
+    cudaError_t e = cudaSuccess;
+    if (first_use_on_device((const void*)kern)) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kM3Smem);
     BDE_REQUIRE(e == cudaSuccess, "bde_mlp_fused: smem attribute: %s", cudaGetErrorString(e));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -682,11 +679,9 @@ extern "C" int bde_mlp_fused_sum(float* x, size_t rows, int c, int hidden, const
   if (rc != 0) return rc;
   rc = get_weight_tmap(w2, kMlpC, kMlpH, kMlpC, &t2);       // boxes [64 k x 64 n]
   if (rc != 0) return rc;
-  static bool configured = false;
-  if (!configured) {
+  if (first_use_on_device((const void*)mlp_fused_kernel)) {
     cudaError_t e = cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmem);
     BDE_REQUIRE(e == cudaSuccess, "bde_mlp_fused: smem attribute: %s", cudaGetErrorString(e));
-    configured = true;
   }
   MlpParams p;
   p.x = x; p.b1 = b1; p.b2 = b2; p.P = (int)rows;

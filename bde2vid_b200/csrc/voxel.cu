@@ -552,11 +552,7 @@ static int launch_atomic(const Src& src, bool agg, const int64_t* offsets, int T
   }
   int per_chunk = (int)((chunk_mb << 20) / (grid_elems * sizeof(float)));   // L2 footprint of a window = its grid, not the stride
   per_chunk = per_chunk < 1 ? 1 : (per_chunk > T ? T : per_chunk);
-  int n_sm = kNumSMs;
-  {
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int n_sm = device_sm_count();
   for (int w0 = 0; w0 < T; w0 += per_chunk) {
     const int n = (T - w0 < per_chunk) ? T - w0 : per_chunk;
     float* base = out + (size_t)w0 * out_window_stride;
