@@ -32,7 +32,14 @@ GF_CONV, GF_LINEAR, GF_BMM = 125.79, 32.36, 5.19
 VOXEL_BYTES_PER_WINDOW = 16 * NEV + 4 * BINS * H * W
 # dram__bytes_read.sum + dram__bytes_write.sum of the voxeliser (memset + reduction kernels) from the committed ncu capture;
 # filled in from profiles/ once measured (None = not captured for this build)
-VOXEL_TRAFFIC = {}
+VOXEL_TRAFFIC = {
+    # profiles/r02_ncu_voxel_traffic.csv (ncu --cache-control none over one 100-window call at 346x260): the four reduction
+    # kernels read 50.1 MB from DRAM (= the events, 16 B x 3.15 M: the memset grids are still L2-resident, nothing is
+    # re-read) and the 264x352 grids (185.9 MB) are written back once
+    "bytes_per_100_windows": 50.1e6 + 185.9e6,
+    "source": "ncu --cache-control none, dram__bytes_read.sum of the 4 reduction kernels (50.1 MB = events) + one write-back of the "
+              "padded grids (185.9 MB); profiles/r02_ncu_voxel_traffic.csv",
+}
 
 
 def cfg_dict():

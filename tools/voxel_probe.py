@@ -54,12 +54,13 @@ def run_shape(H, W, NEV, T, Hp, Wp, pt, pl, algos, streams=("uniform", "clustere
 
 
 if "--ncu-shape" in sys.argv:
-    ev = synth.gen_events(0, 64, 720, 1280, 333333)
-    f32 = [torch.from_numpy(a).to(DEV) for a in synth.to_loader_format_seq(ev)]
-    out = torch.empty(64, 5, 720, 1280, device=DEV)
-    for _ in range(3):
-        ops.voxelize_seq(*f32, 5, 720, 1280, 0, 0, 720, 1280, out=out, min_events=3)
-    torch.cuda.synchronize()
+    for (H, W, N, T, Hp, Wp, pt, pl) in ((260, 346, 31500, 100, 264, 352, 2, 3), (720, 1280, 333333, 64, 720, 1280, 0, 0)):
+        ev = synth.gen_events(0, T, H, W, N)
+        f32 = [torch.from_numpy(a).to(DEV) for a in synth.to_loader_format_seq(ev)]
+        out = torch.empty(T, 5, Hp, Wp, device=DEV)
+        for _ in range(2):
+            ops.voxelize_seq(*f32, 5, H, W, pt, pl, Hp, Wp, out=out, min_events=3)
+        torch.cuda.synchronize()
     sys.exit(0)
 
 ALGOS = (("2 memset + global RED (default)", 2, {}), ("5 = 2 + warp aggregation", 5, {}), ("1 row-band tiles + warp aggregation", 1, {}),
