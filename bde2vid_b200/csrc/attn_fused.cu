@@ -14,6 +14,7 @@
 // of the expanded [heads, 49, D*49] tensor, which would not fit in shared memory next to the operands.
 #include "common.cuh"
 
+#include <cuda_fp16.h>
 #include <stdlib.h>
 namespace bde {
 namespace tc {
@@ -387,12 +388,11 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
   // "special" unit packs row 48 of all 16 heads into a single tile (tile row = head; the query fragment carries only
   // that head's 4 channels, the key fragment all 64, so each row still sees its own head's dot product).
   const uint32_t vs_u32 = sb + Cfg::OFF_V;
-  const uint32_t ks_u32 = sb + Cfg::OFF_K;
   const uint32_t tbl_u32 = sb + Cfg::OFF_TBL;
   const uint32_t coff_u32 = sb + Cfg::OFF_COFF;
   __nv_bfloat16* os = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_OS);  // C == 64 only
   constexpr int MTN = HD == 4 ? 3 : 4;                 // query tiles per head handled by normal units
-  constexpr int NUNITS = HG * MTN + (HD == 4 ? 1 : 0);
+  constexpr int NUNITS = HG * MTN;
   constexpr uint32_t kOnes = 0x3C003C00u;              // fp16x2 (1, 1)
   constexpr float kLog2e = 1.4426950408889634f;
   if (HD == 4) {
@@ -518,12 +518,72 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
       }
     }
   }
-  for (int unit = HD == 4 ? HG * MTN + warp : warp; unit < NUNITS; unit += kThreadsF / 32) {
-    const bool special = HD == 4 && unit == HG * MTN;
+  if (HD == 4) {
+    // ---- query token 48 of all 16 heads on the CUDA cores: warp = two heads, 16 lanes per head, keys strided over lanes ----
+    // (As a 49th tensor-core unit this row cost one warp ~1000 instructions while the other seven waited at the barrier
+    // below: 10 % of the kernel's warp-time in the round-2 profile.  Spread over every lane it is ~300 per warp.)
+    const int h = warp * 2 + (lane >> 4), sl = lane & 15;
+    float qf[4];
+    {
+      const uint2 qr = *reinterpret_cast<const uint2*>(qs + 48 * PQ + h * 4);
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qr.x));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qr.y));
+      qf[0] = a.x; qf[1] = a.y; qf[2] = b.x; qf[3] = b.y;
+    }
+    const uint32_t ra = tbl_u32 + (uint32_t)(h * tbl_ld * 4 + roff[48]);
+    constexpr int NI = (NKEY + 15) / 16;
+    float sv[NI];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int n = sl + 16 * i;
+      sv[i] = -INFINITY;
+      if (n < n_kv) {
+        const uint2 kr = *reinterpret_cast<const uint2*>(ks + n * PQ + h * 4);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kr.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kr.y));
+        float acc = lds_f32(ra + (uint32_t)coff[n]);
+        acc = fmaf(qf[0], a.x, acc); acc = fmaf(qf[1], a.y, acc); acc = fmaf(qf[2], b.x, acc); acc = fmaf(qf[3], b.y, acc);
+        sv[i] = acc;
+      }
+      mx = fmaxf(mx, sv[i]);
+    }
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float ms = mx * kLog2e;   // every lane owns at least three real keys (n_kv >= 49), so mx is finite
+    float l = 0.f, o4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int n = sl + 16 * i;
+      if (n < n_kv) {
+        float pr;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pr) : "f"(fmaf(sv[i], kLog2e, -ms)));
+        const uint2 vr = *reinterpret_cast<const uint2*>(vs + n * PQ + h * 4);   // fp16 x 4
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&vr.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&vr.y));
+        l += pr;
+        o4[0] = fmaf(pr, a.x, o4[0]); o4[1] = fmaf(pr, a.y, o4[1]); o4[2] = fmaf(pr, b.x, o4[2]); o4[3] = fmaf(pr, b.y, o4[3]);
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      l += __shfl_xor_sync(0xffffffffu, l, o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o4[e] += __shfl_xor_sync(0xffffffffu, o4[e], o);
+    }
+    if (sl == 0) {
+      const float inv = 1.0f / l;
+      uint2 pk;
+      pk.x = pack2(o4[0] * inv, o4[1] * inv);
+      pk.y = pack2(o4[2] * inv, o4[3] * inv);
+      *reinterpret_cast<uint2*>(os + 48 * PQ + h * 4) = pk;
+    }
+  }
+  for (int unit = HD == 4 ? NUNITS : warp; unit < NUNITS; unit += kThreadsF / 32) {   // head_dim >= 8 (C == 256) only
     const int hl = unit / MTN, mt = unit - hl * MTN;
     const int row0 = mt * 16 + g, row1 = row0 + 8;
     float s[NT][4];
-    if (!special) {
+    {
       const uint32_t r0a = tbl_u32 + (uint32_t)(hl * tbl_ld * 4 + roff[row0]);
       const uint32_t r1a = tbl_u32 + (uint32_t)(hl * tbl_ld * 4 + roff[row1]);
       uint32_t qa[4] = {0u, 0u, 0u, 0u};
@@ -554,40 +614,6 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
         if (2 * t + 8 < HD) kb1 = *reinterpret_cast<const uint32_t*>(kr + 2 * t + 8);
         mma16816(s[j], qa, kb0, kb1);
       }
-    } else {
-      // tile row g <-> head g, row g + 8 <-> head g + 8; query token 48
-      const uint32_t r0a = tbl_u32 + (uint32_t)(g * tbl_ld * 4 + roff[48]);
-      const uint32_t r1a = tbl_u32 + (uint32_t)((g + 8) * tbl_ld * 4 + roff[48]);
-      uint32_t qa4[4][4];
-#pragma unroll
-      for (int kq = 0; kq < 4; ++kq) {
-        const int ch0 = 16 * kq + 2 * t, ch1 = ch0 + 8;
-        const uint32_t v0 = *reinterpret_cast<const uint32_t*>(qs + 48 * PQ + ch0);
-        const uint32_t v1 = *reinterpret_cast<const uint32_t*>(qs + 48 * PQ + ch1);
-        qa4[kq][0] = (ch0 >> 2) == g ? v0 : 0u;
-        qa4[kq][1] = (ch0 >> 2) == g + 8 ? v0 : 0u;
-        qa4[kq][2] = (ch1 >> 2) == g ? v1 : 0u;
-        qa4[kq][3] = (ch1 >> 2) == g + 8 ? v1 : 0u;
-      }
-      // ldmatrix.x4 of an 8-key x 32-channel block: b0 / b1 of two consecutive k16 steps
-      const uint32_t kaddr0 = ks_u32 + (uint32_t)(((lane & 7) * PQ + (lane >> 3) * 8) * 2);
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const uint2 cp = lds_u64(coff_u32 + (uint32_t)((j * 8 + 2 * t) * 4));
-        s[j][0] = lds_f32(r0a + cp.x); s[j][1] = lds_f32(r0a + cp.y);
-        s[j][2] = lds_f32(r1a + cp.x); s[j][3] = lds_f32(r1a + cp.y);
-        if (j == NT - 1) {
-          if (j * 8 + 2 * t >= n_kv) s[j][0] = s[j][2] = -1e30f;
-          if (j * 8 + 2 * t + 1 >= n_kv) s[j][1] = s[j][3] = -1e30f;
-        }
-        uint32_t kb[4];
-        ldsm_x4(kb, kaddr0 + (uint32_t)(j * 8 * PQ * 2));
-        mma16816(s[j], qa4[0], kb[0], kb[1]);
-        mma16816(s[j], qa4[1], kb[2], kb[3]);
-        ldsm_x4(kb, kaddr0 + (uint32_t)(j * 8 * PQ * 2 + 64));
-        mma16816(s[j], qa4[2], kb[0], kb[1]);
-        mma16816(s[j], qa4[3], kb[2], kb[3]);
-      }
     }
     // ---- softmax numerators (the row sums come out of the P.V product through a column of ones) -------------------
     float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -607,100 +633,37 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
       pp[j][0] = ex2_h2(fmaf(s[j][0], kLog2e, -m0s), fmaf(s[j][1], kLog2e, -m0s));
       pp[j][1] = ex2_h2(fmaf(s[j][2], kLog2e, -m1s), fmaf(s[j][3], kLog2e, -m1s));
     }
-    auto p_frag = [&](int kk, uint32_t (&pa)[4]) {
+    constexpr int NV = HD >= 8 ? HD / 8 : 1;
+    float o[NV][4], ol[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int v = 0; v < NV; ++v) o[v][0] = o[v][1] = o[v][2] = o[v][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KSTEPS; ++kk) {
+      uint32_t pa[4];
       pa[0] = pp[2 * kk][0];
       pa[1] = pp[2 * kk][1];
       pa[2] = 2 * kk + 1 < NT ? pp[2 * kk + 1][0] : 0u;
       pa[3] = 2 * kk + 1 < NT ? pp[2 * kk + 1][1] : 0u;
-    };
-    if (!special) {
-      if (HD == 4) {
-        // one 8-channel V tile holds a head pair; the other head's columns are replaced by ones -> row sums
-        const bool ones_lane = (g >> 2) != (hl & 1);
-        float oa[4] = {0.f, 0.f, 0.f, 0.f}, ob[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint32_t vaddr = vs_u32 + (uint32_t)(((lane & 15) * PQ + (hl >> 1) * 8) * 2);
 #pragma unroll
-        for (int kk = 0; kk < KSTEPS; ++kk) {
-          uint32_t pa[4];
-          p_frag(kk, pa);
-          uint32_t vb0, vb1;
-          ldsm_x2_trans(vb0, vb1, vaddr + (uint32_t)(kk * 16 * PQ * 2));
-          if (ones_lane) { vb0 = kOnes; vb1 = kOnes; }
-          if (kk & 1) mma16816_f16(ob, pa, vb0, vb1); else mma16816_f16(oa, pa, vb0, vb1);
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) oa[e] += ob[e];
-        const float l0 = __shfl_xor_sync(0xffffffffu, oa[0], 2), l1 = __shfl_xor_sync(0xffffffffu, oa[2], 2);
-        if ((t >> 1) == (hl & 1)) {
-          const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-          const int col = (hl >> 1) * 8 + 2 * t;
-          *reinterpret_cast<uint32_t*>(os + row0 * PQ + col) = pack2(oa[0] * inv0, oa[1] * inv0);
-          *reinterpret_cast<uint32_t*>(os + row1 * PQ + col) = pack2(oa[2] * inv1, oa[3] * inv1);
-        }
-      } else {
-        constexpr int NV = HD >= 8 ? HD / 8 : 1;
-        float o[NV][4], ol[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int v = 0; v < NV; ++v) o[v][0] = o[v][1] = o[v][2] = o[v][3] = 0.f;
-#pragma unroll
-        for (int kk = 0; kk < KSTEPS; ++kk) {
-          uint32_t pa[4];
-          p_frag(kk, pa);
-#pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            uint32_t vb0, vb1;
-            ldsm_x2_trans(vb0, vb1, vs_u32 + (uint32_t)(((kk * 16 + (lane & 15)) * PQ + hl * HD + 8 * v) * 2));
-            mma16816_f16(o[v], pa, vb0, vb1);
-          }
-          mma16816_f16(ol, pa, kOnes, kOnes);   // row sums
-        }
-        const float inv0 = 1.0f / ol[0], inv1 = 1.0f / ol[2];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          const int col = hl * HD + 8 * v + 2 * t;
-          const uint32_t v0 = pack2(o[v][0] * inv0, o[v][1] * inv0), v1 = pack2(o[v][2] * inv1, o[v][3] * inv1);
-          if (C == 64) {
-            *reinterpret_cast<uint32_t*>(os + row0 * PQ + col) = v0;
-            *reinterpret_cast<uint32_t*>(os + row1 * PQ + col) = v1;
-          } else {
-            __nv_bfloat16* og = p.o_out + (size_t)w * kTok * C + hg * 64 + col;
-            if (row0 < kTok) *reinterpret_cast<uint32_t*>(og + (size_t)row0 * C) = v0;
-            if (row1 < kTok) *reinterpret_cast<uint32_t*>(og + (size_t)row1 * C) = v1;
-          }
-        }
+      for (int v = 0; v < NV; ++v) {
+        uint32_t vb0, vb1;
+        ldsm_x2_trans(vb0, vb1, vs_u32 + (uint32_t)(((kk * 16 + (lane & 15)) * PQ + hl * HD + 8 * v) * 2));
+        mma16816_f16(o[v], pa, vb0, vb1);
       }
-    } else {
-      // special unit: P [16 heads x keys] . V [keys x 64 channels]; row g keeps the 4 channels of head g.
-      // Two passes of four channel tiles keep the register footprint under the 2-CTA budget.
-      float ol[4] = {0.f, 0.f, 0.f, 0.f};
+      mma16816_f16(ol, pa, kOnes, kOnes);   // row sums
+    }
+    const float inv0 = 1.0f / ol[0], inv1 = 1.0f / ol[2];
 #pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        float o[4][4];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) o[v][0] = o[v][1] = o[v][2] = o[v][3] = 0.f;
-#pragma unroll
-        for (int kk = 0; kk < KSTEPS; ++kk) {
-          uint32_t pa[4];
-          p_frag(kk, pa);
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            uint32_t vb0, vb1;
-            ldsm_x2_trans(vb0, vb1, vs_u32 + (uint32_t)(((kk * 16 + (lane & 15)) * PQ + (pass * 4 + v) * 8) * 2));
-            mma16816_f16(o[v], pa, vb0, vb1);
-          }
-          if (pass == 0) mma16816_f16(ol, pa, kOnes, kOnes);
-        }
-        const float inv0 = 1.0f / ol[0], inv1 = 1.0f / ol[2];
-        // channel tile pass*4 + v holds heads 2(pass*4 + v), +1: pass 0 -> heads 0..7 = tile rows g, pass 1 -> rows g + 8
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          if ((g >> 1) == v && (t >> 1) == (g & 1)) {
-            const int head = pass * 8 + g;
-            const float a = pass == 0 ? o[v][0] * inv0 : o[v][2] * inv1;
-            const float b = pass == 0 ? o[v][1] * inv0 : o[v][3] * inv1;
-            *reinterpret_cast<uint32_t*>(os + 48 * PQ + head * 4 + 2 * (t & 1)) = pack2(a, b);
-          }
-        }
+    for (int v = 0; v < NV; ++v) {
+      const int col = hl * HD + 8 * v + 2 * t;
+      const uint32_t v0 = pack2(o[v][0] * inv0, o[v][1] * inv0), v1 = pack2(o[v][2] * inv1, o[v][3] * inv1);
+      if (C == 64) {
+        *reinterpret_cast<uint32_t*>(os + row0 * PQ + col) = v0;
+        *reinterpret_cast<uint32_t*>(os + row1 * PQ + col) = v1;
+      } else {
+        __nv_bfloat16* og = p.o_out + (size_t)w * kTok * C + hg * 64 + col;
+        if (row0 < kTok) *reinterpret_cast<uint32_t*>(og + (size_t)row0 * C) = v0;
+        if (row1 < kTok) *reinterpret_cast<uint32_t*>(og + (size_t)row1 * C) = v1;
       }
     }
   }
