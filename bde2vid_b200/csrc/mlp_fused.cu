@@ -38,6 +38,7 @@ struct MlpParams {
   // sum_io[m] += x_new[m] (fp32, in place) and sum_t[m] = bf16(sum_io[m])
   float* sum_io;
   __nv_bfloat16* sum_t;
+  long long* dbg;    // optional per-CTA phase timestamps (8 per CTA), bring-up profiling
 };
 
 __device__ __forceinline__ void mlp_fused_sum(float* sum_io, __nv_bfloat16* sum_t, size_t off, float4 xnew) {
@@ -53,6 +54,50 @@ __device__ __forceinline__ void mlp_fused_sum(float* sum_io, __nv_bfloat16* sum_
   }
 }
 
+// LayerNorm statistics of R rows held as v[R][NKB][8] (8 lanes per row; lane j owns channels 64 kb + 8 j .. + 7).  All R rows
+// advance together and the sums are trees, so every dependent chain (adds, shuffles, rsqrt) has several independent copies
+// in flight: with one row after the other and 32-long serial add chains the phase ran at ~19 cycles per instruction on the
+// two warps a scheduler holds (2.3 K cycles per row, round-2 phase counters).  On return v holds x - mean.
+template <int R, int NKB>
+__device__ __forceinline__ void ln_rows(float (&v)[R][NKB][8], float (&rstd)[R]) {
+  constexpr float kInvC = 1.0f / (float)(NKB * 64);
+  float s[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb) {
+      a0 += (v[i][kb][0] + v[i][kb][1]) + (v[i][kb][2] + v[i][kb][3]);
+      a1 += (v[i][kb][4] + v[i][kb][5]) + (v[i][kb][6] + v[i][kb][7]);
+    }
+    s[i] = a0 + a1;
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+    for (int i = 0; i < R; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const float mean = s[i] * kInvC;
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb)
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        const float d0 = v[i][kb][e] - mean, d1 = v[i][kb][e + 1] - mean;
+        v[i][kb][e] = d0; v[i][kb][e + 1] = d1;
+        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1);
+      }
+    s[i] = q0 + q1;
+  }
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+    for (int i = 0; i < R; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+#pragma unroll
+  for (int i = 0; i < R; ++i) rstd[i] = rsqrtf(fmaf(s[i], kInvC, 1e-5f));
+}
+
 __global__ void __launch_bounds__(kMlpThreads, 2)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2, const MlpParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -66,6 +111,17 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM;
+  // bring-up timestamps: the whole of warp 0 takes them (a warp-uniform branch) and re-converges at once -- a single diverged
+  // lane made every later __shfl_sync of its warp take the divergent slow path and inflated the LayerNorm phase by 6 K cycles
+  const bool dbg = p.dbg != nullptr && threadIdx.x < 32;
+  const long long t_begin = dbg ? clock64() : 0;
+  auto mark = [&](int slot) {
+    if (dbg) {
+      const long long c = clock64() - t_begin;
+      if (threadIdx.x == 0) p.dbg[(size_t)blockIdx.x * 8 + slot] = c;
+      __syncwarp();
+    }
+  };
 
   for (int i = threadIdx.x; i < kMlpH + kMlpC; i += kMlpThreads) b1_s[i] = i < kMlpH ? __ldg(p.b1 + i) : __ldg(p.b2 + i - kMlpH);
   if (threadIdx.x == 0) {
@@ -86,53 +142,48 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
   tcgen05_fence_after();
   const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t*>(sgen + kMlpOffBar + 48);
 
+  mark(0);
   if (warp < kNumProducerWarps) {
     // ---------------- LayerNorm producer: lane j = lane & 7 owns 8 channels of rows warp*16 + 4i + (lane >> 3) -------
     const int j = lane & 7, rsub = lane >> 3;
+    {
+      float v[kRowsPerThread][1][8];
 #pragma unroll
-    for (int i = 0; i < kRowsPerThread; ++i) {
-      const int row = warp * (4 * kRowsPerThread) + i * 4 + rsub;
-      const int mm = m0 + row;
-      float v[8];
-      if (mm < p.P) {
-        const float4 t0 = *reinterpret_cast<const float4*>(p.x + (size_t)mm * kMlpC + j * 8);
-        const float4 t1 = *reinterpret_cast<const float4*>(p.x + (size_t)mm * kMlpC + j * 8 + 4);
-        v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
-      } else {
+      for (int i = 0; i < kRowsPerThread; ++i) {   // every load of the thread is in flight before the first reduction
+        const int mm = m0 + warp * (4 * kRowsPerThread) + i * 4 + rsub;
+        if (mm < p.P) {
+          const float4 t0 = *reinterpret_cast<const float4*>(p.x + (size_t)mm * kMlpC + j * 8);
+          const float4 t1 = *reinterpret_cast<const float4*>(p.x + (size_t)mm * kMlpC + j * 8 + 4);
+          v[i][0][0] = t0.x; v[i][0][1] = t0.y; v[i][0][2] = t0.z; v[i][0][3] = t0.w;
+          v[i][0][4] = t1.x; v[i][0][5] = t1.y; v[i][0][6] = t1.z; v[i][0][7] = t1.w;
+        } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+          for (int e = 0; e < 8; ++e) v[i][0][e] = 0.f;
+        }
       }
-      float sum = 0.f;
+      float rstd[kRowsPerThread];
+      ln_rows<kRowsPerThread, 1>(v, rstd);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) sum += v[e];
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-      const float mean = sum / (float)kMlpC;
-      float sq = 0.f;
+      for (int i = 0; i < kRowsPerThread; ++i) {
+        const int row = warp * (4 * kRowsPerThread) + i * 4 + rsub;
+        float o[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        v[e] -= mean;
-        sq += v[e] * v[e];
+        for (int e = 0; e < 8; ++e) o[e] = v[i][0][e] * rstd[i];
+        const uint4 pk = pack8_bf16(o);
+        const uint32_t dst = s_a + (uint32_t)row * 128u + (((uint32_t)j ^ (uint32_t)(row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
       }
-      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-      sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-      sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-      const float rstd = 1.0f / sqrtf(sq / (float)kMlpC + 1e-5f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] *= rstd;
-      const uint4 pk = pack8_bf16(v);
-      const uint32_t dst = s_a + (uint32_t)row * 128u + (((uint32_t)j ^ (uint32_t)(row & 7)) << 4);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
     }
     fence_proxy_async_smem();
     mbar_arrive(bar_a);
+    mark(1);
 
     // ---------------- epilogue 1: hidden = GELU(acc1 + b1) -> bf16, swizzled K-major tile for GEMM 2 -----------------
     const int q = warp & 3, half = warp >> 2;
     const int row = q * 32 + lane;  // TMEM lane == tile row
     const uint32_t lane_taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
     mbar_wait(bar_acc1, 0);
+    mark(2);
     tcgen05_fence_after();
 #pragma unroll 1
     for (int ch = 0; ch < 4; ++ch) {
@@ -155,13 +206,23 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
     tcgen05_fence_before();   // our TMEM reads are done before GEMM 2 overwrites the columns
     fence_proxy_async_smem();
     mbar_arrive(bar_h);
+    mark(3);
 
     // ---------------- epilogue 2: x += acc2 + b2, coalesced through a per-warp smem transpose ---------------------------
+    // The residual rows are fetched BEFORE waiting for GEMM 2 (they do not depend on it): inside the store loop every
+    // load waited behind the previous store to the same array, eight global round trips in a row.
+    const int rq = lane >> 3, cq = (lane & 7) * 4;
+    float4 cur8[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int mm = m0 + q * 32 + it * 4 + rq;
+      cur8[it] = mm < p.P ? __ldcg(reinterpret_cast<const float4*>(p.x + (size_t)mm * kMlpC + half * 32 + cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     mbar_wait(bar_acc2, 0);
+    mark(4);
     tcgen05_fence_after();
     constexpr int kPitch = 36;
     float* stg = reinterpret_cast<float*>(sgen) + warp * (32 * kPitch);  // the H region is free once GEMM 2 has completed
-    const int rq = lane >> 3, cq = (lane & 7) * 4;
     {
       uint32_t raw[32];
       tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(half * 32), raw);
@@ -178,7 +239,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
         if (mm < p.P) {
           const float4 acc = *reinterpret_cast<const float4*>(stg + (it * 4 + rq) * kPitch + cq);
           float4* dst = reinterpret_cast<float4*>(p.x + (size_t)mm * kMlpC + half * 32 + cq);
-          float4 cur = *dst;
+          float4 cur = cur8[it];
           cur.x += acc.x + bb.x; cur.y += acc.y + bb.y; cur.z += acc.z + bb.z; cur.w += acc.w + bb.w;
           *dst = cur;
           if (p.sum_io != nullptr) mlp_fused_sum(p.sum_io, p.sum_t, (size_t)mm * kMlpC + half * 32 + cq, cur);
@@ -186,6 +247,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
       }
     }
     tcgen05_fence_before();
+    mark(5);
   } else {
     // ---------------- TMA + MMA warp: all lanes wait, one elected lane issues (elect_one_sync, tc_common.cuh) --------------
     if (elect_one_sync()) {
@@ -263,14 +325,14 @@ struct Mlp3Params {
   int P;
   float* sum_io;             // optional fused "x + merged" (see MlpParams)
   __nv_bfloat16* sum_t;
+  long long* dbg;            // optional per-CTA phase timestamps (8 per CTA), bring-up profiling
 };
 
 // CL > 1: a thread-block CLUSTER of CL CTAs shares one 128-row tile and splits the HIDDEN dimension: CTA `rank` runs the
 // chunks rank, rank + CL, ... (fc1 + GELU + its K-slice of fc2), so every CTA streams only 1 / CL of the 1 MB of weights
 // and does 1 / CL of the GELU work, and CL x as many SMs are busy (46 tiles -> 92 CTAs for four 33 x 44 maps; the single-CTA
-// form ran on 46 of the 148 SMs).  The partial fc2 accumulators are then exchanged through distributed shared memory:
-// CTA r finalises output columns [256 r / CL, 256 (r + 1) / CL) = its own TMEM partial + the peers' partials in a FIXED
-// order (deterministic, no atomics), + bias + residual.
+// form ran on 46 of the 148 SMs).  The partial fc2 accumulators are summed into x in CL phases separated by cluster
+// barriers (see the final epilogue): a fixed order, deterministic, no atomics.
 __device__ __forceinline__ uint32_t m3_cluster_rank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -279,15 +341,6 @@ __device__ __forceinline__ uint32_t m3_cluster_rank() {
 __device__ __forceinline__ void m3_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ uint32_t m3_mapa(uint32_t addr, uint32_t cta) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
-  return r;
-}
-__device__ __forceinline__ void m3_st_cluster_v4(uint32_t addr, float4 v) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
 template <int CL>
 __global__ void __launch_bounds__(kM3Threads, 1)
 mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_w2, const Mlp3Params p) {
@@ -312,6 +365,17 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = (blockIdx.x / CL) * BM;
+  // bring-up timestamps: the whole of warp 0 takes them (a warp-uniform branch) and re-converges at once -- a single diverged
+  // lane made every later __shfl_sync of its warp take the divergent slow path and inflated the LayerNorm phase by 6 K cycles
+  const bool dbg = p.dbg != nullptr && threadIdx.x < 32;
+  const long long t_begin = dbg ? clock64() : 0;
+  auto mark = [&](int slot) {
+    if (dbg) {
+      const long long c = clock64() - t_begin;
+      if (threadIdx.x == 0) p.dbg[(size_t)blockIdx.x * 8 + slot] = c;
+      __syncwarp();
+    }
+  };
 
   if (threadIdx.x == 0) {
     mbar_init(bar_xn, kNumProducerThreads);
@@ -338,52 +402,41 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + kM3OffBar + 128);
   const uint32_t acc2 = tmem_base + 256;   // acc1[a] = tmem_base + 128 a
 
+  mark(0);
   if (warp < kNumProducerWarps) {
     // ---------------- LayerNorm producer (affine folded into W1 / b1 by the caller) ------------------------------------
+    // All 32 loads of the thread (4 row passes x 1 KB rows) are issued before the first reduction, then ln_rows() advances
+    // the four rows together.
     {
       const int j = lane & 7, rsub = lane >> 3;
-#pragma unroll 2
+      float v[kRowsPerThread][4][8];
+#pragma unroll
       for (int i = 0; i < kRowsPerThread; ++i) {
-        const int row = warp * (4 * kRowsPerThread) + i * 4 + rsub;
-        const int mm = m0 + row;
-        float v[4][8];
-        float sum = 0.f;
+        const int mm = m0 + warp * (4 * kRowsPerThread) + i * 4 + rsub;
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           if (mm < p.P) {
             const float* src = p.x + (size_t)mm * kM3C + kb * 64 + j * 8;
             const float4 t0 = *reinterpret_cast<const float4*>(src), t1 = *reinterpret_cast<const float4*>(src + 4);
-            v[kb][0] = t0.x; v[kb][1] = t0.y; v[kb][2] = t0.z; v[kb][3] = t0.w;
-            v[kb][4] = t1.x; v[kb][5] = t1.y; v[kb][6] = t1.z; v[kb][7] = t1.w;
+            v[i][kb][0] = t0.x; v[i][kb][1] = t0.y; v[i][kb][2] = t0.z; v[i][kb][3] = t0.w;
+            v[i][kb][4] = t1.x; v[i][kb][5] = t1.y; v[i][kb][6] = t1.z; v[i][kb][7] = t1.w;
           } else {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[kb][e] = 0.f;
+            for (int e = 0; e < 8; ++e) v[i][kb][e] = 0.f;
           }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) sum += v[kb][e];
         }
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-        const float mean = sum / (float)kM3C;
-        float sq = 0.f;
+      }
+      float rstd[kRowsPerThread];
+      ln_rows<kRowsPerThread, 4>(v, rstd);
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            v[kb][e] -= mean;
-            sq += v[kb][e] * v[kb][e];
-          }
-        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-        sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-        const float rstd = 1.0f / sqrtf(sq / (float)kM3C + 1e-5f);
+      for (int i = 0; i < kRowsPerThread; ++i) {
+        const int row = warp * (4 * kRowsPerThread) + i * 4 + rsub;
         const uint32_t dst = s_xn + (uint32_t)row * 128u + (((uint32_t)j ^ (uint32_t)(row & 7)) << 4);
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           float o[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = v[kb][e] * rstd;
+          for (int e = 0; e < 8; ++e) o[e] = v[i][kb][e] * rstd[i];
           const uint4 pk = pack8_bf16(o);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kb * (BM * 128)), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w)
                        : "memory");
@@ -392,6 +445,7 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
       fence_proxy_async_smem();
       mbar_arrive(bar_xn);
     }
+    mark(1);
     // ---------------- GELU epilogues: thread = tile row, 64 hidden columns of the chunk per warp half ------------------
     const int q = warp & 3, half = warp >> 2;
     const int row = q * 32 + lane;
@@ -400,7 +454,13 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
     for (int jl = 0; jl < NL; ++jl) {
       const int jc = rank + CL * jl;            // global hidden chunk
       const uint32_t a = jl & 1, ph = (jl >> 1) & 1;
+      // this chunk's 64 bias values travel while the thread waits for the accumulator
+      const float* b1p = p.b1 + jc * kM3Chunk + half * 64;
+      float4 bia[16];
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) bia[jj] = __ldg(reinterpret_cast<const float4*>(b1p + jj * 4));
       mbar_wait(bar_a1full + 8 * a, ph);
+      if (jl == 0) mark(2);
       tcgen05_fence_after();
       uint32_t raw0[32], raw1[32];
       tmem_ld_32x32b_x32(tmem_base + a * 128 + lane_off + (uint32_t)(half * 64), raw0);
@@ -410,11 +470,10 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_a1empty + 8 * a);   // fc1 of chunk jc + 2 may overwrite the accumulator
       mbar_wait(bar_hempty + 8 * a, ph ^ 1u);            // fc2 of chunk jc - 2 has finished reading H[a]
-      const float* b1p = p.b1 + jc * kM3Chunk + half * 64;
       const uint32_t hrow = s_h + a * 32768 + (uint32_t)half * (BM * 128) + (uint32_t)row * 128u;   // slab `half` of H[a]
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
-        const float4 bA = __ldg(reinterpret_cast<const float4*>(b1p + jj * 8)), bB = __ldg(reinterpret_cast<const float4*>(b1p + jj * 8 + 4));
+        const float4 bA = bia[2 * jj], bB = bia[2 * jj + 1];
         const uint32_t* r = jj < 4 ? raw0 + jj * 8 : raw1 + (jj - 4) * 8;
         float o[8];
         o[0] = fast_gelu(__uint_as_float(r[0]) + bA.x); o[1] = fast_gelu(__uint_as_float(r[1]) + bA.y);
@@ -428,7 +487,9 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
       fence_proxy_async_smem();
       mbar_arrive(bar_hfull + 8 * a);
     }
+    mark(3);
     mbar_wait(bar_a2full, 0);     // this CTA's (partial) fc2 accumulator is complete: all its MMAs have retired
+    mark(4);
     tcgen05_fence_after();
   } else if (warp == kTmaWarp) {
     // ---------------- weight loads, in the order the MMA warp consumes them ----------------------------------------------
@@ -520,84 +581,72 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
     }
   }
 
-  // ---------------- exchange of the partial accumulators (CL > 1) and final epilogue -------------------------------------
-  // staging slots (fp32 [128 rows][NC cols], 16-byte chunks XOR-swizzled by row) live in the XN / H regions, which are free
-  // in EVERY CTA of the cluster once all of them have passed the first cluster barrier (their MMAs have retired)
-  constexpr int kSlotBytes = BM * NC * 4;
+  // ---------------- final epilogue: x += (sum over the cluster of the partial fc2 accumulators) + b2 -----------------------
+  // CL > 1: the partial sums meet IN x (global memory, i.e. L2) instead of in distributed shared memory: the DSMEM exchange
+  // of 64 KB per CTA ran at the ~17 B / clk of the SM-to-SM network (7.2 K cycles, round-2 phase counters).
+  // Phase k < CL - 1: CTA r adds its partial of the columns OWNED by CTA (r + 1 + k) % CL into x, then a cluster barrier
+  // (release / acquire: the peers' global writes are visible; the loads bypass L1); last phase: its own columns + b2.
+  // Every element is updated by exactly one CTA per phase, in a fixed order -> deterministic, no atomics.
   const int q = warp & 3, half = warp >> 2;
   const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-  if (CL > 1) {
-    m3_cluster_sync();
+  float* stg = reinterpret_cast<float*>(sgen) + warp * 1024;   // per-warp transpose tile in the XN region (this CTA's MMAs have retired)
+  const int rq = lane >> 3, cq4 = lane & 7;
+  if (CL > 1) m3_cluster_sync();   // nobody writes x before every CTA of the cluster has read its LayerNorm rows
+  mark(5);
+#pragma unroll 1
+  for (int ph = 0; ph < CL; ++ph) {
+    const int owner = (rank + 1 + ph) % CL;   // ph == CL - 1: my own columns
+    const bool last = ph == CL - 1;
     if (warp < kNumProducerWarps) {
-      const int row = q * 32 + lane;
-      for (int pr = 0; pr < CL; ++pr) {
-        if (pr == rank) continue;
-        const int slot = rank < pr ? rank : rank - 1;            // my slot in peer pr (its peers in rank order)
-        const uint32_t dst_row = m3_mapa(sb + slot * kSlotBytes + (uint32_t)row * (NC * 4), (uint32_t)pr);
-#pragma unroll 1
-        for (int c0 = half * (NC / 2); c0 < (half + 1) * (NC / 2); c0 += 32) {      // my partial of the peer's columns
-          uint32_t raw[32];
-          tmem_ld_32x32b_x32(acc2 + lane_off + (uint32_t)(pr * NC + c0), raw);
-          tmem_ld_wait();
+      auto load_rows = [&](int cb, float4 (&dst)[8]) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const int chunk = (c0 >> 2) + j4;
-            m3_st_cluster_v4(dst_row + (uint32_t)(((chunk & ~7) | ((chunk ^ row) & 7)) << 4),
-                             make_float4(__uint_as_float(raw[4 * j4]), __uint_as_float(raw[4 * j4 + 1]),
-                                         __uint_as_float(raw[4 * j4 + 2]), __uint_as_float(raw[4 * j4 + 3])));
-          }
+        for (int it = 0; it < 8; ++it) {
+          const int mm = m0 + q * 32 + it * 4 + rq;
+          dst[it] = mm < p.P ? __ldcg(reinterpret_cast<const float4*>(p.x + (size_t)mm * kM3C + cb + cq4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      }
-    }
-    m3_cluster_sync();   // every peer's partial of my columns has landed in my staging slots
-  }
-  if (warp < kNumProducerWarps) {
-    // x += (sum of the partial accumulators) + b2 for my columns, coalesced through a per-warp smem transpose
-    float* stg = reinterpret_cast<float*>(sgen + 98304) + warp * 1024;      // above the (CL - 1) staging slots (<= 96 KB)
-    const int rq = lane >> 3, cq4 = lane & 7;
-#pragma unroll 1
-    for (int cl = half * 32; cl < NC; cl += 64) {      // local column offset inside my NC columns
-      const int cb = rank * NC + cl;
-      uint32_t raw[32];
-      tmem_ld_32x32b_x32(acc2 + lane_off + (uint32_t)cb, raw);
-      tmem_ld_wait();
-      __syncwarp();
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4)
-        *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
-            make_float4(__uint_as_float(raw[4 * j4]), __uint_as_float(raw[4 * j4 + 1]), __uint_as_float(raw[4 * j4 + 2]),
-                        __uint_as_float(raw[4 * j4 + 3]));
-      __syncwarp();
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + cb + cq4 * 4));
+      };
       float4 cur[8];
+      load_rows(owner * NC + half * 32, cur);
+#pragma unroll 1
+      for (int cl = half * 32; cl < NC; cl += 64) {
+        const int cb = owner * NC + cl;
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(acc2 + lane_off + (uint32_t)cb, raw);
+        tmem_ld_wait();
+        __syncwarp();
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int mm = m0 + q * 32 + it * 4 + rq;
-        cur[it] = mm < p.P ? *reinterpret_cast<const float4*>(p.x + (size_t)mm * kM3C + cb + cq4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+        for (int j4 = 0; j4 < 8; ++j4)
+          *reinterpret_cast<float4*>(stg + lane * 32 + ((j4 ^ (lane & 7)) << 2)) =
+              make_float4(__uint_as_float(raw[4 * j4]), __uint_as_float(raw[4 * j4 + 1]), __uint_as_float(raw[4 * j4 + 2]),
+                          __uint_as_float(raw[4 * j4 + 3]));
+        __syncwarp();
+        float4 nxt[8];
+        if (cl + 64 < NC) load_rows(cb + 64, nxt);   // the next pass's rows travel while this pass is added and stored
+        const float4 bb = last ? __ldg(reinterpret_cast<const float4*>(p.b2 + cb + cq4 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + rq;
-        const int trow = q * 32 + r;
-        const int mm = m0 + trow;
-        float4 acc = *reinterpret_cast<const float4*>(stg + r * 32 + ((cq4 ^ (r & 7)) << 2));
-        if (CL > 1) {
-          const int chunk = (cl >> 2) + cq4;
-#pragma unroll
-          for (int sl = 0; sl < CL - 1; ++sl) {
-            const float4 pv = *reinterpret_cast<const float4*>(sgen + sl * kSlotBytes + trow * (NC * 4) + (((chunk & ~7) | ((chunk ^ trow) & 7)) << 4));
-            acc.x += pv.x; acc.y += pv.y; acc.z += pv.z; acc.w += pv.w;
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + rq;
+          const int mm = m0 + q * 32 + r;
+          const float4 acc = *reinterpret_cast<const float4*>(stg + r * 32 + ((cq4 ^ (r & 7)) << 2));
+          if (mm < p.P) {
+            const float4 xnew = make_float4(cur[it].x + acc.x + bb.x, cur[it].y + acc.y + bb.y, cur[it].z + acc.z + bb.z, cur[it].w + acc.w + bb.w);
+            *reinterpret_cast<float4*>(p.x + (size_t)mm * kM3C + cb + cq4 * 4) = xnew;
+            if (last && p.sum_io != nullptr) mlp_fused_sum(p.sum_io, p.sum_t, (size_t)mm * kM3C + cb + cq4 * 4, xnew);
           }
         }
-        if (mm < p.P) {
-          const float4 xnew = make_float4(cur[it].x + acc.x + bb.x, cur[it].y + acc.y + bb.y, cur[it].z + acc.z + bb.z, cur[it].w + acc.w + bb.w);
-          *reinterpret_cast<float4*>(p.x + (size_t)mm * kM3C + cb + cq4 * 4) = xnew;
-          if (p.sum_io != nullptr) mlp_fused_sum(p.sum_io, p.sum_t, (size_t)mm * kM3C + cb + cq4 * 4, xnew);
+        if (cl + 64 < NC) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) cur[it] = nxt[it];
         }
       }
     }
-    tcgen05_fence_before();
+    if (CL > 1 && !last) {
+      m3_cluster_sync();
+      mark(6);
+    }
   }
+  if (warp < kNumProducerWarps) tcgen05_fence_before();
+  mark(7);
 
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -647,14 +696,16 @@ extern "C" int bde_mlp_fused_sum(float* x, size_t rows, int c, int hidden, const
     // cluster size: split the hidden dimension over 2 (or 4) CTAs while the grid still fits one wave of SMs
     const int tiles = (int)ceil_div(rows, BM);
     const int n_sm = device_sm_count();
-    // (measured on B200, tools/mlp_probe.py: 46 tiles 29.1 -> 24.8 us with 2 CTAs per tile; 4 per tile is not faster even for 12 tiles)
-    int cl = tiles * 2 <= n_sm ? 2 : 1;
+    // (measured on B200, tools/mlp_probe.py, us per launch for 1 / 2 / 4 CTAs per tile: 46 tiles 25.2 / 21.0 / 33.3 (184 CTAs no longer
+    // fit one wave), 12 tiles 25.1 / 20.9 / 17.9)
+    int cl = tiles * 4 <= n_sm ? 4 : (tiles * 2 <= n_sm ? 2 : 1);
     if (const char* e = getenv("BDE2VID_MLP256_CLUSTER")) {
       const int f = atoi(e);
       if (f == 1 || f == 2 || f == 4) cl = f;
     }
     void (*kern)(const CUtensorMap, const CUtensorMap, const Mlp3Params) =
         cl == 4 ? mlp_fused256_kernel<4> : (cl == 2 ? mlp_fused256_kernel<2> : mlp_fused256_kernel<1>);
+    p3.dbg = (g_dbg != nullptr && (size_t)tiles * cl <= g_dbg_ctas) ? g_dbg : nullptr;
     cudaError_t e = cudaSuccess;
     if (first_use_on_device((const void*)kern)) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kM3Smem);
     BDE_REQUIRE(e == cudaSuccess, "bde_mlp_fused: smem attribute: %s", cudaGetErrorString(e));
@@ -686,6 +737,7 @@ extern "C" int bde_mlp_fused_sum(float* x, size_t rows, int c, int hidden, const
   MlpParams p;
   p.x = x; p.b1 = b1; p.b2 = b2; p.P = (int)rows;
   p.sum_io = sum_io; p.sum_t = (__nv_bfloat16*)sum_t;
+  p.dbg = (g_dbg != nullptr && ceil_div(rows, BM) <= g_dbg_ctas) ? g_dbg : nullptr;
   mlp_fused_kernel<<<(unsigned)ceil_div(rows, BM), kMlpThreads, kMlpSmem, (cudaStream_t)stream>>>(t1, t2, p);
   return check_launch("mlp_fused_kernel");
 }

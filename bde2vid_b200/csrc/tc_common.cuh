@@ -78,6 +78,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// Same wait with a sleep between polls, for the single-purpose warps (TMA producer, MMA issuer) whose waits are long: a warp
+// spinning on try_wait is always ready to issue and takes the scheduler slots of the worker warps on its sub-partition.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, uint32_t ns = 64) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(ns);
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -245,17 +263,17 @@ __device__ __forceinline__ float mufu_tanh(float x) {
 __device__ __forceinline__ float mufu_sigmoid(float x) { return fmaf(mufu_tanh(0.5f * x), 0.5f, 0.5f); }
 
 // Exact-erf GELU (DTransformer.py:345-346, nn.GELU approximate='none') for the bf16 path, as x * sigmoid(p(x)) with an
-// odd degree-5 polynomial p fitted (minimax over [-6, 6], tools: scipy least squares) to the logit of the normal CDF:
-// |error| <= 5.4e-5 absolute, 40x below the bf16 rounding the result undergoes, in ~10 instructions (2 MUFU) instead
-// of ~26 for the Abramowitz & Stegun erf form used before.  The coefficients carry the factor -log2(e) of the exp.
-// The fp32 parity engine keeps erff.
+// odd degree-5 polynomial p fitted (minimax over [-6, 6], scipy least squares) to the logit of the normal CDF
+// (|error of the form| <= 5.4e-5), and sigmoid(p) = 0.5 + 0.5 tanh(p / 2) so that ONE MUFU op (tanh.approx, relative
+// error 2^-11) serves an element: the ex2 + rcp form kept the XU pipe busy for 2 x 8 cycles per warp instruction and made
+// the GELU epilogues of both fused MLP kernels MUFU-bound (4 K cycles per 128 x 128 chunk, round-2 phase counters).
+// Absolute error <= 0.5 |x| 2^-11, below the bf16 rounding (2^-9 |gelu|) except in the far negative tail where it stays
+// under 1.3e-3.  The fp32 parity engine keeps erff.
 __device__ __forceinline__ float fast_gelu(float x) {
-  const float xc = fminf(fmaxf(x, -5.0f), 5.0f);
-  const float x2 = xc * xc;
-  const float q = xc * fmaf(x2, fmaf(x2, 1.10189789e-3f, -1.07380675e-1f), -2.30034094f);  // -log2(e) * p(xc)
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
-  return __fdividef(x, 1.0f + e);
+  const float x2 = fminf(x * x, 25.0f);   // beyond |x| = 5 the polynomial factor is frozen: the argument stays monotone and tanh saturates
+  const float r = x * fmaf(x2, fmaf(x2, -3.81888e-4f, 3.72153e-2f), 7.972375e-1f);   // p(x) / 2
+  const float h = 0.5f * x;
+  return fmaf(h, mufu_tanh(r), h);
 }
 
 __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
