@@ -1,6 +1,7 @@
 // C-ABI glue: error reporting, device check and the bde_gemm dispatcher.
 #include <stdarg.h>
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace bde {
 
@@ -27,6 +28,11 @@ bool first_use_on_device(const void* key) {
   std::lock_guard<std::mutex> lock(mu);
   return seen.insert(std::make_pair(dev, key)).second;
 }
+bool pdl_enabled() {
+  const char* e = getenv("BDE2VID_PDL");
+  return !(e != nullptr && e[0] == '0');
+}
+
 int device_sm_count() {
   static int cache[64] = {0};
   int dev = 0;

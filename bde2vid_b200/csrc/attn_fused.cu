@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
   const int n_kv = p.D * kTok;
   const int tbl_ld = p.D * kRel;
 
+  pdl_trigger();   // the next kernel of the chain may start its prologue
   // ---- weight slices (q, k, v rows of this head group) -> smem, asynchronously ----------------------
   auto load_w_slice = [&](int which, int buf) {  // which: 0 = q, 1 = k, 2 = v
     const __nv_bfloat16* src = p.wqkv + (size_t)(which * C + hg * 64) * C;
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
     pix_s[tid] = tid < kTok ? __ldg(p.tok_map + (size_t)w * kTok + tid) : -1;
   }
   __syncthreads();
+  pdl_wait();   // everything above is static data; the frames below were written by the previous kernel of the chain
 
   // ---- gather + LayerNorm: 8 lanes per token, 4 tokens per warp pass ----------------------------------
   // The loads of NB passes are issued together (independent global reads in flight) before any of them is reduced.
@@ -249,8 +251,8 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
 #pragma unroll
         for (int kb = 0; kb < NCH; ++kb) {
           if (src != nullptr) {
-            const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + kb * 64));
-            const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + kb * 64 + 4));
+            const float4 t0 = *(reinterpret_cast<const float4*>(src + kb * 64));
+            const float4 t1 = *(reinterpret_cast<const float4*>(src + kb * 64 + 4));
             v[b][kb][0] = t0.x; v[b][kb][1] = t0.y; v[b][kb][2] = t0.z; v[b][kb][3] = t0.w;
             v[b][kb][4] = t1.x; v[b][kb][5] = t1.y; v[b][kb][6] = t1.z; v[b][kb][7] = t1.w;
           } else {
@@ -684,7 +686,7 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
         const int pix = r < kTok ? pix_s[r] : -1;
 #pragma unroll
         for (int n = 0; n < 2; ++n)
-          sc[i][hrow][n] = pix >= 0 ? __ldg(reinterpret_cast<const float2*>(shortcut + (size_t)pix * C + npair * 16 + n * 8 + 2 * t))
+          sc[i][hrow][n] = pix >= 0 ? *(reinterpret_cast<const float2*>(shortcut + (size_t)pix * C + npair * 16 + n * 8 + 2 * t))
                                     : make_float2(0.f, 0.f);
       }
     __syncthreads();
@@ -729,7 +731,8 @@ int launch_fused(const FusedAttnParams& p, cudaStream_t s) {
   }
   FusedAttnParams q = p;
   q.dbg = (tc::g_dbg != nullptr && (size_t)p.n_win * (C / 64) <= tc::g_dbg_ctas) ? tc::g_dbg : nullptr;
-  kern<<<p.n_win * (C / 64), kThreadsF, Cfg::SMEM, s>>>(q);
+  const cudaError_t le = launch_pdl(kern, (unsigned)(p.n_win * (C / 64)), (unsigned)kThreadsF, (size_t)Cfg::SMEM, s, 1, q);
+  BDE_REQUIRE(le == cudaSuccess, "bde_window_attention_fused: launch: %s", cudaGetErrorString(le));
   return check_launch("attn_fused_kernel");
 }
 
@@ -869,6 +872,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
     pix_s[tid] = tid < kTok ? __ldg(p.tok_map + (size_t)w * kTok + tid) : -1;
   }
   __syncthreads();
+  pdl_wait();   // the frames (and the precomputed k | v) below were written by earlier kernels of the chain
 
   // ---- gather + LayerNorm, once per window: 8 lanes per token, 64 tokens per pass ---------------------
   {
@@ -890,8 +894,8 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb) {
         if (src != nullptr) {
-          const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + kb * 64));
-          const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + kb * 64 + 4));
+          const float4 t0 = *(reinterpret_cast<const float4*>(src + kb * 64));
+          const float4 t1 = *(reinterpret_cast<const float4*>(src + kb * 64 + 4));
           v[kb][0] = t0.x; v[kb][1] = t0.y; v[kb][2] = t0.z; v[kb][3] = t0.w;
           v[kb][4] = t1.x; v[kb][5] = t1.y; v[kb][6] = t1.z; v[kb][7] = t1.w;
         } else {
@@ -1187,7 +1191,8 @@ int launch_win256(const FusedAttnParams& p, cudaStream_t s) {
   }
   FusedAttnParams q = p;
   q.dbg = (tc::g_dbg != nullptr && (size_t)p.n_win <= tc::g_dbg_ctas) ? tc::g_dbg : nullptr;
-  kern<<<p.n_win, kThreadsW, Cfg::SMEM, s>>>(q);
+  const cudaError_t le = launch_pdl(kern, (unsigned)p.n_win, (unsigned)kThreadsW, (size_t)Cfg::SMEM, s, 1, q);
+  BDE_REQUIRE(le == cudaSuccess, "bde_window_attention_fused: launch: %s", cudaGetErrorString(le));
   return check_launch("attn_win256_kernel");
 }
 

@@ -214,6 +214,7 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
   const long long t_begin = dbg ? clock64() : 0;
   long long t_ln = 0, t_wait = 0, t_conv = 0, t_attn = 0;
 
+  pdl_trigger();   // the next kernel of the chain may start its prologue
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
@@ -329,6 +330,7 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
     }
     for (int i = tid; i < 768; i += kWorkers) bias_s[i] = __ldg(p.bqkv + i);
     worker_sync();
+    pdl_wait();   // everything above is static data; the frames below were written by the previous kernel of the chain
 
     // ---- gather + LayerNorm -> 128B-swizzled K-major slabs (8 lanes per token, 64 tokens per pass) ------------------------
     // The loads of pass i + 1 are issued before pass i is reduced (two passes of 32 registers in flight), and the MMA warp
@@ -351,8 +353,8 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
           if (src != nullptr) {
-            const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + kb * 64));
-            const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + kb * 64 + 4));
+            const float4 t0 = *(reinterpret_cast<const float4*>(src + kb * 64));
+            const float4 t1 = *(reinterpret_cast<const float4*>(src + kb * 64 + 4));
             v[kb][0] = t0.x; v[kb][1] = t0.y; v[kb][2] = t0.z; v[kb][3] = t0.w;
             v[kb][4] = t1.x; v[kb][5] = t1.y; v[kb][6] = t1.z; v[kb][7] = t1.w;
           } else {
@@ -610,7 +612,7 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
         for (int e = 0; e < 8; ++e) {
           const int tok = (c0 + i) * 8 + e;
           const int pix = (i < nch && tok < kTok) ? pix_s[tok] : -1;
-          sc[i][e] = pix >= 0 ? __ldg(shortcut + (size_t)pix * C + ch) : 0.f;
+          sc[i][e] = pix >= 0 ? *(shortcut + (size_t)pix * C + ch) : 0.f;
         }
       mbar_wait_polite(bar_pfull, 0, lane);
       tcgen05_fence_after();
@@ -653,7 +655,8 @@ int launch_tc256(const CUtensorMap& tq, const CUtensorMap& tp, const TcAttnParam
   }
   TcAttnParams q = p;
   q.dbg = (g_dbg != nullptr && (size_t)2 * p.n_win <= g_dbg_ctas) ? g_dbg : nullptr;   // rows [n_win, 2 n_win): MMA-warp timeline
-  kern<<<p.n_win, kThreadsT, Cfg::SMEM, s>>>(tq, tp, q);
+  const cudaError_t le = launch_pdl(kern, (unsigned)p.n_win, (unsigned)kThreadsT, (size_t)Cfg::SMEM, s, 1, tq, tp, q);
+  BDE_REQUIRE(le == cudaSuccess, "bde_window_attention_fused: launch: %s", cudaGetErrorString(le));
   return check_launch("attn_win256_tc_kernel");
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include "../../include/bde2vid.h"
 
 namespace bde {
@@ -93,6 +94,44 @@ __device__ __forceinline__ void lstm_update(float gi, float gf, float go, float 
 bool first_use_on_device(const void* key);
 // multiProcessorCount of the current device (cached per ordinal)
 int device_sm_count();
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------------
+// The sequential attention chain is 10 small launches per frame (attention + MLP per block), each one wave or less: with
+// the attribute below the NEXT kernel's CTAs may start while the current one drains and run their prologue (barrier init,
+// TMEM allocation, index tables, weight prefetch -- everything that does not depend on the previous kernel's output), then
+// block in pdl_wait() until the previous grid has completed and its writes are visible.  Rules kept in every such kernel:
+// nothing produced by an earlier kernel is read, and nothing global is written, by a thread that has not passed pdl_wait().
+// pdl_wait() returns at once when the kernel was launched without the attribute.  BDE2VID_PDL=0 disables the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();   // api.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, int cluster, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 // implemented per translation unit
 int gemm_simt(const bde_gemm_desc* d, cudaStream_t s);

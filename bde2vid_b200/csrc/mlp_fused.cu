@@ -123,6 +123,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
     }
   };
 
+  pdl_trigger();   // the next kernel of the chain may start its prologue
   for (int i = threadIdx.x; i < kMlpH + kMlpC; i += kMlpThreads) b1_s[i] = i < kMlpH ? __ldg(p.b1 + i) : __ldg(p.b2 + i - kMlpH);
   if (threadIdx.x == 0) {
     mbar_init(bar_a, kNumProducerThreads);
@@ -146,6 +147,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
   if (warp < kNumProducerWarps) {
     // ---------------- LayerNorm producer: lane j = lane & 7 owns 8 channels of rows warp*16 + 4i + (lane >> 3) -------
     const int j = lane & 7, rsub = lane >> 3;
+    pdl_wait();   // x was written by the previous kernel of the chain (the TMA / MMA warp only touches the static weights)
     {
       float v[kRowsPerThread][1][8];
 #pragma unroll
@@ -377,6 +379,7 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
     }
   };
 
+  pdl_trigger();   // the next kernel of the chain may start its prologue
   if (threadIdx.x == 0) {
     mbar_init(bar_xn, kNumProducerThreads);
     for (int s = 0; s < kM3Stages; ++s) {
@@ -404,6 +407,7 @@ mlp_fused256_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_co
 
   mark(0);
   if (warp < kNumProducerWarps) {
+    pdl_wait();   // x was written by the previous kernel of the chain (the TMA / MMA warps only touch the static weights)
     // ---------------- LayerNorm producer (affine folded into W1 / b1 by the caller) ------------------------------------
     // All 32 loads of the thread (4 row passes x 1 KB rows) are issued before the first reduction, then ln_rows() advances
     // the four rows together.
@@ -709,20 +713,7 @@ extern "C" int bde_mlp_fused_sum(float* x, size_t rows, int c, int hidden, const
     cudaError_t e = cudaSuccess;
     if (first_use_on_device((const void*)kern)) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kM3Smem);
     BDE_REQUIRE(e == cudaSuccess, "bde_mlp_fused: smem attribute: %s", cudaGetErrorString(e));
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cl;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.gridDim = dim3((unsigned)(tiles * cl));
-    cfg.blockDim = dim3(kM3Threads);
-    cfg.dynamicSmemBytes = kM3Smem;
-    cfg.stream = (cudaStream_t)stream;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, t1, t2, p3);
+    e = launch_pdl(kern, (unsigned)(tiles * cl), (unsigned)kM3Threads, (size_t)kM3Smem, (cudaStream_t)stream, cl, t1, t2, p3);
     BDE_REQUIRE(e == cudaSuccess, "bde_mlp_fused: launch (cluster %d): %s", cl, cudaGetErrorString(e));
     return check_launch("mlp_fused256_kernel");
   }
@@ -738,6 +729,7 @@ extern "C" int bde_mlp_fused_sum(float* x, size_t rows, int c, int hidden, const
   p.x = x; p.b1 = b1; p.b2 = b2; p.P = (int)rows;
   p.sum_io = sum_io; p.sum_t = (__nv_bfloat16*)sum_t;
   p.dbg = (g_dbg != nullptr && ceil_div(rows, BM) <= g_dbg_ctas) ? g_dbg : nullptr;
-  mlp_fused_kernel<<<(unsigned)ceil_div(rows, BM), kMlpThreads, kMlpSmem, (cudaStream_t)stream>>>(t1, t2, p);
+  const cudaError_t le = launch_pdl(mlp_fused_kernel, (unsigned)ceil_div(rows, BM), (unsigned)kMlpThreads, (size_t)kMlpSmem, (cudaStream_t)stream, 1, t1, t2, p);
+  BDE_REQUIRE(le == cudaSuccess, "bde_mlp_fused: launch: %s", cudaGetErrorString(le));
   return check_launch("mlp_fused_kernel");
 }
