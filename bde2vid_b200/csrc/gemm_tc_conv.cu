@@ -223,6 +223,7 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
   const bool dbg = p.dbg != nullptr;
   const long long dbg_t0 = dbg ? clock64() : 0;
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA; ++s) {
       mbar_init(bar_afull + 8 * s, 1);
@@ -250,6 +251,9 @@ conv_tma_kernel(const __grid_constant__ CUtensorMap tmap_a0, const __grid_consta
   if (kPair) cluster_sync_all();  // both CTAs' barriers exist before the peer signals them
   tcgen05_fence_after();
   const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  // programmatic dependent launch (common.cuh): the set-up above overlapped the previous kernel's tail; every thread
+  // waits here, before the first activation load / residual read / output store
+  pdl_wait();
 
   const int ks = p.ksize;
   if (warp == 0) {
@@ -632,16 +636,25 @@ static int launch_conv(const CUtensorMap& ta0, const CUtensorMap& ta1, const CUt
   auto kern = conv_tma_kernel<BN, kHalo, EPI, kPair, NSUB>;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  unsigned n_attr = 0;
+  if (kPair) {
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = CS;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+  }
+  if (pdl_enabled()) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
   cfg.blockDim = dim3(kCvThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = s;
   cfg.attrs = attr;
-  cfg.numAttrs = kPair ? 1 : 0;
+  cfg.numAttrs = n_attr;
   if (first_use_on_device((const void*)kern)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     BDE_REQUIRE(e == cudaSuccess, "bde_gemm(tcgen05 conv): smem attribute: %s", cudaGetErrorString(e));

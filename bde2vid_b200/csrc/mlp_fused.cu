@@ -110,9 +110,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
   float* b2_s = b1_s + kMlpH;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
-  // bring-up timestamps: the whole of warp 0 takes them (a warp-uniform branch) and re-converges at once -- a single diverged
-  // lane made every later __shfl_sync of its warp take the divergent slow path and inflated the LayerNorm phase by 6 K cycles
+  const int n_tiles = (p.P + BM - 1) / BM;
+  // bring-up timestamps (first tile of the CTA): the whole of warp 0 takes them (a warp-uniform branch) and re-converges at
+  // once -- a single diverged lane made every later __shfl_sync of its warp take the divergent slow path and inflated the
+  // LayerNorm phase by 6 K cycles
   const bool dbg = p.dbg != nullptr && threadIdx.x < 32;
   const long long t_begin = dbg ? clock64() : 0;
   auto mark = [&](int slot) {
@@ -142,159 +143,172 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmap_w1, const __grid_const
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t*>(sgen + kMlpOffBar + 48);
-
   mark(0);
-  if (warp < kNumProducerWarps) {
-    // ---------------- LayerNorm producer: lane j = lane & 7 owns 8 channels of rows warp*16 + 4i + (lane >> 3) -------
-    const int j = lane & 7, rsub = lane >> 3;
-    pdl_wait();   // x was written by the previous kernel of the chain (the TMA / MMA warp only touches the static weights)
-    {
-      float v[kRowsPerThread][1][8];
+
+  // PERSISTENT: the CTA walks the row tiles blockIdx.x, + gridDim.x, ... (two CTAs per SM interleave their phases).  Set-up,
+  // TMEM allocation and the W2 load happen once; W1 shares its shared-memory bytes with the hidden tile, so it is re-loaded
+  // per tile, under the next tile's LayerNorm.  Every barrier completes one phase per tile: parity = tile counter & 1.
+  if (warp < kNumProducerWarps) pdl_wait();   // x was written by the previous kernel of the chain (warp 8 only touches the static weights)
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    const int m0 = tile * BM;
+    const uint32_t ph = it & 1u;
+    const bool first = it == 0;
+    if (warp < kNumProducerWarps) {
+      // ---------------- LayerNorm producer: lane j = lane & 7 owns 8 channels of rows warp*16 + 4i + (lane >> 3) -------
+      const int j = lane & 7, rsub = lane >> 3;
+      {
+        float v[kRowsPerThread][1][8];
 #pragma unroll
-      for (int i = 0; i < kRowsPerThread; ++i) {   // every load of the thread is in flight before the first reduction
-        const int mm = m0 + warp * (4 * kRowsPerThread) + i * 4 + rsub;
-        if (mm < p.P) {
-          const float4 t0 = *reinterpret_cast<const float4*>(p.x + (size_t)mm * kMlpC + j * 8);
-          const float4 t1 = *reinterpret_cast<const float4*>(p.x + (size_t)mm * kMlpC + j * 8 + 4);
-          v[i][0][0] = t0.x; v[i][0][1] = t0.y; v[i][0][2] = t0.z; v[i][0][3] = t0.w;
-          v[i][0][4] = t1.x; v[i][0][5] = t1.y; v[i][0][6] = t1.z; v[i][0][7] = t1.w;
-        } else {
+        for (int i = 0; i < kRowsPerThread; ++i) {   // every load of the thread is in flight before the first reduction
+          const int mm = m0 + warp * (4 * kRowsPerThread) + i * 4 + rsub;
+          if (mm < p.P) {
+            const float4 t0 = *reinterpret_cast<const float4*>(p.x + (size_t)mm * kMlpC + j * 8);
+            const float4 t1 = *reinterpret_cast<const float4*>(p.x + (size_t)mm * kMlpC + j * 8 + 4);
+            v[i][0][0] = t0.x; v[i][0][1] = t0.y; v[i][0][2] = t0.z; v[i][0][3] = t0.w;
+            v[i][0][4] = t1.x; v[i][0][5] = t1.y; v[i][0][6] = t1.z; v[i][0][7] = t1.w;
+          } else {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[i][0][e] = 0.f;
+            for (int e = 0; e < 8; ++e) v[i][0][e] = 0.f;
+          }
+        }
+        float rstd[kRowsPerThread];
+        ln_rows<kRowsPerThread, 1>(v, rstd);
+#pragma unroll
+        for (int i = 0; i < kRowsPerThread; ++i) {
+          const int row = warp * (4 * kRowsPerThread) + i * 4 + rsub;
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = v[i][0][e] * rstd[i];
+          const uint4 pk = pack8_bf16(o);
+          const uint32_t dst = s_a + (uint32_t)row * 128u + (((uint32_t)j ^ (uint32_t)(row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
         }
       }
-      float rstd[kRowsPerThread];
-      ln_rows<kRowsPerThread, 1>(v, rstd);
-#pragma unroll
-      for (int i = 0; i < kRowsPerThread; ++i) {
-        const int row = warp * (4 * kRowsPerThread) + i * 4 + rsub;
-        float o[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = v[i][0][e] * rstd[i];
-        const uint4 pk = pack8_bf16(o);
-        const uint32_t dst = s_a + (uint32_t)row * 128u + (((uint32_t)j ^ (uint32_t)(row & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
-      }
-    }
-    fence_proxy_async_smem();
-    mbar_arrive(bar_a);
-    mark(1);
+      fence_proxy_async_smem();
+      mbar_arrive(bar_a);
+      if (first) mark(1);
 
-    // ---------------- epilogue 1: hidden = GELU(acc1 + b1) -> bf16, swizzled K-major tile for GEMM 2 -----------------
-    const int q = warp & 3, half = warp >> 2;
-    const int row = q * 32 + lane;  // TMEM lane == tile row
-    const uint32_t lane_taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
-    mbar_wait(bar_acc1, 0);
-    mark(2);
-    tcgen05_fence_after();
+      // ---------------- epilogue 1: hidden = GELU(acc1 + b1) -> bf16, swizzled K-major tile for GEMM 2 -----------------
+      const int q = warp & 3, half = warp >> 2;
+      const int row = q * 32 + lane;  // TMEM lane == tile row
+      const uint32_t lane_taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+      mbar_wait(bar_acc1, ph);
+      if (first) mark(2);
+      tcgen05_fence_after();
 #pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
-      const int c0 = half * 128 + ch * 32;
-      uint32_t raw[32];
-      tmem_ld_32x32b_x32(lane_taddr + (uint32_t)c0, raw);
-      tmem_ld_wait();
-      const uint32_t kb_base = s_h + (uint32_t)(c0 >> 6) * (BM * 128) + (uint32_t)row * 128u;
-      const int j0 = (c0 & 63) >> 3;
+      for (int ch = 0; ch < 4; ++ch) {
+        const int c0 = half * 128 + ch * 32;
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(lane_taddr + (uint32_t)c0, raw);
+        tmem_ld_wait();
+        const uint32_t kb_base = s_h + (uint32_t)(c0 >> 6) * (BM * 128) + (uint32_t)row * 128u;
+        const int j0 = (c0 & 63) >> 3;
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        float o[8];
+        for (int jj = 0; jj < 4; ++jj) {
+          float o[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = fast_gelu(__uint_as_float(raw[jj * 8 + e]) + b1_s[c0 + jj * 8 + e]);
-        const uint4 pk = pack8_bf16(o);
-        const uint32_t dst = kb_base + ((((uint32_t)(j0 + jj)) ^ (uint32_t)(row & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
-      }
-    }
-    tcgen05_fence_before();   // our TMEM reads are done before GEMM 2 overwrites the columns
-    fence_proxy_async_smem();
-    mbar_arrive(bar_h);
-    mark(3);
-
-    // ---------------- epilogue 2: x += acc2 + b2, coalesced through a per-warp smem transpose ---------------------------
-    // The residual rows are fetched BEFORE waiting for GEMM 2 (they do not depend on it): inside the store loop every
-    // load waited behind the previous store to the same array, eight global round trips in a row.
-    const int rq = lane >> 3, cq = (lane & 7) * 4;
-    float4 cur8[8];
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int mm = m0 + q * 32 + it * 4 + rq;
-      cur8[it] = mm < p.P ? __ldcg(reinterpret_cast<const float4*>(p.x + (size_t)mm * kMlpC + half * 32 + cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    mbar_wait(bar_acc2, 0);
-    mark(4);
-    tcgen05_fence_after();
-    constexpr int kPitch = 36;
-    float* stg = reinterpret_cast<float*>(sgen) + warp * (32 * kPitch);  // the H region is free once GEMM 2 has completed
-    {
-      uint32_t raw[32];
-      tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(half * 32), raw);
-      tmem_ld_wait();
-#pragma unroll
-      for (int jq = 0; jq < 32; jq += 4)
-        *reinterpret_cast<float4*>(stg + lane * kPitch + jq) =
-            make_float4(__uint_as_float(raw[jq]), __uint_as_float(raw[jq + 1]), __uint_as_float(raw[jq + 2]), __uint_as_float(raw[jq + 3]));
-      __syncwarp();
-      const float4 bb = *reinterpret_cast<const float4*>(b2_s + half * 32 + cq);
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int mm = m0 + q * 32 + it * 4 + rq;
-        if (mm < p.P) {
-          const float4 acc = *reinterpret_cast<const float4*>(stg + (it * 4 + rq) * kPitch + cq);
-          float4* dst = reinterpret_cast<float4*>(p.x + (size_t)mm * kMlpC + half * 32 + cq);
-          float4 cur = cur8[it];
-          cur.x += acc.x + bb.x; cur.y += acc.y + bb.y; cur.z += acc.z + bb.z; cur.w += acc.w + bb.w;
-          *dst = cur;
-          if (p.sum_io != nullptr) mlp_fused_sum(p.sum_io, p.sum_t, (size_t)mm * kMlpC + half * 32 + cq, cur);
+          for (int e = 0; e < 8; ++e) o[e] = fast_gelu(__uint_as_float(raw[jj * 8 + e]) + b1_s[c0 + jj * 8 + e]);
+          const uint4 pk = pack8_bf16(o);
+          const uint32_t dst = kb_base + ((((uint32_t)(j0 + jj)) ^ (uint32_t)(row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
         }
       }
-    }
-    tcgen05_fence_before();
-    mark(5);
-  } else {
-    // ---------------- TMA + MMA warp: all lanes wait, one elected lane issues (elect_one_sync, tc_common.cuh) --------------
-    if (elect_one_sync()) {
-      mbar_arrive_expect_tx(bar_w1, kMlpH * 128);
-      tma_load_2d(s_w1, &tmap_w1, bar_w1, 0, 0);
-      mbar_arrive_expect_tx(bar_w2, kMlpC * kMlpH * 2);
+      tcgen05_fence_before();   // our TMEM reads are done before GEMM 2 overwrites the columns
+      fence_proxy_async_smem();
+      mbar_arrive(bar_h);
+      if (first) mark(3);
+
+      // ---------------- epilogue 2: x += acc2 + b2, coalesced through a per-warp smem transpose ---------------------------
+      // The residual rows are fetched BEFORE waiting for GEMM 2 (they do not depend on it): inside the store loop every
+      // load waited behind the previous store to the same array, eight global round trips in a row.
+      const int rq = lane >> 3, cq = (lane & 7) * 4;
+      float4 cur8[8];
 #pragma unroll
-      for (int kb = 0; kb < kMlpH / BK; ++kb) tma_load_2d(s_w2 + kb * (kMlpC * 128), &tmap_w2, bar_w2, kb * BK, 0);
-    }
-    __syncwarp();
-    // GEMM 1: [128 x 64] x [64 x 256]
-    mbar_wait(bar_a, 0);
-    mbar_wait(bar_w1, 0);
-    tcgen05_fence_after();
-    if (elect_one_sync()) {
-      constexpr uint32_t idesc = make_idesc(kMlpH);
-      const uint64_t adesc = make_smem_desc(s_a), bdesc = make_smem_desc(s_w1);
-#pragma unroll
-      for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
-      umma_commit(bar_acc1);
-    }
-    __syncwarp();
-    // GEMM 2: [128 x 256] x [256 x 64], A = the hidden tile written by epilogue 1
-    mbar_wait(bar_h, 0);
-    mbar_wait(bar_w2, 0);
-    tcgen05_fence_after();
-    if (elect_one_sync()) {
-      constexpr uint32_t idesc = make_idesc(kMlpC);
-#pragma unroll
-      for (int kb = 0; kb < kMlpH / BK; ++kb) {
-        const uint64_t adesc = make_smem_desc(s_h + kb * (BM * 128)), bdesc = make_smem_desc(s_w2 + kb * (kMlpC * 128));
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k)
-          umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+      for (int e = 0; e < 8; ++e) {
+        const int mm = m0 + q * 32 + e * 4 + rq;
+        cur8[e] = mm < p.P ? __ldcg(reinterpret_cast<const float4*>(p.x + (size_t)mm * kMlpC + half * 32 + cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      umma_commit(bar_acc2);
+      mbar_wait(bar_acc2, ph);
+      if (first) mark(4);
+      tcgen05_fence_after();
+      constexpr int kPitch = 36;
+      float* stg = reinterpret_cast<float*>(sgen) + warp * (32 * kPitch);  // the H region is free once GEMM 2 has completed
+      {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(lane_taddr + (uint32_t)(half * 32), raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jq = 0; jq < 32; jq += 4)
+          *reinterpret_cast<float4*>(stg + lane * kPitch + jq) =
+              make_float4(__uint_as_float(raw[jq]), __uint_as_float(raw[jq + 1]), __uint_as_float(raw[jq + 2]), __uint_as_float(raw[jq + 3]));
+        __syncwarp();
+        const float4 bb = *reinterpret_cast<const float4*>(b2_s + half * 32 + cq);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int mm = m0 + q * 32 + e * 4 + rq;
+          if (mm < p.P) {
+            const float4 acc = *reinterpret_cast<const float4*>(stg + (e * 4 + rq) * kPitch + cq);
+            float4* dst = reinterpret_cast<float4*>(p.x + (size_t)mm * kMlpC + half * 32 + cq);
+            float4 cur = cur8[e];
+            cur.x += acc.x + bb.x; cur.y += acc.y + bb.y; cur.z += acc.z + bb.z; cur.w += acc.w + bb.w;
+            *dst = cur;
+            if (p.sum_io != nullptr) mlp_fused_sum(p.sum_io, p.sum_t, (size_t)mm * kMlpC + half * 32 + cq, cur);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();   // the transpose tiles were read through the generic proxy; the next W1 load writes them through the async proxy
+      if (first) mark(5);
+    } else {
+      // ---------------- TMA + MMA warp: all lanes wait, one elected lane issues (elect_one_sync, tc_common.cuh) --------------
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(bar_w1, kMlpH * 128);
+        tma_load_2d(s_w1, &tmap_w1, bar_w1, 0, 0);
+        if (first) {
+          mbar_arrive_expect_tx(bar_w2, kMlpC * kMlpH * 2);
+#pragma unroll
+          for (int kb = 0; kb < kMlpH / BK; ++kb) tma_load_2d(s_w2 + kb * (kMlpC * 128), &tmap_w2, bar_w2, kb * BK, 0);
+        }
+      }
+      __syncwarp();
+      // GEMM 1: [128 x 64] x [64 x 256]
+      mbar_wait(bar_a, ph);
+      mbar_wait(bar_w1, ph);
+      tcgen05_fence_after();
+      if (elect_one_sync()) {
+        constexpr uint32_t idesc = make_idesc(kMlpH);
+        const uint64_t adesc = make_smem_desc(s_a), bdesc = make_smem_desc(s_w1);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+        umma_commit(bar_acc1);
+      }
+      __syncwarp();
+      // GEMM 2: [128 x 256] x [256 x 64], A = the hidden tile written by epilogue 1
+      mbar_wait(bar_h, ph);
+      mbar_wait(bar_w2, 0);     // completes once; later waits on the same parity return at once
+      tcgen05_fence_after();
+      if (elect_one_sync()) {
+        constexpr uint32_t idesc = make_idesc(kMlpC);
+#pragma unroll
+        for (int kb = 0; kb < kMlpH / BK; ++kb) {
+          const uint64_t adesc = make_smem_desc(s_h + kb * (BM * 128)), bdesc = make_smem_desc(s_w2 + kb * (kMlpC * 128));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_acc2);
+      }
+      __syncwarp();
     }
-    __syncwarp();
+    // end of tile: the transpose tiles of epilogue 2 (they overlay the A / W1 bytes) and the TMEM columns are free again
+    // for the next tile's LayerNorm stores, W1 load and GEMM 1
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
   }
 
-  __syncthreads();
-  if (warp == kNumProducerWarps) {
-    tcgen05_fence_after();
-    tmem_dealloc(tmem_acc, 256);
-  }
+  if (warp == kNumProducerWarps) tmem_dealloc(tmem_acc, 256);
 }
 
 
@@ -728,8 +742,10 @@ extern "C" int bde_mlp_fused_sum(float* x, size_t rows, int c, int hidden, const
   MlpParams p;
   p.x = x; p.b1 = b1; p.b2 = b2; p.P = (int)rows;
   p.sum_io = sum_io; p.sum_t = (__nv_bfloat16*)sum_t;
-  p.dbg = (g_dbg != nullptr && ceil_div(rows, BM) <= g_dbg_ctas) ? g_dbg : nullptr;
-  const cudaError_t le = launch_pdl(mlp_fused_kernel, (unsigned)ceil_div(rows, BM), (unsigned)kMlpThreads, (size_t)kMlpSmem, (cudaStream_t)stream, 1, t1, t2, p);
+  p.dbg = (g_dbg != nullptr && ceil_div(rows, BM) <= g_dbg_ctas) ? g_dbg : nullptr;   // (at most that many CTAs)
+  // persistent: at most two CTAs per SM (the resident limit of this kernel), each walking its share of the row tiles
+  const unsigned n_tiles = (unsigned)ceil_div(rows, BM), max_ctas = 2u * (unsigned)device_sm_count();
+  const cudaError_t le = launch_pdl(mlp_fused_kernel, n_tiles < max_ctas ? n_tiles : max_ctas, (unsigned)kMlpThreads, (size_t)kMlpSmem, (cudaStream_t)stream, 1, t1, t2, p);
   BDE_REQUIRE(le == cudaSuccess, "bde_mlp_fused: launch: %s", cudaGetErrorString(le));
   return check_launch("mlp_fused_kernel");
 }
