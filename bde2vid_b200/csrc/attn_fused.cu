@@ -79,6 +79,12 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
+template <int OFF>
+__device__ __forceinline__ float lds_f32_off(uint32_t addr) {   // [register + immediate]: no address add
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
 __device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
   uint2 v;
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
@@ -403,33 +409,35 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
     // kernel was issue-latency bound (warps active 24 %, no pipe above 60 %).  Interleaving two independent units doubles
     // the instruction-level parallelism per warp; the online softmax over three key segments (6 / 6 / 7 tiles for D = 3)
     // keeps 2 x 7 score tiles alive instead of 2 x 19, so both fit the 128-register budget of two CTAs per SM.
-    constexpr int NPAIR_UNITS = HG * MTN;                         // 48 normal units: (head, 16-row query tile)
+    // The two units of a warp are the SAME query tile of heads h and h + 8: bias row / column offsets, the ones-lane pattern
+    // and every shared-memory base address are then shared, and the second head's operands sit at compile-time byte
+    // offsets (bias table +8 rows of D * 169 floats, q / k / v columns +32 channels) -> half the address arithmetic.
+    constexpr int NPAIRS = HG * MTN / 2;                          // 24 pairs: (head pair, 16-row query tile)
+    constexpr int TLD = Cfg::DMAX * kRel;                         // == tbl_ld: launch_fused picks NT from D
+    constexpr int kTblOff = 8 * TLD * 4;                          // bias table: head h -> h + 8
+    constexpr int kChOff = 8 * HD * 2;                            // q / k / v tiles: head h -> h + 8 (bf16 / fp16 columns)
     constexpr int SEG = ((NT + 2) / 3) & ~1;                      // even segment size: 19 -> 6, 13 -> 4, 7 -> 2
     constexpr int LAST = NT - 2 * SEG;                            // 7 / 5 / 3
     constexpr int kMaxT = LAST > SEG ? LAST : SEG;
-    for (int u0 = warp; u0 < NPAIR_UNITS; u0 += 2 * (kThreadsF / 32)) {
-      int hl[2], row0[2], row1[2];
-      uint32_t r0a[2], r1a[2], qa0[2], qa1[2], vaddr[2];
-      bool ones_lane[2], live[2];
+    for (int pi = warp; pi < NPAIRS; pi += kThreadsF / 32) {
+      const int hp = pi / MTN, mt = pi - hp * MTN;                // heads hp and hp + 8
+      const int row0 = mt * 16 + g, row1 = row0 + 8;
+      const uint32_t r0a = tbl_u32 + (uint32_t)(hp * TLD * 4 + roff[row0]);
+      const uint32_t r1a = tbl_u32 + (uint32_t)(hp * TLD * 4 + roff[row1]);
+      uint32_t qa0[2] = {0u, 0u}, qa1[2] = {0u, 0u};
+      if (2 * t < HD) {
+        const __nv_bfloat16* q0 = qs + row0 * PQ + hp * HD + 2 * t;
+        const __nv_bfloat16* q1 = qs + row1 * PQ + hp * HD + 2 * t;
+        qa0[0] = *reinterpret_cast<const uint32_t*>(q0); qa0[1] = *reinterpret_cast<const uint32_t*>(q0 + 8 * HD);
+        qa1[0] = *reinterpret_cast<const uint32_t*>(q1); qa1[1] = *reinterpret_cast<const uint32_t*>(q1 + 8 * HD);
+      }
+      // one 8-channel V tile holds a head pair (2 hp', 2 hp' + 1); the other head's columns are replaced by ones -> row sums
+      const bool ones_lane = (g >> 2) != (hp & 1);
+      const uint32_t vaddr = vs_u32 + (uint32_t)(((lane & 15) * PQ + (hp >> 1) * 8) * 2);
+      const __nv_bfloat16* kp = ks + g * PQ + hp * HD + 2 * t;
       float oa[2][4], ob[2][4], m0s[2], m1s[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int unit = u0 + u * (kThreadsF / 32);
-        live[u] = unit < NPAIR_UNITS;                             // (48 units over 8 warps: always true; kept for other shapes)
-        const int un = live[u] ? unit : u0;
-        hl[u] = un / MTN;
-        const int mt = un - hl[u] * MTN;
-        row0[u] = mt * 16 + g; row1[u] = row0[u] + 8;
-        r0a[u] = tbl_u32 + (uint32_t)(hl[u] * tbl_ld * 4 + roff[row0[u]]);
-        r1a[u] = tbl_u32 + (uint32_t)(hl[u] * tbl_ld * 4 + roff[row1[u]]);
-        qa0[u] = qa1[u] = 0u;
-        if (2 * t < HD) {
-          qa0[u] = *reinterpret_cast<const uint32_t*>(qs + row0[u] * PQ + hl[u] * HD + 2 * t);
-          qa1[u] = *reinterpret_cast<const uint32_t*>(qs + row1[u] * PQ + hl[u] * HD + 2 * t);
-        }
-        // one 8-channel V tile holds a head pair; the other head's columns are replaced by ones -> row sums
-        ones_lane[u] = (g >> 2) != (hl[u] & 1);
-        vaddr[u] = vs_u32 + (uint32_t)(((lane & 15) * PQ + (hl[u] >> 1) * 8) * 2);
         oa[u][0] = oa[u][1] = oa[u][2] = oa[u][3] = 0.f;
         ob[u][0] = ob[u][1] = ob[u][2] = ob[u][3] = 0.f;
         m0s[u] = m1s[u] = -INFINITY;                              // running row maxima times log2(e)
@@ -443,18 +451,24 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
           if (jj < nj) {
             const int j = j0 + jj;
             const uint2 cp = lds_u64(coff_u32 + (uint32_t)((j * 8 + 2 * t) * 4));
+            const uint32_t a00 = r0a + cp.x, a01 = r0a + cp.y, a10 = r1a + cp.x, a11 = r1a + cp.y;
+            s[0][jj][0] = lds_f32_off<0>(a00); s[0][jj][1] = lds_f32_off<0>(a01);
+            s[0][jj][2] = lds_f32_off<0>(a10); s[0][jj][3] = lds_f32_off<0>(a11);
+            s[1][jj][0] = lds_f32_off<kTblOff>(a00); s[1][jj][1] = lds_f32_off<kTblOff>(a01);
+            s[1][jj][2] = lds_f32_off<kTblOff>(a10); s[1][jj][3] = lds_f32_off<kTblOff>(a11);
+            uint32_t kb[2] = {0u, 0u};
+            if (2 * t < HD) {
+              kb[0] = *reinterpret_cast<const uint32_t*>(kp + j * 8 * PQ);
+              kb[1] = *reinterpret_cast<const uint32_t*>(kp + j * 8 * PQ + 8 * HD);
+            }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              s[u][jj][0] = lds_f32(r0a[u] + cp.x); s[u][jj][1] = lds_f32(r0a[u] + cp.y);
-              s[u][jj][2] = lds_f32(r1a[u] + cp.x); s[u][jj][3] = lds_f32(r1a[u] + cp.y);
               if (j == NT - 1) {  // only the last key tile can hold padding keys
                 if (j * 8 + 2 * t >= n_kv) s[u][jj][0] = s[u][jj][2] = -1e30f;
                 if (j * 8 + 2 * t + 1 >= n_kv) s[u][jj][1] = s[u][jj][3] = -1e30f;
               }
-              uint32_t kb0 = 0u;
-              if (2 * t < HD) kb0 = *reinterpret_cast<const uint32_t*>(ks + (j * 8 + g) * PQ + hl[u] * HD + 2 * t);
               const uint32_t qa[4] = {qa0[u], qa1[u], 0u, 0u};
-              mma16816(s[u][jj], qa, kb0, 0u);
+              mma16816(s[u][jj], qa, kb[u], 0u);
             }
           }
         }
@@ -499,8 +513,8 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
                 pa[2] = pa[3] = 0u;
               }
               uint32_t vb0, vb1;
-              ldsm_x2_trans(vb0, vb1, vaddr[u] + (uint32_t)(kk * 16 * PQ * 2));
-              if (ones_lane[u]) { vb0 = kOnes; vb1 = kOnes; }
+              ldsm_x2_trans(vb0, vb1, vaddr + (uint32_t)(kk * 16 * PQ * 2 + u * kChOff));
+              if (ones_lane) { vb0 = kOnes; vb1 = kOnes; }
               if (k2 & 1) mma16816_f16(ob[u], pa, vb0, vb1); else mma16816_f16(oa[u], pa, vb0, vb1);
             }
           }
@@ -511,11 +525,11 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
 #pragma unroll
         for (int e = 0; e < 4; ++e) oa[u][e] += ob[u][e];
         const float l0 = __shfl_xor_sync(0xffffffffu, oa[u][0], 2), l1 = __shfl_xor_sync(0xffffffffu, oa[u][2], 2);
-        if (live[u] && (t >> 1) == (hl[u] & 1)) {
+        if ((t >> 1) == (hp & 1)) {
           const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-          const int col = (hl[u] >> 1) * 8 + 2 * t;
-          *reinterpret_cast<uint32_t*>(os + row0[u] * PQ + col) = pack2(oa[u][0] * inv0, oa[u][1] * inv0);
-          *reinterpret_cast<uint32_t*>(os + row1[u] * PQ + col) = pack2(oa[u][2] * inv1, oa[u][3] * inv1);
+          const int col = ((hp + 8 * u) >> 1) * 8 + 2 * t;
+          *reinterpret_cast<uint32_t*>(os + row0 * PQ + col) = pack2(oa[u][0] * inv0, oa[u][1] * inv0);
+          *reinterpret_cast<uint32_t*>(os + row1 * PQ + col) = pack2(oa[u][2] * inv1, oa[u][3] * inv1);
         }
       }
     }
