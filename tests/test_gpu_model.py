@@ -162,6 +162,25 @@ def test_fused_attention_matches_unfused():
         assert err <= 1e-3
 
 
+def test_programmatic_dependent_launch_is_bitwise_neutral(monkeypatch):
+    """The chain kernels (attention, fused MLP, TMA conv) are launched with the programmatic-stream-serialization attribute
+    so that their prologues overlap the previous kernel's tail (common.cuh: launch_pdl / pdl_wait).  The overlap must not
+    change a single bit: BDE2VID_PDL=0 (plain stream order) against the default, eager and through the CUDA graph, several
+    replays each (a race would show up as run-to-run differences)."""
+    H, W, T, N = 64, 96, 6, 2500
+    vox, _ = voxel_inputs(5, T, H, W, N)
+    outs = {}
+    for pdl in ("0", "1"):
+        monkeypatch.setenv("BDE2VID_PDL", pdl)
+        model, cfg, sd = build_model(dict(depths=[2, 0, 2]), 3, "bf16")
+        with torch.no_grad():
+            runs = [torch.cat(model([{"events": v.to(DEV)} for v in vox]), 0).clone() for _ in range(4)]
+        for r in runs[1:]:
+            assert torch.equal(r, runs[0]), "PDL=%s: replays differ" % pdl
+        outs[pdl] = runs[0]
+    assert torch.equal(outs["0"], outs["1"])
+
+
 def test_long_recurrence_bf16_vs_oracle():
     """The north-star frame gate after a long recurrent chain: T = 40 windows, bf16 tcgen05 engine (approximate
     gate activations, bf16 h state) against the fp32 oracle; max-abs <= 2e-3, MSE / SSIM deltas <= 1e-3."""

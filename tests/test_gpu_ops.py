@@ -181,7 +181,9 @@ def test_ln_gather_qkv(dtype, C):
                 assert (oq.float().cpu() - F.layer_norm(tok, (C,), gq, bq, 1e-5)).abs().max() <= tol
 
 
-@pytest.mark.parametrize("rows", [128, 1000, 23232])
+# 1 / 129: ragged tiles; 23232 / 92928: one / four 132 x 176 maps; 37965 = 296 full tiles + a ragged one: every persistent CTA of the
+# C = 64 kernel (2 per SM) walks more than one tile
+@pytest.mark.parametrize("rows", [1, 128, 129, 1000, 23232, 37965, 92928])
 @pytest.mark.parametrize("C", [64, 256])
 def test_mlp_fused(rows, C):
     """x += fc2(GELU(fc1(LN(x)))) in one tcgen05 kernel vs fp32 torch on bf16-rounded weights (DTransformer.py:279-304);
@@ -217,8 +219,8 @@ def test_mlp_fused(rows, C):
     assert float((sm.cpu() - (xd.cpu() + merged)).abs().max()) <= 1e-5
     assert torch.equal(st, sm.to(torch.bfloat16))
     if C == 256:
-        # hidden dimension split over a thread-block cluster (BDE2VID_MLP256_CLUSTER = 1 / 2 / 4): partial fc2 accumulators
-        # are exchanged through distributed shared memory and summed in a fixed order -> deterministic; the split only
+        # hidden dimension split over a thread-block cluster (BDE2VID_MLP256_CLUSTER = 1 / 2 / 4): the partial fc2 accumulators
+        # are summed into x in CL phases separated by cluster barriers, in a fixed order -> deterministic; the split only
         # changes the fp32 summation order of the K = 1024 product
         import os
         outs = {}
