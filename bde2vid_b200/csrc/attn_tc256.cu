@@ -173,14 +173,41 @@ __host__ __device__ constexpr StageInfo stage_info(int it) {
   return {2, 3, it - 30, 0, it == 31};
 }
 
+// CL = 2 (a 2-CTA cluster per window, used when 2 * n_win CTAs fit one wave): CTA `rank` owns head groups 2 rank, 2 rank + 1
+// (16 stages, idx = LOCAL head group / Q tile 0):   0-3 Q | 4-7 K|V l 0 | 8-11 K|V l 1 | 12-13 proj(l 0) | 14-15 proj(l 1)
+__host__ __device__ constexpr StageInfo stage_info2(int it) {
+  if (it < 4) return {0, 0, it, it == 0, it == 3};
+  if (it < 8) return {1, 0, it - 4, it == 4, it == 7};
+  if (it < 12) return {1, 1, it - 8, it == 8, it == 11};
+  if (it < 14) return {2, 0, it - 12, 1, 0};
+  return {2, 1, it - 14, 0, it == 15};
+}
+__device__ __forceinline__ uint32_t tc_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void tc_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 // 544 threads = 17 warps: one SM sub-partition hosts 5 of them, so its 16 K registers allow 102 -> 96 registers per thread
 // (a cap of 112 or 120 makes the launch fail with "too many resources").  The attention core therefore runs its softmax
 // over two key halves (online rescaling), which keeps at most 10 score tiles (40 registers) alive instead of 19 (76).
-template <int NT>
+//
+// CL = 2: the two CTAs of a cluster share one window and split its four head groups (each streams half of the weights and
+// runs half of the attention core; the LayerNorm is done by both).  Their partial output projections meet in x itself, like
+// the partial sums of the fused MLP: phase A, CTA r writes shortcut + its partial for the PEER's 128 channels; cluster
+// barrier; phase B, it adds its partial + bias to its own 128 channels.  Fixed order -> deterministic.  A first cluster
+// barrier after the LayerNorm keeps a fast CTA from overwriting rows its peer has not gathered yet.
+template <int NT, int CL>
 __global__ void __launch_bounds__(kThreadsT, 1)
 attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __grid_constant__ CUtensorMap tmap_wproj,
                       const TcAttnParams p) {
   using Cfg = TCfg<NT>;
+  constexpr int NSTG = CL == 2 ? 16 : 32;         // weight stages of this CTA
+  constexpr int NHGL = Cfg::NHG / CL;             // head groups of this CTA
+  const int rank = CL == 2 ? (int)tc_cluster_rank() : 0;
+  const int hg0 = rank * NHGL;                    // first (global) head group of this CTA
   constexpr int C = Cfg::C, HD = Cfg::HD, HG = Cfg::HG, PQ = Cfg::PQ;
   constexpr int KSTEPS = Cfg::KSTEPS, XROWS = Cfg::XROWS, NKEY = Cfg::NKEY;
   extern __shared__ uint8_t smem_raw[];
@@ -207,7 +234,7 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
   const uint32_t tmem_slot = bar0 + 200;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int w = blockIdx.x;
+  const int w = blockIdx.x / CL;
   const int n_kv = p.D * kTok;
   const int tbl_ld = p.D * kRel;
   const bool dbg = p.dbg != nullptr;
@@ -246,16 +273,19 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
     // coordinate / descriptor offset is an immediate: as a rolled loop the single issuing lane spent ~1.5 K cycles per
     // stage in ~300 dependent scalar instructions (batch decoding, % 3, 64-bit descriptor arithmetic) -- 4x the MMA time.
     const uint32_t ring = sb + Cfg::OFF_RING;
+    if (CL == 2) tc_cluster_arrive();   // barrier 0 (see the workers); this warp waits for it after its schedule
     auto issue_load = [&](const int it) {
-      const StageInfo si = stage_info(it);
+      const StageInfo si = CL == 2 ? stage_info2(it) : stage_info(it);
       const int s = it % kStages;
       const uint32_t dst = ring + s * kStageBytes, bar = bar_full + 8 * s;
       mbar_arrive_expect_tx(bar, kStageBytes);
-      if (si.kind == 2) {         // Wproj rows [128 kb, +128), K block = head group idx
-        tma_load_2d(dst, &tmap_wproj, bar, si.idx * BK, 128 * si.kb);
-        tma_load_2d(dst + 8192, &tmap_wproj, bar, si.idx * BK, 128 * si.kb + 64);
-      } else {                    // Q tile: Wq rows [128 idx, +128);  K|V: Wk rows of head group idx, then its Wv rows
-        const int r0 = si.kind == 1 ? C + 64 * si.idx : 128 * si.idx, r1 = si.kind == 1 ? 2 * C + 64 * si.idx : 128 * si.idx + 64;
+      // global indices: head group hg0 + idx; Q tile = rank for CL = 2 (the tile that holds this CTA's two head groups)
+      const int ghg = hg0 + si.idx, gq = CL == 2 ? rank : si.idx;
+      if (si.kind == 2) {         // Wproj rows [128 kb, +128), K block = head group
+        tma_load_2d(dst, &tmap_wproj, bar, ghg * BK, 128 * si.kb);
+        tma_load_2d(dst + 8192, &tmap_wproj, bar, ghg * BK, 128 * si.kb + 64);
+      } else {                    // Q tile: Wq rows [128 gq, +128);  K|V: Wk rows of the head group, then its Wv rows
+        const int r0 = si.kind == 1 ? C + 64 * ghg : 128 * gq, r1 = si.kind == 1 ? 2 * C + 64 * ghg : 128 * gq + 64;
         tma_load_2d(dst, &tmap_wqkv, bar, si.kb * BK, r0);
         tma_load_2d(dst + 8192, &tmap_wqkv, bar, si.kb * BK, r1);
       }
@@ -270,8 +300,8 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
     const uint64_t adesc0 = make_smem_desc(ring);
     const uint64_t bdesc_xn = make_smem_desc(sb + Cfg::OFF_XN), bdesc_o = make_smem_desc(sb + Cfg::OFF_O);
 #pragma unroll
-    for (int it = 0; it < 32; ++it) {
-      const StageInfo si = stage_info(it);
+    for (int it = 0; it < NSTG; ++it) {
+      const StageInfo si = CL == 2 ? stage_info2(it) : stage_info(it);
       const int s = it % kStages;
       if (dbg && lane == 0 && (it & 7) == 0) p.dbg[(size_t)gridDim.x * 8 + (size_t)blockIdx.x * 8 + (it >> 3)] = clock64() - t_begin;
       // operands / accumulator of this group available?
@@ -285,7 +315,7 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
         const uint64_t adesc = adesc0 + (uint64_t)((s * kStageBytes) >> 4);
         // B: the LayerNorm'ed tokens, K block kb (the query frame's tokens are rows 0 .. 48), or attention-output slab idx
         const uint64_t bdesc = si.kind == 2 ? bdesc_o + (uint64_t)((si.idx * 64 * 128) >> 4) : bdesc_xn + (uint64_t)((si.kb * Cfg::XN_SLAB) >> 4);
-        const uint32_t d_tmem = tmem_base + (si.kind == 1 ? Cfg::TM_KV : si.kind == 0 ? Cfg::TM_Q + 64 * si.idx : Cfg::TM_P + 64 * si.kb);
+        const uint32_t d_tmem = tmem_base + (si.kind == 1 ? Cfg::TM_KV : si.kind == 0 ? Cfg::TM_Q + 64 * si.idx : Cfg::TM_P + 64 * si.kb);   // idx is local
         const uint32_t idesc = si.kind == 1 ? idesc_mn(128, XROWS) : idesc_mn(128, 64);
         const bool fresh = si.kind == 2 ? si.idx == 0 : si.kb == 0;      // first K block of its accumulator
 #pragma unroll
@@ -301,7 +331,7 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
       __syncwarp();
       // refill AFTER this iteration's MMAs are queued: the wait below is for the MMAs of the PREVIOUS iteration (they
       // free stage (it - 1) % kStages), so the tensor pipe always has the next batch queued behind the running one
-      if (it + kStages - 1 < 32) {
+      if (it + kStages - 1 < NSTG) {
         const int nx = it + kStages - 1, sn = nx % kStages;
         if (nx >= kStages) mbar_wait(bar_empty + 8 * sn, ((nx / kStages) - 1) & 1u);
         if (elect_one_sync()) issue_load(nx);
@@ -309,6 +339,12 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
       }
     }
     if (dbg && lane == 0) p.dbg[(size_t)gridDim.x * 8 + (size_t)blockIdx.x * 8 + 4] = clock64() - t_begin;
+    __syncwarp();
+    if (CL == 2) {
+      tc_cluster_wait();      // barrier 0
+      tc_cluster_arrive();    // barrier 1 (between the two phases of the workers' epilogue)
+      tc_cluster_wait();
+    }
   } else {
     // =========================================== worker warps ===========================================================
     const int g = lane >> 2, t = lane & 3;
@@ -413,6 +449,11 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_xn);
     if (dbg) t_ln = clock64() - t_begin;
+    if (CL == 2) {      // barrier 0: both CTAs have gathered their tokens; from here on the peer may write rows of x
+      __syncwarp();
+      tc_cluster_arrive();
+      tc_cluster_wait();
+    }
 
     const uint32_t vs_u32 = sb + Cfg::OFF_V, tbl_u32 = sb + Cfg::OFF_TBL, coff_u32 = sb + Cfg::OFF_COFF;
     constexpr uint32_t kOnes = 0x3C003C00u;
@@ -420,7 +461,9 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
     const int qd = warp & 3, part = warp >> 2;                   // TMEM lane quarter of this warp, column-chunk phase
     const uint32_t lane_sel = (uint32_t)(qd * 32) << 16;
 
-    for (int hg = 0; hg < Cfg::NHG; ++hg) {
+    for (int l = 0; l < NHGL; ++l) {
+      const int hg = hg0 + l;             // global head group (weights, biases, bias table); l indexes barriers / TMEM / O slabs
+      const int lq = CL == 2 ? 0 : hg >> 1;
       long long t0 = dbg ? clock64() : 0;
       // bias table of this head group (cp.async, lands while the accumulators are converted)
       {
@@ -429,8 +472,8 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
         for (int i = tid; i < n16; i += kWorkers) cpa16(sb + Cfg::OFF_TBL + (uint32_t)(i * 16), src + i * 4);
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
-      if ((hg & 1) == 0) mbar_wait_polite(bar_qfull + 8 * (hg >> 1), 0, lane);
-      mbar_wait_polite(bar_kvfull + 8 * hg, 0, lane);
+      if ((hg & 1) == 0) mbar_wait_polite(bar_qfull + 8 * lq, 0, lane);
+      mbar_wait_polite(bar_kvfull + 8 * l, 0, lane);
       tcgen05_fence_after();
       if (dbg) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
       // ---- K^T | V^T (TMEM lane = channel: 0..63 k, 64..127 v; column = token) -> [token][channel] tiles -----------------
@@ -451,7 +494,7 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
         // the accumulators are in registers: hand the TMEM buffer back to the MMA warp before the stores
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_kvempty + 8 * hg);
+        if (lane == 0) mbar_arrive(bar_kvempty + 8 * l);
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
           const int c8 = part + 4 * i;
@@ -470,7 +513,7 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
         }
         // Q^T tile hg / 2, lanes (hg & 1) * 64 + channel, columns = the 64 staged query tokens
         if (has_q) {
-          const uint32_t tq = tmem_base + Cfg::TM_Q + 64 * (hg >> 1) + lane_sel;
+          const uint32_t tq = tmem_base + Cfg::TM_Q + 64 * lq + lane_sel;
           uint32_t rq[2][8];
           tmem_ld_x8(tq + (uint32_t)(part * 8), rq[0]);
           tmem_ld_x8(tq + (uint32_t)((part + 4) * 8), rq[1]);
@@ -577,7 +620,7 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
         }
         const float inv0 = 1.0f / ol[0], inv1 = 1.0f / ol[2];
         // attention output -> slab hg of the swizzled K-major O tile (token row, 64 channels of this head group)
-        const uint32_t o_slab = sb + Cfg::OFF_O + hg * (64 * 128);
+        const uint32_t o_slab = sb + Cfg::OFF_O + l * (64 * 128);
 #pragma unroll
         for (int v = 0; v < 2; ++v) {
           const int col = hl * HD + 8 * v + 2 * t;                     // channel within the head group's 64
@@ -592,12 +635,12 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
       // go on with the next head group (only head group 3's share of the projection is left for the end)
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_oready + 8 * hg);
+      if (lane == 0) mbar_arrive(bar_oready + 8 * l);
       worker_sync();   // every warp is done with this head group's q / k / v tiles and bias table
     }
     // ---- x[pix] = shortcut + proj(o) + b (DTransformer.py:204, 294-299) --------------------------------------------------------
     const long long t_p0 = dbg ? clock64() : 0;
-    {
+    if (CL == 1) {
       const int pt = part & 1, th = part >> 1;                  // projection tile (128 channels), token half
       const int ch = pt * 128 + qd * 32 + lane;
       const float bp = __ldg(p.bproj + ch);
@@ -630,6 +673,71 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
           }
         }
       }
+    } else {
+      // phase A: the PEER's 128 channels = shortcut + my partial projection.  All 16 warps work on one projection tile:
+      // lane quarter -> 32 channels, part -> token chunks 2 part, 2 part + 1 (7 chunks of 8 tokens)
+      const float* shortcut = p.frames[p.q_slot];
+      {
+        const int pt = 1 - rank;
+        const int ch = pt * 128 + qd * 32 + lane;
+        float sc[2][8];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int tok = (2 * part + i) * 8 + e;
+            const int pix = tok < kTok ? pix_s[tok] : -1;
+            sc[i][e] = pix >= 0 ? *(shortcut + (size_t)pix * C + ch) : 0.f;
+          }
+        mbar_wait_polite(bar_pfull, 0, lane);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if ((2 * part + i) * 8 < kTok) {
+            uint32_t raw[8];
+            tmem_ld_x8(tmem_base + Cfg::TM_P + 64 * pt + (uint32_t)((2 * part + i) * 8) + lane_sel, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int tok = (2 * part + i) * 8 + e;
+              const int pix = tok < kTok ? pix_s[tok] : -1;
+              if (pix >= 0) p.xs[(size_t)pix * C + ch] = sc[i][e] + __uint_as_float(raw[e]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      tc_cluster_arrive();    // barrier 1: the peer's phase-A rows of my channels are in x (release / acquire at cluster scope)
+      tc_cluster_wait();
+      // phase B: my own 128 channels += my partial + bias (read through L2: the peer wrote them)
+      {
+        const int pt = rank;
+        const int ch = pt * 128 + qd * 32 + lane;
+        const float bp = __ldg(p.bproj + ch);
+        float cur[2][8];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int tok = (2 * part + i) * 8 + e;
+            const int pix = tok < kTok ? pix_s[tok] : -1;
+            cur[i][e] = pix >= 0 ? __ldcg(p.xs + (size_t)pix * C + ch) : 0.f;
+          }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if ((2 * part + i) * 8 < kTok) {
+            uint32_t raw[8];
+            tmem_ld_x8(tmem_base + Cfg::TM_P + 64 * pt + (uint32_t)((2 * part + i) * 8) + lane_sel, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int tok = (2 * part + i) * 8 + e;
+              const int pix = tok < kTok ? pix_s[tok] : -1;
+              if (pix >= 0) p.xs[(size_t)pix * C + ch] = cur[i][e] + __uint_as_float(raw[e]) + bp;
+            }
+          }
+        }
+      }
     }
     tcgen05_fence_before();
     if (dbg && tid == 0) {
@@ -645,17 +753,17 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
   }
 }
 
-template <int NT>
+template <int NT, int CL>
 int launch_tc256(const CUtensorMap& tq, const CUtensorMap& tp, const TcAttnParams& p, cudaStream_t s) {
   using Cfg = TCfg<NT>;
-  auto kern = attn_win256_tc_kernel<NT>;
+  auto kern = attn_win256_tc_kernel<NT, CL>;
   if (first_use_on_device((const void*)kern)) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     BDE_REQUIRE(e == cudaSuccess, "bde_window_attention_fused: smem attribute (%d bytes): %s", Cfg::SMEM, cudaGetErrorString(e));
   }
   TcAttnParams q = p;
-  q.dbg = (g_dbg != nullptr && (size_t)2 * p.n_win <= g_dbg_ctas) ? g_dbg : nullptr;   // rows [n_win, 2 n_win): MMA-warp timeline
-  const cudaError_t le = launch_pdl(kern, (unsigned)p.n_win, (unsigned)kThreadsT, (size_t)Cfg::SMEM, s, 1, tq, tp, q);
+  q.dbg = (g_dbg != nullptr && (size_t)2 * CL * p.n_win <= g_dbg_ctas) ? g_dbg : nullptr;   // rows [n_ctas, 2 n_ctas): MMA-warp timeline
+  const cudaError_t le = launch_pdl(kern, (unsigned)(p.n_win * CL), (unsigned)kThreadsT, (size_t)Cfg::SMEM, s, CL, tq, tp, q);
   BDE_REQUIRE(le == cudaSuccess, "bde_window_attention_fused: launch: %s", cudaGetErrorString(le));
   return check_launch("attn_win256_tc_kernel");
 }
@@ -686,10 +794,23 @@ int attn_win256_tc_launch(const float* const* frames, int D, int q_slot, const i
     const char* e = getenv("BDE2VID_ATTN_TC256_PARK");
     p.park = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
+  // a 2-CTA cluster per window while both CTAs of every window still fit one wave (one sequence: 35 windows -> 70 CTAs)
+  int cl = 2 * n_win <= device_sm_count() ? 2 : 1;
+  if (const char* e = getenv("BDE2VID_ATTN_TC256_CLUSTER")) {
+    const int f = atoi(e);
+    if (f == 1 || f == 2) cl = f;
+  }
+  if (cl == 2) {
+    switch (D) {
+      case 1: return launch_tc256<7, 2>(tq, tp, p, s);
+      case 2: return launch_tc256<13, 2>(tq, tp, p, s);
+      default: return launch_tc256<19, 2>(tq, tp, p, s);
+    }
+  }
   switch (D) {
-    case 1: return launch_tc256<7>(tq, tp, p, s);
-    case 2: return launch_tc256<13>(tq, tp, p, s);
-    default: return launch_tc256<19>(tq, tp, p, s);
+    case 1: return launch_tc256<7, 1>(tq, tp, p, s);
+    case 2: return launch_tc256<13, 1>(tq, tp, p, s);
+    default: return launch_tc256<19, 1>(tq, tp, p, s);
   }
 }
 

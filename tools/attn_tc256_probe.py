@@ -40,8 +40,11 @@ for (B, D, dil, zero) in ((4, 3, False, None), (4, 3, True, 2), (1, 3, False, No
         ops.window_attention_fused(fr, qi, tm.view(-1), nwin, Cc, heads, wqkv, bqkv, tbl, wproj, bproj, xs=xs)
 
     outs = {}
-    for mode in ("0", "1"):
-        os.environ["BDE2VID_ATTN_TC256"] = mode
+    modes = ("0", "1", "1c2") if 2 * nwin <= 148 else ("0", "1")     # "1c2": one window per 2-CTA cluster (head groups split)
+    for mode in modes:
+        os.environ["BDE2VID_ATTN_TC256"] = mode[0]
+        os.environ["BDE2VID_ATTN_TC256_CLUSTER"] = "2" if mode == "1c2" else "1"
+        ncta = nwin * (2 if mode == "1c2" else 1)
         xs = frames[qi].clone()
         run(xs)
         torch.cuda.synchronize()
@@ -63,10 +66,10 @@ for (B, D, dil, zero) in ((4, 3, False, None), (4, 3, True, 2), (1, 3, False, No
         buf = np.zeros((1024, 8), dtype=np.int64)
         lib.bde_tc_debug_read(buf.ctypes.data_as(C.c_void_p), 1024)
         lib.bde_tc_debug_enable(0)
-        if mode == "1":     # MMA-warp timeline: rows [nwin, 2 nwin) = cycles since kernel start at stage 0 / 8 / 16 / 24 and at the end
-            tl = buf[nwin:2 * nwin].mean(0)
+        if mode != "0":     # MMA-warp timeline: rows [ncta, 2 ncta) = cycles since kernel start at stage 0 / 8 / 16 / 24 and at the end
+            tl = buf[ncta:2 * ncta].mean(0)
             print("   MMA warp timeline (cycles): stage0 %d  stage8 %d  stage16 %d  stage24 %d  end %d" % tuple(tl[:5]))
-            buf = buf[:nwin]
+            buf = buf[:ncta]
         used = buf[buf[:, 0] != 0]
         m = used.mean(0) if len(used) else np.zeros(8)
         names = ("total LN gather qkv tbl attn proj" if mode == "0" else "total LN wait conv - attn proj+epi").split()
@@ -76,4 +79,9 @@ for (B, D, dil, zero) in ((4, 3, False, None), (4, 3, True, 2), (1, 3, False, No
     upd = float((outs["0"] - frames[qi]).abs().max())
     print("   max |tc256 - mma.sync| = %.3e  (update magnitude %.3f, finite %s)" % (d, upd, bool(torch.isfinite(outs["1"]).all())))
     assert d <= 2e-2 * max(1.0, upd)
+    if "1c2" in outs:
+        d2 = float((outs["1c2"] - outs["1"]).abs().max())
+        print("   max |cluster of 2 - single CTA| = %.3e" % d2)
+        assert d2 <= 1e-4 * max(1.0, upd)     # same products; only the fp32 order of the projection's K = 256 sum differs
+del os.environ["BDE2VID_ATTN_TC256_CLUSTER"]
 print("attn_tc256 probe ok")
