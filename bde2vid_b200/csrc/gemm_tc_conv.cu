@@ -750,9 +750,12 @@ int conv_tma_launch(const bde_gemm_desc* d, const TcParams& p0, cudaStream_t s) 
   const bool pair = env_flag("BDE2VID_CONV_PAIR", false) && cp.num_m_tiles >= 2 && halo && bn_max == 256 && nsub == 1;
   const int cs = pair ? 2 : 1;
   const int units = device_sm_count() / cs;   // CTAs or CTA pairs that run concurrently
-  // tile width: the widest N tile that divides N, narrowed while the grid would leave SMs idle
+  // tile width: the widest N tile that divides N, narrowed only while even the narrower tiles leave half of the SMs idle.
+  // A narrow tile re-streams the activations per N tile and issues MMAs of half the width: measured on the ConvLSTM gate
+  // convolutions of one sequence (tools/conv_probe.py, us per launch for BN = 64 / 128 / 256): level 2 (110 tiles of 256)
+  // 36.9 / 29.2 / 20.8, level 3 (60 tiles of 256) 46.2 / 29.1 / 32.0; two sequences, level 3: 85.8 / 52.9 / 33.9.
   int bn = bn_max;
-  while (nsub == 1 && !pair && bn > 64 && ceil_div(cp.num_m_tiles, cs) * (size_t)(p.N / bn) < (size_t)units) bn /= 2;
+  while (nsub == 1 && !pair && bn > 64 && 2 * ceil_div(cp.num_m_tiles, cs) * (size_t)(p.N / bn) <= (size_t)units) bn /= 2;
   {
     const int f = env_int("BDE2VID_CONV_BN", 0);
     if ((f == 32 || f == 64 || f == 128 || f == 256) && p.N % f == 0 && nsub == 1 && !pair) bn = f;

@@ -146,7 +146,10 @@ def main():
     time_case("lstm L2 (B=4)", B, 256, 512, 66, 88, 3, 1, lstm=True)
     time_case("lstm L3 (B=4)", B, 512, 1024, 33, 44, 3, 1, lstm=True)
     time_case("lstm L1 (B=1)", 1, 128, 256, 132, 176, 3, 1, lstm=True)
+    time_case("lstm L2 (B=1)", 1, 256, 512, 66, 88, 3, 1, lstm=True)
     time_case("lstm L3 (B=1)", 1, 512, 1024, 33, 44, 3, 1, lstm=True)
+    time_case("lstm L2 (B=2)", 2, 256, 512, 66, 88, 3, 1, lstm=True)
+    time_case("lstm L3 (B=2)", 2, 512, 1024, 33, 44, 3, 1, lstm=True)
     time_case("dec0 256->128 (24 fr)", 24, 256, 128, 66, 88, 5, 1)
     time_case("dec1 128->64 (24 fr)", 24, 128, 64, 132, 176, 5, 1)
     time_case("dec2 64->32 (24 fr)", 24, 64, 32, 264, 352, 5, 1, iters=5)
