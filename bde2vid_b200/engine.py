@@ -318,7 +318,15 @@ class Engine:
         # plans (buffers + CUDA graph per (T, B, Hp, Wp, slot)) are kept in an LRU bounded in bytes: the reference driver
         # with subseq_L=None calls the model with a different T per file (eval_models_seq.py:216-221)
         self.plans = OrderedDict()
-        self.plan_cache_bytes = int(float(os.environ.get("BDE2VID_PLAN_CACHE_GB", "64")) * 2 ** 30)
+        # budget: BDE2VID_PLAN_CACHE_GB, else 60 % of the device's memory (108 GB on a B200: two streams x eight 100-window
+        # sequences keep ~2 x 33 GB of plans alive and must not evict each other inside a step)
+        gb = os.environ.get("BDE2VID_PLAN_CACHE_GB")
+        if gb is not None:
+            self.plan_cache_bytes = int(float(gb) * 2 ** 30)
+        elif torch.cuda.is_available():
+            self.plan_cache_bytes = int(0.6 * torch.cuda.get_device_properties(self.device).total_memory)
+        else:
+            self.plan_cache_bytes = 64 * 2 ** 30
         self.dec_chunk = 8
 
     # ------------------------------------------------------------------------------------

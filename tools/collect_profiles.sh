@@ -3,11 +3,11 @@
 S=gpurun_out/final; D=profiles; R=r02
 cp $S/pytest_gpu.log $D/${R}_pytest_gpu.log
 cp $S/smoke.log $D/${R}_smoke.log
-cp $S/bench.json $D/${R}_bench_default_3x4.json
+cp $S/bench.json $D/${R}_bench_default_2x8.json
 cp $S/bench_reference.json $D/${R}_bench_reference_arm.json
 for c in e2vid16 gen4 shard64; do [ -s $S/bench_$c.json ] && cp $S/bench_$c.json $D/${R}_bench_$c.json; done
-cp $S/launches_b4.csv $D/${R}_ncu_launches_batch4_T6.csv
-cp $S/launches_b4.summary.txt $D/${R}_ncu_launches_batch4_T6.summary.txt
+cp $S/launches_b8.csv $D/${R}_ncu_launches_batch8_T6.csv
+cp $S/launches_b8.summary.txt $D/${R}_ncu_launches_batch8_T6.summary.txt
 for f in attn_tc256 attn64 mlp256 mlp64 conv_lstm; do
   [ -s $S/prof_$f.raw.csv ] || continue
   cp $S/prof_$f.raw.csv $D/${R}_ncu_full_prof_$f.raw.csv

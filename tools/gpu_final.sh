@@ -16,12 +16,12 @@ timeout 300 python tools/voxel_probe.py > $O/voxel_probe.log 2>&1; echo "voxel p
 timeout 300 python tools/mlp_probe.py > $O/mlp_probe.log 2>&1; echo "mlp probe exit $?"
 timeout 300 python tools/attn_tc256_probe.py > $O/attn_tc256_probe.log 2>&1; echo "tc256 probe exit $?"
 fi
-CMD="python bench.py --windows 6 --steps 1 --warmup 3 --concurrent 1 --batch 4 --no-cpu-baseline --no-kernel-timing --no-single"
+CMD="python bench.py --windows 6 --steps 1 --warmup 3 --concurrent 1 --batch 8 --no-cpu-baseline --no-kernel-timing --no-single"
 timeout 600 $CMD > $O/plain.log 2>&1 && \
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file $O/launches_b4.csv $CMD > $O/ncu.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file $O/launches_b8.csv $CMD > $O/ncu.log 2>&1
 echo "ncu launch list exit $?"
-python tools/launch_summary.py $O/launches_b4.csv > $O/launches_b4.summary.txt 2>&1
-CMD1="python bench.py --windows 4 --steps 1 --warmup 3 --concurrent 1 --batch 4 --no-cpu-baseline --no-kernel-timing --no-single"
+python tools/launch_summary.py $O/launches_b8.csv > $O/launches_b8.summary.txt 2>&1
+CMD1="python bench.py --windows 4 --steps 1 --warmup 3 --concurrent 1 --batch 8 --no-cpu-baseline --no-kernel-timing --no-single"
 timeout 600 $CMD1 > $O/plain1.log 2>&1
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:attn_win256_tc_kernel -s 30 -c 1 -o $O/prof_attn_tc256 $CMD1 > $O/ncu1.log 2>&1; echo "ncu tc256 exit $?"
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:attn_fused_kernel -s 20 -c 1 -o $O/prof_attn64 $CMD1 > $O/ncu2.log 2>&1; echo "ncu attn64 exit $?"

@@ -1,8 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for cfg in "2 4" "2 8" "1 8" "3 4" "2 6" "1 16"; do
+export BDE2VID_PLAN_CACHE_GB=150
+for cfg in "2 6" "3 6" "2 8" "4 4" "3 8" "3 4"; do
   set -- $cfg
-  timeout 400 python bench.py --steps 3 --warmup 3 --concurrent $1 --batch $2 --no-cpu-baseline --no-kernel-timing > gpurun_out/sweep_$1x$2.json 2> gpurun_out/sweep_$1x$2.err
+  timeout 400 python bench.py --steps 3 --warmup 3 --concurrent $1 --batch $2 --no-cpu-baseline --no-kernel-timing --no-single > gpurun_out/sweep_$1x$2.json 2> gpurun_out/sweep_$1x$2.err
   python - <<PY
 import json
 try:
