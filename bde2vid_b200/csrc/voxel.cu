@@ -228,15 +228,22 @@ struct EvSrcRaw {
 };
 
 template <typename Src, bool kAgg>
-__global__ void __launch_bounds__(256) voxel_atomic_kernel(
+__global__ void __launch_bounds__(256, 4) voxel_atomic_kernel(
     const Src src, const int64_t* __restrict__ offsets, int win0, int bins, int H, int W, int pad_top, int pad_left, int Hp, int Wp,
-    float* __restrict__ out, size_t win_stride, int* oob_count, int min_events, const float* __restrict__ hot_mask) {
+    float* __restrict__ out, size_t win_stride, int* oob_count, int min_events, const float* __restrict__ hot_mask,
+    int zero_win0, int zero_n, unsigned long long grid_elems4) {
+  // Chunk pipeline (launch_atomic): this launch reduces into the windows [win0, win0 + gridDim.y), which the PREVIOUS
+  // launch (or a memset, for the first chunk) zeroed, and zeroes the windows [zero_win0, zero_win0 + zero_n) of the NEXT
+  // chunk.  Launched with programmatic stream serialisation, so everything up to pdl_wait() -- the window bounds, t0 / dt
+  // and the first four events of every thread, all inputs that no kernel of the chain writes -- overlaps the tail of the
+  // previous launch; the reductions and the zero stores come after pdl_wait() (previous grid complete, its zeroes visible).
+  pdl_trigger();
   const int win = win0 + blockIdx.y;
   const int64_t ea = offsets[win], eb = offsets[win + 1];
   // loader contract (h5_dataset.py:219-221): windows with fewer than `min_events` events give an all-zero grid
-  if (eb - ea < (int64_t)min_events || eb <= ea) return;
-  float dt;
-  src.window(ea, eb, dt);
+  const bool live_win = !(eb - ea < (int64_t)min_events || eb <= ea);
+  float dt = 1.0f;
+  if (live_win) src.window(ea, eb, dt);
   const float bm1 = (float)(bins - 1);
   float* dst = out + (size_t)win * win_stride;
   const size_t plane = (size_t)Hp * Wp;
@@ -295,26 +302,39 @@ __global__ void __launch_bounds__(256) voxel_atomic_kernel(
   // scalar head up to a multiple of 4, vector body, scalar tail
   const int64_t body_a = vec ? min(eb, (ea + 3) & ~(int64_t)3) : eb;
   const int64_t body_b = vec ? max(body_a, eb & ~(int64_t)3) : eb;
-  const int64_t n_edge = (body_a - ea) + (eb - body_b);
+  const int64_t n_edge = live_win ? (body_a - ea) + (eb - body_b) : 0;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nvec = live_win ? (body_b - body_a) >> 2 : 0;
+  float x[4], y[4], t[4], p[4];
+  if (nvec > 0 && (kAgg || tid < nvec)) src.load4(body_a + 4 * (tid < nvec ? tid : 0), x, y, t, p);
+  pdl_wait();
   // (warp-uniform trip counts so that the aggregated form's votes stay convergent)
   for (int64_t base = 0; base < n_edge; base += nthr) {
     const int64_t i = base + tid;
     const bool valid = i < n_edge;
     const int64_t e = valid ? (i < body_a - ea ? ea + i : body_b + (i - (body_a - ea))) : ea;
-    float x, y, t, p;
-    src.load1(e, x, y, t, p);
-    if (kAgg || valid) one(x, y, t, p, valid);
+    float x1, y1, t1, p1;
+    src.load1(e, x1, y1, t1, p1);
+    if (kAgg || valid) one(x1, y1, t1, p1, valid);
   }
-  const int64_t nvec = (body_b - body_a) >> 2;
   for (int64_t base = 0; base < nvec; base += nthr) {
     const int64_t v = base + tid;
     const bool valid = v < nvec;
     if (!kAgg && !valid) break;
-    float x[4], y[4], t[4], p[4];
-    src.load4(body_a + 4 * (valid ? v : 0), x, y, t, p);
+    if (base != 0) src.load4(body_a + 4 * (valid ? v : 0), x, y, t, p);   // the first group was loaded ahead of pdl_wait()
 #pragma unroll
     for (int k = 0; k < 4; ++k) one(x[k], y[k], t[k], p[k], valid);
+  }
+  // zero the next chunk's grids (16-byte stores, the whole launch strides over them)
+  if (zero_n > 0) {
+    const unsigned long long gtid = ((unsigned long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    const unsigned long long gn = (unsigned long long)gridDim.y * gridDim.x * blockDim.x;
+    const unsigned long long total = (unsigned long long)zero_n * grid_elems4;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (unsigned long long i = gtid; i < total; i += gn) {
+      const unsigned long long w = i / grid_elems4, r = i - w * grid_elems4;
+      reinterpret_cast<float4*>(out + (size_t)(zero_win0 + w) * win_stride)[r] = z;
+    }
   }
   if (oob_count != nullptr && oob > 0) atomicAdd(oob_count, oob);
 }
@@ -537,15 +557,42 @@ __global__ void pack_voxel_kernel(const float* __restrict__ vox, int bins, size_
 
 using namespace bde;
 
-// memset + reduction kernel, in chunks of windows whose grids fit L2 together: the lines zeroed by the memset are still
-// resident when the reductions hit them, so the grid goes to HBM once (write-back) instead of memset-write + reduction
-// read + write-back.
+// Reduction kernel over chunks of windows whose grids fit L2 together: the zeroed lines are still resident when the
+// reductions hit them, so the grid goes to HBM once (write-back) instead of zero-write + reduction read + write-back.
+// Chunk 0 is zeroed by a memset; every launch zeroes the NEXT chunk's grids after its own reductions have been issued,
+// and the launches are chained with programmatic stream serialisation (see the kernel), so that the zero stores (HBM /
+// L2 write bandwidth) run under the reductions (L2 atomic units) and the event loads of chunk c + 1 under the tail of
+// chunk c.  Round 2 measured memset + kernel back to back: 36 + 64 us per 100 windows of the bench shape.
+template <typename Src, bool kAgg>
+static cudaError_t launch_voxel_atomic(dim3 grid, cudaStream_t s, const Src& src, const int64_t* offsets, int w0, int num_bins, int H,
+                                       int W, int pad_top, int pad_left, int Hp, int Wp, float* out, size_t stride, int* oob_count,
+                                       int min_events, const float* hot_mask, int zero_win0, int zero_n, unsigned long long grid_elems4) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(256);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  unsigned n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, voxel_atomic_kernel<Src, kAgg>, src, offsets, w0, num_bins, H, W, pad_top, pad_left, Hp, Wp, out,
+                            stride, oob_count, min_events, hot_mask, zero_win0, zero_n, grid_elems4);
+}
+
 template <typename Src>
 static int launch_atomic(const Src& src, bool agg, const int64_t* offsets, int T, int num_bins, int H, int W, int pad_top, int pad_left,
                          int Hp, int Wp, float* out, size_t out_window_stride, int* oob_count, int min_events, const float* hot_mask,
                          cudaStream_t s) {
   const size_t grid_elems = (size_t)num_bins * Hp * Wp;
-  size_t chunk_mb = 48;
+  // the chunk being reduced and the chunk being zeroed share L2.  Measured (tools/voxel_probe.py --pipeline2): 32 MB is
+  // best at 346x260 (17 windows per chunk), 40 MB at 1280x720 (two 18.4 MB windows per chunk instead of one)
+  size_t chunk_mb = grid_elems * sizeof(float) > (8u << 20) ? 40 : 32;
   if (const char* e = getenv("BDE2VID_VOXEL_CHUNK_MB")) {
     const long v = atol(e);
     if (v > 0) chunk_mb = (size_t)v;
@@ -553,21 +600,35 @@ static int launch_atomic(const Src& src, bool agg, const int64_t* offsets, int T
   int per_chunk = (int)((chunk_mb << 20) / (grid_elems * sizeof(float)));   // L2 footprint of a window = its grid, not the stride
   per_chunk = per_chunk < 1 ? 1 : (per_chunk > T ? T : per_chunk);
   const int n_sm = device_sm_count();
+  // in-kernel zeroing uses 16-byte stores
+  bool zero_in_kernel = grid_elems % 4 == 0 && out_window_stride % 4 == 0 && (((uintptr_t)out) & 15) == 0;
+  if (const char* e = getenv("BDE2VID_VOXEL_ZERO_IN_KERNEL")) zero_in_kernel = zero_in_kernel && e[0] != '0';
+  // exactly one wave (4 CTAs of 256 threads x 64 registers per SM): the next launch of the chain can only start once every
+  // CTA of this one has started, so a partial second wave delays it (5 or 6 CTAs per SM: 0.089 ms vs 0.076 ms per 100 windows)
+  size_t ctas_per_sm = 4;
+  if (const char* e = getenv("BDE2VID_VOXEL_CTAS_PER_SM")) {
+    const long v = atol(e);
+    if (v > 0) ctas_per_sm = (size_t)v;
+  }
   for (int w0 = 0; w0 < T; w0 += per_chunk) {
     const int n = (T - w0 < per_chunk) ? T - w0 : per_chunk;
-    float* base = out + (size_t)w0 * out_window_stride;
-    cudaError_t e = cudaMemset2DAsync(base, out_window_stride * sizeof(float), 0, grid_elems * sizeof(float), (size_t)n, s);
-    BDE_REQUIRE(e == cudaSuccess, "bde_voxelize_seq: memset: %s", cudaGetErrorString(e));
+    if (w0 == 0 || !zero_in_kernel) {
+      float* base = out + (size_t)w0 * out_window_stride;
+      cudaError_t e = cudaMemset2DAsync(base, out_window_stride * sizeof(float), 0, grid_elems * sizeof(float), (size_t)n, s);
+      BDE_REQUIRE(e == cudaSuccess, "bde_voxelize_seq: memset: %s", cudaGetErrorString(e));
+    }
+    const int zw0 = w0 + n;
+    const int zn = zero_in_kernel ? ((T - zw0 < per_chunk) ? T - zw0 : per_chunk) : 0;
     // grid.x sized so that the chunk is a few waves over the SMs regardless of its window count
-    int bx = (int)ceil_div((size_t)n_sm * 8, (size_t)n);
+    int bx = (int)ceil_div((size_t)n_sm * ctas_per_sm, (size_t)n);
     bx = bx < 1 ? 1 : (bx > 1024 ? 1024 : bx);
     dim3 grid(bx, n);
-    if (agg)
-      voxel_atomic_kernel<Src, true><<<grid, 256, 0, s>>>(src, offsets, w0, num_bins, H, W, pad_top, pad_left, Hp, Wp, out,
-                                                          out_window_stride, oob_count, min_events, hot_mask);
-    else
-      voxel_atomic_kernel<Src, false><<<grid, 256, 0, s>>>(src, offsets, w0, num_bins, H, W, pad_top, pad_left, Hp, Wp, out,
-                                                           out_window_stride, oob_count, min_events, hot_mask);
+    const cudaError_t e =
+        agg ? launch_voxel_atomic<Src, true>(grid, s, src, offsets, w0, num_bins, H, W, pad_top, pad_left, Hp, Wp, out, out_window_stride,
+                                             oob_count, min_events, hot_mask, zw0, zn, (unsigned long long)(grid_elems / 4))
+            : launch_voxel_atomic<Src, false>(grid, s, src, offsets, w0, num_bins, H, W, pad_top, pad_left, Hp, Wp, out, out_window_stride,
+                                              oob_count, min_events, hot_mask, zw0, zn, (unsigned long long)(grid_elems / 4));
+    BDE_REQUIRE(e == cudaSuccess, "voxel_atomic_kernel: launch: %s", cudaGetErrorString(e));
     const int rc = check_launch("voxel_atomic_kernel");
     if (rc != 0) return rc;
   }

@@ -63,6 +63,25 @@ if "--ncu-shape" in sys.argv:
         torch.cuda.synchronize()
     sys.exit(0)
 
+if "--pipeline2" in sys.argv:
+    base = {"BDE2VID_VOXEL_ZERO_IN_KERNEL": "1", "BDE2VID_PDL": "1"}
+    mk = lambda mb, cps: ("zero in kernel, %d MB, %d CTAs/SM" % (mb, cps), 2, dict(base, BDE2VID_VOXEL_CHUNK_MB=str(mb), BDE2VID_VOXEL_CTAS_PER_SM=str(cps)))  # noqa: E731
+    run_shape(260, 346, 31500, 100, 264, 352, 2, 3, [mk(mb, cps) for mb in (28, 32, 36, 40) for cps in (2, 3, 4, 5, 6)], streams=("uniform",))
+    run_shape(720, 1280, 333333, 64, 720, 1280, 0, 0, [mk(mb, cps) for mb in (20, 40, 60) for cps in (4, 6, 8, 12, 16)], streams=("uniform",))
+    sys.exit(0)
+if "--pipeline" in sys.argv:
+    # chunk pipeline of the default algorithm: in-kernel zeroing of the next chunk on / off, chunk size, CTAs per SM
+    base = {"BDE2VID_VOXEL_ZERO_IN_KERNEL": "1", "BDE2VID_VOXEL_CHUNK_MB": "32", "BDE2VID_VOXEL_CTAS_PER_SM": "8", "BDE2VID_PDL": "1"}
+    variants = [("memset per chunk, 48 MB (round-2 form)", dict(base, BDE2VID_VOXEL_ZERO_IN_KERNEL="0", BDE2VID_VOXEL_CHUNK_MB="48"))]
+    for mb in (16, 24, 32, 48):
+        for cps in (4, 8):
+            variants.append(("zero in kernel, %d MB, %d CTAs/SM" % (mb, cps), dict(base, BDE2VID_VOXEL_CHUNK_MB=str(mb), BDE2VID_VOXEL_CTAS_PER_SM=str(cps))))
+    variants.append(("zero in kernel, 32 MB, 8 CTAs/SM, no PDL", dict(base, BDE2VID_PDL="0")))
+    algos = tuple((n, 2, env) for n, env in variants)
+    run_shape(260, 346, 31500, 100, 264, 352, 2, 3, algos, streams=("uniform",))
+    run_shape(720, 1280, 333333, 64, 720, 1280, 0, 0, algos[:1] + algos[5:7], streams=("uniform",))
+    sys.exit(0)
+
 ALGOS = (("2 memset + global RED (default)", 2, {}), ("5 = 2 + warp aggregation", 5, {}), ("1 row-band tiles + warp aggregation", 1, {}),
          ("3 cluster DSMEM reductions", 3, {}), ("4 cluster zero + global RED", 4, {}))
 run_shape(260, 346, 31500, 100, 264, 352, 2, 3, ALGOS)
