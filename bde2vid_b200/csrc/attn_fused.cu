@@ -103,6 +103,13 @@ __device__ __forceinline__ uint32_t pack2_h(float lo, float hi) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// V tiles: values beyond the fp16 range saturate at +-65504 instead of becoming inf (inf * p = nan for p = 0); with the
+// LayerNorm'ed inputs of this model |v| is O(10), the clamp only matters for pathological checkpoints
+__device__ __forceinline__ uint32_t pack2_hs(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 // (2^lo, 2^hi) as an fp16 pair.  Two fp32 MUFU.EX2 + one packing convert: ex2.approx.f16x2 is NOT a single MUFU op on
 // sm_100a (ptxas expands it to unpack + 2 x MUFU.EX2 + pack: measured +30 % instructions in this kernel).
 __device__ __forceinline__ uint32_t ex2_h2(float lo, float hi) {
@@ -359,9 +366,9 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
             const int col = npair * 16 + n * 8 + 2 * t;
             // k stays bf16 (q.k^T is a bf16 product); v is stored as fp16 for the fp16 P.V product
             const float v00 = acc[i][n][0] + bb.x, v01 = acc[i][n][1] + bb.y, v10 = acc[i][n][2] + bb.x, v11 = acc[i][n][3] + bb.y;
-            if (r0 < row_lim) *reinterpret_cast<uint32_t*>(dstm + r0 * PQ + col) = which == 1 ? pack2(v00, v01) : pack2_h(v00, v01);
+            if (r0 < row_lim) *reinterpret_cast<uint32_t*>(dstm + r0 * PQ + col) = which == 1 ? pack2(v00, v01) : pack2_hs(v00, v01);
             if (r0 + 8 < row_lim)
-              *reinterpret_cast<uint32_t*>(dstm + (r0 + 8) * PQ + col) = which == 1 ? pack2(v10, v11) : pack2_h(v10, v11);
+              *reinterpret_cast<uint32_t*>(dstm + (r0 + 8) * PQ + col) = which == 1 ? pack2(v10, v11) : pack2_hs(v10, v11);
           }
         }
       }
@@ -1006,7 +1013,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[e]));
-            wv[e] = pack2_h(f2.x, f2.y);
+            wv[e] = pack2_hs(f2.x, f2.y);
           }
           val = make_uint4(wv[0], wv[1], wv[2], wv[3]);
         }
@@ -1044,9 +1051,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
           const float2 bb = n == 0 ? bia0 : bia1;
           const int col = npair * 16 + n * 8 + 2 * t;
           const float v00 = acc[0][n][0] + bb.x, v01 = acc[0][n][1] + bb.y, v10 = acc[0][n][2] + bb.x, v11 = acc[0][n][3] + bb.y;
-          if (tok0 < kTok) *reinterpret_cast<uint32_t*>(dstm + (base + tok0) * PQ + col) = which == 1 ? pack2(v00, v01) : pack2_h(v00, v01);
+          if (tok0 < kTok) *reinterpret_cast<uint32_t*>(dstm + (base + tok0) * PQ + col) = which == 1 ? pack2(v00, v01) : pack2_hs(v00, v01);
           if (tok0 + 8 < kTok)
-            *reinterpret_cast<uint32_t*>(dstm + (base + tok0 + 8) * PQ + col) = which == 1 ? pack2(v10, v11) : pack2_h(v10, v11);
+            *reinterpret_cast<uint32_t*>(dstm + (base + tok0 + 8) * PQ + col) = which == 1 ? pack2(v10, v11) : pack2_hs(v10, v11);
         }
       } else {
         float acc[MTK][2][4];
@@ -1068,9 +1075,9 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_win256_kernel(const FusedAt
               const float2 bb = n == 0 ? bia0 : bia1;
               const int col = npair * 16 + n * 8 + 2 * t;
               const float v00 = acc[i][n][0] + bb.x, v01 = acc[i][n][1] + bb.y, v10 = acc[i][n][2] + bb.x, v11 = acc[i][n][3] + bb.y;
-              if (r0 < row_lim) *reinterpret_cast<uint32_t*>(dstm + r0 * PQ + col) = which == 1 ? pack2(v00, v01) : pack2_h(v00, v01);
+              if (r0 < row_lim) *reinterpret_cast<uint32_t*>(dstm + r0 * PQ + col) = which == 1 ? pack2(v00, v01) : pack2_hs(v00, v01);
               if (r0 + 8 < row_lim)
-                *reinterpret_cast<uint32_t*>(dstm + (r0 + 8) * PQ + col) = which == 1 ? pack2(v10, v11) : pack2_h(v10, v11);
+                *reinterpret_cast<uint32_t*>(dstm + (r0 + 8) * PQ + col) = which == 1 ? pack2(v10, v11) : pack2_hs(v10, v11);
             }
           }
         }

@@ -506,7 +506,7 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
               if (tok < row_lim) {
                 // k stays bf16 (q.k^T is a bf16 product); v is fp16 for the fp16 P.V product
                 if (is_k) dstm[tok * PQ + ch] = __float2bfloat16_rn(val);
-                else reinterpret_cast<__half*>(dstm)[tok * PQ + ch] = __float2half_rn(val);
+                else reinterpret_cast<__half*>(dstm)[tok * PQ + ch] = __float2half_rn(fminf(fmaxf(val, -65504.0f), 65504.0f));   // saturate, never inf
               }
             }
           }

@@ -367,6 +367,8 @@ def main():
     pk = peaks()
     roofline = None
     voxel_roof = None
+    attn_roof = None
+    shares = None
     if not args.no_kernel_timing:
         # live per-kernel timing of the dominant kernel (the tcgen05 implicit-GEMM engine): one eager
         # (non-graph) pass of the same step with a CUDA event pair recorded in C right around every launch on
@@ -377,12 +379,62 @@ def main():
         lib = _lib.load()
         torch.cuda.synchronize()
         lib.bde_profile_begin(200000)
-        torch.cuda._sleep(int(0.15 * 1.9e9))
+        # the same pass also gives the live share of every kernel class: each ops.* entry point of the schedule is
+        # bracketed by a CUDA event pair on the (single) launching stream
+        klass = {"window_attention_fused": lambda a: "attention_level1" if a[4] == 64 else "attention_level3",
+                 "mlp_fused": lambda a: "fused_mlp_c%d" % a[2], "gemm": lambda a: "bde_gemm_tcgen05_convs",
+                 "head_conv": lambda a: "head_conv", "voxelize_seq_into": lambda a: "voxeliser",
+                 "upsample2x_sum": lambda a: "elementwise", "pred_sigmoid": lambda a: "elementwise",
+                 "add": lambda a: "elementwise", "cast": lambda a: "elementwise"}
+        pairs, saved = [], {}
+
+        def bracket(name, fn, cls_of):
+            def wrapped(*a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = fn(*a, **k)
+                e1.record()
+                pairs.append((cls_of(a), e0, e1))
+                return r
+            return wrapped
+        for name, cls_of in klass.items():
+            saved[name] = getattr(ops, name)
+            setattr(ops, name, bracket(name, saved[name], cls_of))
+        torch.cuda._sleep(int(0.3 * 1.9e9))
         plan.overlap = False           # one stream: every launch is timed alone
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.no_grad():
+            p0.record()
             plan._enqueue(True)
+            p1.record()
         torch.cuda.synchronize()
         plan.overlap = True
+        for name, fn in saved.items():
+            setattr(ops, name, fn)
+        pass_ms = p0.elapsed_time(p1)
+        shares = {}
+        for cls, e0, e1 in pairs:
+            d = shares.setdefault(cls, {"ms": 0.0, "launches": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["launches"] += 1
+        for d in shares.values():
+            d["share"] = d["ms"] / pass_ms
+            d["avg_us"] = d["ms"] * 1e3 / d["launches"]
+        shares["_pass"] = {"ms": pass_ms, "what": "one eager single-stream pass of one model call (%d sequences x %d windows), "
+                                                 "every launch serialised; shares are of this pass" % (NB, T)}
+        # level-1 attention (the largest share): its binding unit is the special-function pipe -- one ex2 per
+        # (head, query, key) score: 16 heads x 49 x 147 per window; measured MUFU.EX2 rate 16 / clk / SM
+        attn_roof = None
+        if "attention_level1" in shares:
+            a1 = shares["attention_level1"]
+            nwin1 = plan.lv[0]["nwin"] if "nwin" in plan.lv[0] else 0
+            ex2 = 16.0 * 49 * 147 * nwin1 * a1["launches"]
+            sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            peak_ex2 = 16.0 * sm * (clocks.get("sm_mhz") or 1965.0) * 1e6
+            attn_roof = {"kernel": "attn_fused_kernel<64,4,19> (level-1 window attention, head_dim 4)", "bound": "sfu (MUFU.EX2)",
+                         "achieved": ex2 / (a1["ms"] * 1e-3) / 1e12, "peak": peak_ex2 / 1e12, "unit": "T ex2/s",
+                         "frac": ex2 / (a1["ms"] * 1e-3) / peak_ex2, "avg_launch_us": a1["avg_us"], "windows_per_launch": nwin1,
+                         "peak_source": "16 ex2 / clk / SM (tools/micro/mufu_probe.cu) x SMs x SM clock under load"}
         tot, cnt = C.c_double(0.0), C.c_int(0)
         lib.bde_profile_end(C.byref(tot), C.byref(cnt))
         gemm_ms, n_rec = float(tot.value), int(cnt.value)
@@ -417,8 +469,9 @@ def main():
         torch.cuda.synchronize()
         vms = s.elapsed_time(e) / 10
         vach = VOXEL_BYTES_PER_WINDOW * T / (vms * 1e-3) / 1e9
-        voxel_roof = {"kernel": "voxel_atomic_kernel (grid memset + global RED.ADD.F32 executed by L2, in L2-sized chunks of "
-                                "windows; 128-bit event loads)", "bound": "hbm", "achieved": vach, "peak": pk["hbm"], "unit": "GB/s",
+        voxel_roof = {"kernel": "voxel_atomic_kernel (global RED.ADD.F32 executed by L2 into L2-resident zeroed grids, in chunks of "
+                                "windows; every launch zeroes the next chunk, launches chained with programmatic dependent launch; "
+                                "128-bit event loads)", "bound": "hbm", "achieved": vach, "peak": pk["hbm"], "unit": "GB/s",
                       "frac": vach / pk["hbm"], "traffic": VOXEL_TRAFFIC.get("bytes_per_100_windows"),
                       "traffic_source": VOXEL_TRAFFIC.get("source"), "ms_per_launch": vms,
                       "bytes_per_launch": VOXEL_BYTES_PER_WINDOW * T}
@@ -472,7 +525,8 @@ def main():
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
-            "clocks": clocks, "roofline": roofline, "roofline_voxeliser": voxel_roof, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roofline, "roofline_voxeliser": voxel_roof, "roofline_attention": attn_roof,
+            "kernel_shares": shares, "cpu_baseline": cpu,
             "tflops_algorithmic": fps / world * (GF_CONV + GF_LINEAR + GF_BMM) / 1e3,
             "frame_checksum": chk, "precision": args.precision,
             "single_sequence": single, "parity": parity, "resident_plan_gb": plan_gb,
