@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbde2vid_sm100.so")
+# BDE2VID_LIB: another build of the same library (ablation builds of tools/attn64_probe.sh); the default is the in-tree one
+LIB_PATH = os.environ.get("BDE2VID_LIB") or os.path.join(_HERE, "libbde2vid_sm100.so")
 
 F32, BF16 = 0, 1
 ABI_VERSION = 2

@@ -16,6 +16,11 @@
 
 #include <cuda_fp16.h>
 #include <stdlib.h>
+// Ablation builds for tools/attn64_probe.sh (timing only, results are wrong): bit 0 = no bias-table loads, bit 1 = no MUFU.EX2
+// in the probabilities, 4 = skip the level-1 attention core altogether.  0 in every shipped build.
+#ifndef BDE_ATTN_PROBE
+#define BDE_ATTN_PROBE 0
+#endif
 namespace bde {
 namespace tc {
 extern long long* g_dbg;   // bring-up cycle-counter buffer owned by gemm_tc.cu (bde_tc_debug_enable)
@@ -113,6 +118,9 @@ __device__ __forceinline__ uint32_t pack2_hs(float lo, float hi) {
 // (2^lo, 2^hi) as an fp16 pair.  Two fp32 MUFU.EX2 + one packing convert: ex2.approx.f16x2 is NOT a single MUFU op on
 // sm_100a (ptxas expands it to unpack + 2 x MUFU.EX2 + pack: measured +30 % instructions in this kernel).
 __device__ __forceinline__ uint32_t ex2_h2(float lo, float hi) {
+#if BDE_ATTN_PROBE & 2
+  return pack2_h(lo, hi);
+#endif
   float a, b;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(lo));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(hi));
@@ -426,7 +434,7 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
     constexpr int SEG = ((NT + 2) / 3) & ~1;                      // even segment size: 19 -> 6, 13 -> 4, 7 -> 2
     constexpr int LAST = NT - 2 * SEG;                            // 7 / 5 / 3
     constexpr int kMaxT = LAST > SEG ? LAST : SEG;
-    for (int pi = warp; pi < NPAIRS; pi += kThreadsF / 32) {
+    for (int pi = warp; pi < (BDE_ATTN_PROBE == 4 ? 0 : NPAIRS); pi += kThreadsF / 32) {
       const int hp = pi / MTN, mt = pi - hp * MTN;                // heads hp and hp + 8
       const int row0 = mt * 16 + g, row1 = row0 + 8;
       const uint32_t r0a = tbl_u32 + (uint32_t)(hp * TLD * 4 + roff[row0]);
@@ -457,12 +465,17 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
         for (int jj = 0; jj < kMaxT; ++jj) {
           if (jj < nj) {
             const int j = j0 + jj;
+#if BDE_ATTN_PROBE & 1
+            s[0][jj][0] = s[0][jj][1] = s[0][jj][2] = s[0][jj][3] = 0.f;
+            s[1][jj][0] = s[1][jj][1] = s[1][jj][2] = s[1][jj][3] = 0.f;
+#else
             const uint2 cp = lds_u64(coff_u32 + (uint32_t)((j * 8 + 2 * t) * 4));
             const uint32_t a00 = r0a + cp.x, a01 = r0a + cp.y, a10 = r1a + cp.x, a11 = r1a + cp.y;
             s[0][jj][0] = lds_f32_off<0>(a00); s[0][jj][1] = lds_f32_off<0>(a01);
             s[0][jj][2] = lds_f32_off<0>(a10); s[0][jj][3] = lds_f32_off<0>(a11);
             s[1][jj][0] = lds_f32_off<kTblOff>(a00); s[1][jj][1] = lds_f32_off<kTblOff>(a01);
             s[1][jj][2] = lds_f32_off<kTblOff>(a10); s[1][jj][3] = lds_f32_off<kTblOff>(a11);
+#endif
             uint32_t kb[2] = {0u, 0u};
             if (2 * t < HD) {
               kb[0] = *reinterpret_cast<const uint32_t*>(kp + j * 8 * PQ);
