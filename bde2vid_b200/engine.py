@@ -379,7 +379,7 @@ class Engine:
         """Fused path: raw events -> frames (voxeliser writes the padded grids the UNet reads)."""
         return self.forward_events_batch([(xs, ys, ts, ps, offsets)], H, W, crop, use_graph, slot, normalize, hot_mask)[0]
 
-    def forward_events_batch(self, seqs, H, W, crop, use_graph=True, slot=0, normalize=None, hot_mask=None):
+    def forward_events_batch(self, seqs, H, W, crop, use_graph=True, slot=0, normalize=None, hot_mask=None, pair=None):
         """B independent sequences (each a tuple xs, ys, ts, ps, offsets with the same number of windows)
         processed as one batch: every kernel of the schedule runs once for all B sequences.  Returns a list
         (per sequence) of T frames [1, 1, Hp, Wp].  Event arrays: loader format (four float32 arrays) or the on-disk
@@ -390,11 +390,46 @@ class Engine:
         if any(s[4].numel() - 1 != T for s in seqs):
             raise ValueError("sequences batched together must have the same number of windows")
         Hp, Wp = crop.height_crop_size, crop.width_crop_size
-        p = self.plan(T, B, Hp, Wp, slot)
+        p = self.plan(T, B, Hp, Wp, slot if pair is None else ("pair", pair.rank, slot))
+        p.pair = pair
         p.set_events(seqs, H, W, crop.padding_top, crop.padding_left, normalize, hot_mask)
-        p.run(use_graph, from_events=True)
+        p.run(use_graph and (pair is None or pair.graph), from_events=True)
         img = p.img.clone().view(T, B, 1, 1, Hp, Wp)
         return [list(img[:, b].unbind(0)) for b in range(B)]
+
+
+class PairSplit:
+    """Two GPUs share ONE sequence.  Time cannot be split (the bidirectional recurrence and the
+    in-place attention chain, ...V5.py:119-169), but per level the two recurrent chains are independent of each other:
+
+      * rank 0 of the pair runs the FORWARD chain of every level, rank 1 the BACKWARD chain;
+      * after the chains of a level the hidden-state sequences are exchanged (``hf`` from rank 0, ``hb`` from rank 1: one
+        NCCL broadcast each over NVLink, T x B x h x w x C bf16) and both ranks form ``ff + fb``;
+      * the attention chain of the level is sequential in t and needs every frame: both ranks run it, redundantly and
+        bit-identically (same kernels, same inputs);
+      * the decoder chunks (frames [c Tc, (c + 1) Tc)) alternate between the ranks; the frames meet in one all-reduce(sum)
+        over the image buffer whose foreign chunks are zero (x + 0 is exact), so both ranks return all T frames.
+
+    Head conv and the (merged) encoder convs are batched over all frames and cheap; both ranks run them.  ``graph``: capture
+    the schedule incl. the NCCL calls in a CUDA graph (off by default: eager launches)."""
+
+    def __init__(self, rank, group=None, src_ranks=(0, 1), graph=False):
+        assert rank in (0, 1)
+        self.rank, self.group, self.src_ranks, self.graph = rank, group, tuple(src_ranks), graph
+
+    def owns_direction(self, rev):
+        return self.rank == (1 if rev else 0)
+
+    def owns_chunk(self, chunk_index):
+        return chunk_index % 2 == self.rank
+
+    def broadcast(self, t, owner):
+        import torch.distributed as dist
+        dist.broadcast(t, src=self.src_ranks[owner], group=self.group)
+
+    def sum_frames(self, img):
+        import torch.distributed as dist
+        dist.all_reduce(img, op=dist.ReduceOp.SUM, group=self.group)
 
 
 class _Plan:
@@ -489,6 +524,7 @@ class _Plan:
             self.dec.append(dd)
         self.graphs = {}
         self.runs = {}
+        self.pair = None                # PairSplit: this plan runs its share of a sequence split over two GPUs
         self.ev = None
         self.ev_kind = None
         self.norm = (0, 0.0, 95.0)      # voxel normalisation of the fused events path: (mode, low_perc, top_perc)
@@ -643,8 +679,11 @@ class _Plan:
                 eng._gemm(e["fb_conv"], x, d["efb"], N, xh, xw, xc, act=eng.net_act)
                 self.launches += 1
             side.wait_stream(main)
+            pair = self.pair
             for (strm, key, conv, src, rev) in ((main, "f", e["f_conv"], d["ef"], False), (side, "b", e["b_conv"], d["eb"], True)):
-                with torch.cuda.stream(strm):
+                if pair is not None and eng.rec is not None and not pair.owns_direction(rev):
+                    continue                      # the other GPU of the pair runs this direction (PairSplit)
+                with torch.cuda.stream(main if pair is not None else strm):
                     if not merged:
                         # encoder conv is not recurrent: one launch over all T (...V5.py:129-130, conv part)
                         eng._gemm(conv, x, src, N, xh, xw, xc, act=eng.net_act)
@@ -661,6 +700,9 @@ class _Plan:
                             xin, pitch = src[t * B:(t + 1) * B], {}
                         self._chain_step(d, key, e, xin, pitch, hbuf, cbuf, t, tprev, k, rev)
             main.wait_stream(side)
+            if pair is not None and eng.rec is not None:
+                pair.broadcast(d["hf"], 0)
+                pair.broadcast(d["hb"], 1)
             # merged = ff + fb (...V5.py:137-147)
             ff, fb = (d["ef"], d["eb"]) if eng.rec is None else (d["hf"], d["hb"])
             ops.add(ff, fb, out_f32=d["feat"], out_t=None if eng.dtype == torch.float32 else d["feat_t"], dtype=eng.dtype)
@@ -675,6 +717,8 @@ class _Plan:
             x, xc, xh, xw = d["feat_t"], C, h, w
         if self.overlap:
             torch.cuda.current_stream().wait_stream(self.side)
+        if self.pair is not None:
+            self.pair.sum_frames(self.img)
 
     def _tail_level(self, l, on_frame_done):
         """Last level with depth 0 (...V5.py:77-80, 151-169, 261-282): per frame, in order, x = feats_buffer[0] (ParseLayer:
@@ -710,6 +754,9 @@ class _Plan:
         if (t + 1) % Tc != 0 and t != T - 1:
             return
         t0 = (t // Tc) * Tc
+        if self.pair is not None and not self.pair.owns_chunk(t // Tc):
+            self.img[t0 * self.B:(min(t0 + Tc, T)) * self.B].zero_()     # the other GPU's chunk: zero for the final all-reduce(sum)
+            return
         if not self.overlap:
             self._decode_chunk(t0)
             return

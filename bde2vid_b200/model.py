@@ -283,6 +283,24 @@ class BDE2VID(nn.Module):
         return [[crop.crop(f) for f in frames] for frames in out]
 
 
+    def reconstruct_events_pair(self, xs, ys, ts, ps, offsets, sensor_size, pair_rank, group=None, src_ranks=(0, 1),
+                                num_encoders=None, normalize=None, hot_mask=None, graph=False):
+        """ONE sequence split over TWO GPUs: both ranks of the pair (process group ``group``,
+        global ranks ``src_ranks``) call this with the same events; rank 0 runs the forward recurrent chains, rank 1 the
+        backward ones, the hidden states are exchanged per level over NCCL, decoder chunks alternate, and both ranks return
+        all T frames (bit-identical to ``reconstruct_events`` on one GPU).  See ``engine.PairSplit``."""
+        from .croper import Croper
+        from .engine import PairSplit
+        H, W = sensor_size
+        crop = Croper(self.generator.num_encoders if num_encoders is None else num_encoders)
+        crop.update_params(W, H)
+        eng = self.generator.engine()
+        split = PairSplit(pair_rank, group, src_ranks, graph)
+        out = eng.forward_events_batch([(xs, ys, ts, ps, offsets)], H, W, crop, use_graph=self.generator.use_cuda_graph,
+                                       normalize=normalize, hot_mask=hot_mask, pair=split)
+        return [crop.crop(f) for f in out[0]]
+
+
 def load_checkpoint(path_or_dict, device="cuda"):
     """Reference loading path (eval_models_seq.py:41-60,:86) for mmengine-style checkpoints."""
     from .registry import Config

@@ -227,8 +227,8 @@ def main():
     ap.add_argument("--ref-windows", type=int, default=6, help="windows of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--full-cpu", action="store_true", help="CPU arm / cpu_baseline on SURVEY's C1: 240x180, T=100, whole sequence")
-    ap.add_argument("--config", default="default", choices=["default", "e2vid16", "gen4", "shard64"],
-                    help="default = BASELINE.json configs[1] (the headline); e2vid16 = configs[2]; shard64 = configs[3]; gen4 = configs[4]")
+    ap.add_argument("--config", default="default", choices=["default", "e2vid16", "gen4", "shard64", "pair"],
+                    help="default = BASELINE.json configs[1] (the headline); e2vid16 = configs[2]; shard64 = configs[3]; gen4 = configs[4]; pair = one sequence split over two GPUs (SURVEY 8 f4)")
     ap.add_argument("--no-single", action="store_true", help="skip the extra one-sequence-in-flight measurement")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--concurrent", type=int, default=2, help="CUDA streams (independent model calls in flight) per GPU")

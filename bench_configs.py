@@ -265,3 +265,68 @@ def run_shard64(args, rank, world, dev):
                  plan.launches * ((len(mine) + NB - 1) // NB) * args.steps, clocks,
                  {"cpu_baseline": None, "metric_means": result.get("means"), "precision": args.precision,
                   "tflops_algorithmic": fps / world * 163.34 / 1e3})
+
+
+def run_pair(args, rank, world, dev):
+    """ONE 346x260 sequence on ONE GPU vs split over a PAIR of GPUs (engine.PairSplit).  Needs 2 ranks.
+    value = frames/s of the pair-split sequence; the single-GPU rate of the same sequence (every rank measures its own) is in
+    `single_gpu`.  Strong scaling of one sequence's latency -- the only case the sequence-sharded path cannot speed up."""
+    import bench
+    from bde2vid_b200.model import MODELS
+    assert world == 2, "--config pair needs exactly two ranks (torchrun --nproc-per-node 2)"
+    barrier, timed = _common(dev, world)
+    Hh, Ww, N, T = 260, 346, 31500, args.windows
+    model = MODELS.build(bench.cfg_dict())
+    model.load_state_dict(synth.init_state_dict(bench.cfg_dict()["generator"], 0), strict=True)
+    model = model.eval().to(dev)
+    model.generator.precision = args.precision
+    ev = synth.gen_events(0, T, Hh, Ww, N)
+    seq = [torch.from_numpy(a).to(dev) for a in synth.to_loader_format_seq(ev)]
+    out = {}
+
+    def single(i):
+        out["single"] = model.reconstruct_events(*seq, (Hh, Ww))
+
+    def pair_eager(i):
+        out["pair"] = model.reconstruct_events_pair(*seq, (Hh, Ww), pair_rank=rank, graph=False)
+
+    def pair_graph(i):
+        out["pair_graph"] = model.reconstruct_events_pair(*seq, (Hh, Ww), pair_rank=rank, graph=True)
+
+    res = {}
+    warm = max(3, args.warmup)
+    with torch.no_grad():
+        sampler = bench.ClockSampler(dev.index or 0)
+        for name, fn in (("single", single), ("pair", pair_eager), ("pair_graph", pair_graph)):
+            try:
+                for i in range(warm):
+                    fn(i)
+                if name == "pair":
+                    sampler.start()
+                res[name] = timed(fn, args.steps)
+                if name == "pair":
+                    clocks = sampler.stop()
+            except Exception as e:          # graph capture of the NCCL calls is the one thing that may be refused
+                if name != "pair_graph":
+                    raise
+                res[name] = None
+                out["pair_graph_error"] = repr(e)[:200]
+    same = bool(torch.equal(torch.cat(out["single"], 0), torch.cat(out["pair"], 0)))
+    fps = {k: (None if v is None else args.steps * T / (v * 1e-3)) for k, v in res.items()}
+    best = max(v for k, v in fps.items() if k != "single" and v is not None)
+    eng = model.generator.engine()
+    plan = [q for k, q in eng.plans.items() if isinstance(k[4], tuple)][0]
+    exch = sum(2 * d["hf"].numel() * 2 for d in plan.lv if "hf" in d) + plan.img.numel() * 4
+    return _line("reconstructed frames/s (346x260, 5-bin), ONE sequence split over two GPUs", best, "frames/s", world, args.steps, warm,
+                 min(v for k, v in res.items() if k != "single" and v is not None), "strong",
+                 "bf16" if args.precision.startswith("bf16") else "f32",
+                 {"workload": "SURVEY 8(f4): one 346x260 sequence, T=%d x %d events; rank 0 runs the forward recurrent chains, rank 1 the "
+                              "backward ones, hidden states exchanged per level (NCCL broadcast), attention on both, decoder chunks "
+                              "alternate, frames by one all-reduce" % (T, N),
+                  "l2_policy": "no flush: one sequence streams >2 GB of activations"},
+                 {"value": best, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                  "note": "events resident; this config measures the device-side latency of one sequence"},
+                 plan.launches * args.steps, clocks,
+                 {"cpu_baseline": None, "precision": args.precision, "single_gpu": fps["single"], "pair_eager": fps["pair"],
+                  "pair_cuda_graph": fps["pair_graph"], "pair_graph_error": out.get("pair_graph_error"),
+                  "bit_identical_to_single_gpu": same, "nccl_bytes_per_sequence": exch})

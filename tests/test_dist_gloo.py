@@ -67,3 +67,50 @@ def test_two_rank_headless_driver_sharding_and_gather():
     n = [2, 3, 4, 5, 6]
     want = sum(0.1 * i * n[i] for i in range(5)) / sum(n)
     assert abs(o0["mse"] - want) < 1e-12 and abs(o1["mse"] - want) < 1e-12 and abs(o0["ssim"] - 0.5) < 1e-12
+
+
+def _pair_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bde2vid_b200.engine import PairSplit
+    pair = PairSplit(rank)
+    T, Tc = 19, 8
+    # stand-ins for the per-level hidden-state sequences: every rank computes only its own direction
+    hf = torch.full((T, 4), float("nan"))
+    hb = torch.full((T, 4), float("nan"))
+    if pair.owns_direction(False):
+        hf = torch.arange(T * 4, dtype=torch.float32).view(T, 4)
+    if pair.owns_direction(True):
+        hb = -torch.arange(T * 4, dtype=torch.float32).view(T, 4) * 0.5
+    pair.broadcast(hf, 0)
+    pair.broadcast(hb, 1)
+    # decoder chunks alternate; foreign chunks are zero, the frames meet in one all-reduce(sum)
+    img = torch.full((T, 3), float("nan"))
+    owned = []
+    for c in range((T + Tc - 1) // Tc):
+        sl = slice(c * Tc, min((c + 1) * Tc, T))
+        if pair.owns_chunk(c):
+            img[sl] = (hf + hb)[sl, :3] + 100.0
+            owned.append(c)
+        else:
+            img[sl] = 0.0
+    pair.sum_frames(img)
+    ret[rank] = (owned, hf.clone(), hb.clone(), img.clone())
+    dist.destroy_process_group()
+
+
+def test_pair_split_schedule_and_exchange():
+    """engine.PairSplit: rank 0 = forward chains, rank 1 = backward chains, decoder chunks alternate,
+    hidden states by broadcast, frames by one all-reduce: both ranks end with identical, complete data."""
+    world, port = 2, 29545
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_pair_worker, args=(world, port, ret), nprocs=world, join=True)
+    (o0, hf0, hb0, i0), (o1, hf1, hb1, i1) = ret[0], ret[1]
+    assert sorted(o0 + o1) == [0, 1, 2] and not set(o0) & set(o1) and o0 and o1
+    T = 19
+    hf = torch.arange(T * 4, dtype=torch.float32).view(T, 4)
+    hb = -hf * 0.5
+    assert torch.equal(hf0, hf) and torch.equal(hf1, hf) and torch.equal(hb0, hb) and torch.equal(hb1, hb)
+    want = (hf + hb)[:, :3] + 100.0
+    assert torch.equal(i0, want) and torch.equal(i1, want)
