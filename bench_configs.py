@@ -297,7 +297,13 @@ def run_pair(args, rank, world, dev):
     warm = max(3, args.warmup)
     with torch.no_grad():
         sampler = bench.ClockSampler(dev.index or 0)
-        for name, fn in (("single", single), ("pair", pair_eager), ("pair_graph", pair_graph)):
+        # the CUDA-graph form (NCCL calls captured) is opt-in: it measured 1736 vs 1706 frames/s eager, but tearing the process
+        # group down while the captured graph is alive hung torch.distributed (profiles/r02_bench_pair_2gpu.json)
+        variants = [("single", single), ("pair", pair_eager)]
+        if os.environ.get("BDE2VID_PAIR_GRAPH", "0") == "1":
+            variants.append(("pair_graph", pair_graph))
+        res["pair_graph"] = None
+        for name, fn in variants:
             try:
                 for i in range(warm):
                     fn(i)
