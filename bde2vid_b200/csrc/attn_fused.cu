@@ -17,7 +17,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 // Ablation builds for tools/attn64_probe.sh (timing only, results are wrong): bit 0 = no bias-table loads, bit 1 = no MUFU.EX2
-// in the probabilities, 4 = skip the level-1 attention core altogether.  0 in every shipped build.
+// in the probabilities, 4 = skip the level-1 attention core altogether, 8 = no global gather (LayerNorm of zeros), 16 = no q/k/v
+// projection MMAs, 32 = no output projection + scatter.  0 in every shipped build.
 #ifndef BDE_ATTN_PROBE
 #define BDE_ATTN_PROBE 0
 #endif
@@ -269,6 +270,9 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
           for (int q = 1; q < 8; ++q) fr = (d == q) ? p.frames[q] : fr;
           if (fr != nullptr && pix >= 0) src = fr + (size_t)pix * C + j * 8;
         }
+#if BDE_ATTN_PROBE & 8
+        src = nullptr;
+#endif
 #pragma unroll
         for (int kb = 0; kb < NCH; ++kb) {
           if (src != nullptr) {
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
     cpa_wait<0>();
     __syncthreads();
   }
-  for (int which = 0; which < 3; ++which) {
+  for (int which = 0; which < ((BDE_ATTN_PROBE & 16) ? 0 : 3); ++which) {
     if (NW != 3) {
       // slices were committed in order: wait until slice `which` has landed
       if (which == 2) cpa_wait<0>(); else cpa_wait<1>();
@@ -434,7 +438,7 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
     constexpr int SEG = ((NT + 2) / 3) & ~1;                      // even segment size: 19 -> 6, 13 -> 4, 7 -> 2
     constexpr int LAST = NT - 2 * SEG;                            // 7 / 5 / 3
     constexpr int kMaxT = LAST > SEG ? LAST : SEG;
-    for (int pi = warp; pi < (BDE_ATTN_PROBE == 4 ? 0 : NPAIRS); pi += kThreadsF / 32) {
+    for (int pi = warp; pi < ((BDE_ATTN_PROBE & 4) ? 0 : NPAIRS); pi += kThreadsF / 32) {
       const int hp = pi / MTN, mt = pi - hp * MTN;                // heads hp and hp + 8
       const int row0 = mt * 16 + g, row1 = row0 + 8;
       const uint32_t r0a = tbl_u32 + (uint32_t)(hp * TLD * 4 + roff[row0]);
@@ -705,7 +709,7 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
   }
 
   if (dbg) { const long long c = clock64(); t_attn = c - t_mark; t_mark = c; }
-  if (C == 64) {
+  if (C == 64 && !(BDE_ATTN_PROBE & 32)) {
     // ---- output projection + window_reverse + shortcut: x[pix] += proj(o) + b (DTransformer.py:204,294-299) ----
     // shortcut = the query frame (DTransformer.py:294-299; xs itself when the block runs in place): this thread's eight
     // float2 values are fetched BEFORE the projection GEMM -- inside the store loop every load waited behind the previous
