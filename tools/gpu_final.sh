@@ -13,6 +13,7 @@ for c in e2vid16 gen4 shard64; do
   timeout 900 python bench.py --config $c > $O/bench_$c.json 2> $O/bench_$c.err; echo "bench $c exit $?"
 done
 timeout 300 python tools/voxel_probe.py > $O/voxel_probe.log 2>&1; echo "voxel probe exit $?"
+timeout 300 python tools/attn_phase_probe.py > $O/attn_phase_probe.log 2>&1; echo "attn phase probe exit $?"
 timeout 300 python tools/mlp_probe.py > $O/mlp_probe.log 2>&1; echo "mlp probe exit $?"
 timeout 300 python tools/attn_tc256_probe.py > $O/attn_tc256_probe.log 2>&1; echo "tc256 probe exit $?"
 fi
