@@ -33,12 +33,13 @@ VOXEL_BYTES_PER_WINDOW = 16 * NEV + 4 * BINS * H * W
 # dram__bytes_read.sum + dram__bytes_write.sum of the voxeliser (memset + reduction kernels) from the committed ncu capture;
 # filled in from profiles/ once measured (None = not captured for this build)
 VOXEL_TRAFFIC = {
-    # profiles/r02_ncu_voxel_traffic.csv (ncu --cache-control none over one 100-window call at 346x260): the four reduction
-    # kernels read 50.1 MB from DRAM (= the events, 16 B x 3.15 M: the memset grids are still L2-resident, nothing is
-    # re-read) and the 264x352 grids (185.9 MB) are written back once
-    "bytes_per_100_windows": 50.1e6 + 185.9e6,
-    "source": "ncu --cache-control none, dram__bytes_read.sum of the 4 reduction kernels (50.1 MB = events) + one write-back of the "
-              "padded grids (185.9 MB); profiles/r02_ncu_voxel_traffic.csv",
+    # profiles/r02_ncu_voxel_traffic.csv (ncu --cache-control none over one 100-window call at 346x260, launches 6-11): the six
+    # chained reduction kernels (each also zeroes the next chunk's grids) read 50.4 MB from DRAM (= the events, 16 B x 3.15 M:
+    # the zeroed grids are still L2-resident, nothing is re-read); 143.6 MB of the 264x352 grids are written back while the
+    # kernels run, the rest of the 185.9 MB after the last one -- every grid line goes to HBM once
+    "bytes_per_100_windows": 50.4e6 + 185.9e6,
+    "source": "ncu --cache-control none, dram__bytes_read.sum of the 6 chained reduction kernels of one call (50.4 MB = events) + one "
+              "write-back of the padded grids (185.9 MB, of which 143.6 MB inside the kernels); profiles/r02_ncu_voxel_traffic.csv",
 }
 
 
