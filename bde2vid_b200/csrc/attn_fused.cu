@@ -128,8 +128,13 @@ __device__ __forceinline__ uint32_t ex2_h2(float lo, float hi) {
   return pack2_h(a, b);
 }
 
-template <int C, int HD, int NT>
+// kPers (C == 64 only): ONE 512-thread CTA per SM; its two 256-thread halves walk the windows independently (named barriers)
+// on private token / q / k / v / output tiles, while the q|k|v weight slices, the bias table and the projection weights
+// are loaded ONCE per CTA into a region both halves share (the one-window form reloads those 65 KB for every window and
+// overlays the table on the token region to stay under half an SM's shared memory).
+template <int C, int HD, int NT, bool kPers = false>
 struct FusedCfg {
+  static_assert(!kPers || C == 64, "the persistent form exists for C == 64 only");
   static constexpr int HG = 64 / HD;              // heads per CTA
   static constexpr int PX = C + 8;                // pitch (bf16 elements) of the LayerNorm'ed tokens and weight slices
   static constexpr int PQ = 72;                   // pitch of q / k / v / o tiles
@@ -143,23 +148,28 @@ struct FusedCfg {
   static constexpr int TBL_BYTES = HG * DMAX * kRel * 4;
   static constexpr int OS_BYTES = 64 * PQ * 2;
   static constexpr int WP_BYTES = C == 64 ? 64 * PX * 2 : 0;
-  // C == 64: the bias table, the attention-output tile and the projection weights reuse the token / weight
-  // region once the q, k, v projections are done (keeps the CTA under half an SM's shared memory)
-  static constexpr int A_BYTES = C == 64 ? (XN_BYTES + W_BYTES > TBL_BYTES + OS_BYTES + WP_BYTES ? XN_BYTES + W_BYTES
+  // C == 64, one window per CTA: the bias table, the attention-output tile and the projection weights reuse the token /
+  // weight region once the q, k, v projections are done (keeps the CTA under half an SM's shared memory)
+  static constexpr int A_BYTES = kPers ? (XN_BYTES > OS_BYTES ? XN_BYTES : OS_BYTES)
+                                 : C == 64 ? (XN_BYTES + W_BYTES > TBL_BYTES + OS_BYTES + WP_BYTES ? XN_BYTES + W_BYTES
                                                                                                   : TBL_BYTES + OS_BYTES + WP_BYTES)
-                                         : XN_BYTES + W_BYTES + TBL_BYTES;
+                                           : XN_BYTES + W_BYTES + TBL_BYTES;
+  // regions relative to the SHARED base (kPers: start of shared memory, common to both halves)
+  static constexpr int OFF_W = kPers ? 0 : XN_BYTES;
+  static constexpr int OFF_TBL = kPers ? W_BYTES : (C == 64 ? 0 : XN_BYTES + W_BYTES);
+  static constexpr int OFF_WP = kPers ? W_BYTES + TBL_BYTES : TBL_BYTES + OS_BYTES;    // C == 64 only
+  static constexpr int SHARED_BYTES = kPers ? W_BYTES + TBL_BYTES + WP_BYTES : 0;
+  // regions relative to the HALF base (kPers: SHARED_BYTES + half * HALF_BYTES; otherwise the start of shared memory)
   static constexpr int OFF_XN = 0;
-  static constexpr int OFF_W = XN_BYTES;
-  static constexpr int OFF_TBL = C == 64 ? 0 : XN_BYTES + W_BYTES;
-  static constexpr int OFF_OS = TBL_BYTES;               // C == 64 only
-  static constexpr int OFF_WP = TBL_BYTES + OS_BYTES;    // C == 64 only
+  static constexpr int OFF_OS = kPers ? 0 : TBL_BYTES;      // C == 64 only; kPers: over the (dead) token tile
   static constexpr int OFF_Q = A_BYTES;
   static constexpr int OFF_K = OFF_Q + 64 * PQ * 2;
   static constexpr int OFF_V = OFF_K + NKEY * PQ * 2;
   static constexpr int OFF_COFF = OFF_V + XROWS * PQ * 2;   // int32 [NKEY]  byte offsets into a bias-table row block
   static constexpr int OFF_ROFF = OFF_COFF + NKEY * 4;      // int32 [64]
   static constexpr int OFF_PIX = OFF_ROFF + 256;            // int32 [64]
-  static constexpr int SMEM = OFF_PIX + 256;
+  static constexpr int HALF_BYTES = OFF_PIX + 256;
+  static constexpr int SMEM = kPers ? SHARED_BYTES + 2 * HALF_BYTES : HALF_BYTES;
 };
 
 // acc[mt][nt][4] += A[rows, C] (smem, pitch PX) * Wslice[64, C]^T (smem, pitch PX) for this warp's
@@ -190,29 +200,40 @@ __device__ __forceinline__ void warp_gemm(float (&acc)[MT][2][4], int n_mt, uint
   }
 }
 
-template <int C, int HD, int NT>
-__global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(const FusedAttnParams p) {
-  using Cfg = FusedCfg<C, HD, NT>;
+template <int C, int HD, int NT, bool kPers = false>
+__global__ void __launch_bounds__(kPers ? 2 * kThreadsF : kThreadsF, (C == 64 && !kPers) ? 2 : 1) attn_fused_kernel(const FusedAttnParams p) {
+  using Cfg = FusedCfg<C, HD, NT, kPers>;
   constexpr int PX = Cfg::PX, PQ = Cfg::PQ, HG = Cfg::HG, KSTEPS = Cfg::KSTEPS, XROWS = Cfg::XROWS, NKEY = Cfg::NKEY;
   constexpr int NW = Cfg::NW;
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem);
-  __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_XN);
+  // kPers: `half` = which 256-thread half of the CTA; tid / warp are relative to the half, smem_h / sb_h its private tiles
+  const int half = kPers ? (int)(threadIdx.x >> 8) : 0;
+  uint8_t* smem_h = smem + (kPers ? Cfg::SHARED_BYTES + half * Cfg::HALF_BYTES : 0);
+  const uint32_t sb_h = sb + (uint32_t)(kPers ? Cfg::SHARED_BYTES + half * Cfg::HALF_BYTES : 0);
+  __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(smem_h + Cfg::OFF_XN);
   float* tbl_s = reinterpret_cast<float*>(smem + Cfg::OFF_TBL);
-  __nv_bfloat16* qs = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_Q);
-  __nv_bfloat16* ks = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_K);
-  __nv_bfloat16* vs = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_V);
-  int* coff = reinterpret_cast<int*>(smem + Cfg::OFF_COFF);
-  int* roff = reinterpret_cast<int*>(smem + Cfg::OFF_ROFF);
-  int* pix_s = reinterpret_cast<int*>(smem + Cfg::OFF_PIX);
+  __nv_bfloat16* qs = reinterpret_cast<__nv_bfloat16*>(smem_h + Cfg::OFF_Q);
+  __nv_bfloat16* ks = reinterpret_cast<__nv_bfloat16*>(smem_h + Cfg::OFF_K);
+  __nv_bfloat16* vs = reinterpret_cast<__nv_bfloat16*>(smem_h + Cfg::OFF_V);
+  int* coff = reinterpret_cast<int*>(smem_h + Cfg::OFF_COFF);
+  int* roff = reinterpret_cast<int*>(smem_h + Cfg::OFF_ROFF);
+  int* pix_s = reinterpret_cast<int*>(smem_h + Cfg::OFF_PIX);
+  // barrier over the threads that share the tiles: the whole CTA, or (kPers) the 256 threads of this half
+  auto sync_tiles = [&]() {
+    if (kPers) asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
+    else __syncthreads();
+  };
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = kPers ? (int)(threadIdx.x & 255) : (int)threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const bool dbg = p.dbg != nullptr;
   const long long t_begin = dbg ? clock64() : 0;
   long long t_mark = t_begin, t_ln = 0, t_qkv = 0, t_tbl = 0, t_attn = 0;
   constexpr int NHG = C / 64;
-  const int w = blockIdx.x / NHG, hg = blockIdx.x - w * NHG;
+  const int hg = kPers ? 0 : (int)(blockIdx.x % NHG);
+  int w = kPers ? (int)blockIdx.x * 2 + half : (int)(blockIdx.x / NHG);
+  const int w_step = kPers ? (int)gridDim.x * 2 : 0;
   const int n_kv = p.D * kTok;
   const int tbl_ld = p.D * kRel;
 
@@ -228,7 +249,20 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
     cpa_commit();
   };
 #pragma unroll
-  for (int i = 0; i < NW; ++i) load_w_slice(i, i);
+  for (int i = 0; i < NW; ++i) {
+    if (!kPers || i % 2 == half) load_w_slice(i, i);   // kPers: the halves share the loading (each thread waits for its own groups)
+  }
+  if (kPers) {
+    // bias table + projection weights, once per CTA (static data: before pdl_wait)
+    const float* src = p.tbl;
+    const int n16 = HG * tbl_ld / 4;
+    for (int i = (int)threadIdx.x; i < n16; i += 2 * kThreadsF) cpa16(sb + Cfg::OFF_TBL + (uint32_t)(i * 16), src + i * 4);
+    for (int i = (int)threadIdx.x; i < 64 * (C / 8); i += 2 * kThreadsF) {
+      const int r = i / (C / 8), ch = i - r * (C / 8);
+      cpa16(sb + Cfg::OFF_WP + (uint32_t)((r * PX + ch * 8) * 2), p.wproj + (size_t)r * C + ch * 8);
+    }
+    cpa_commit();
+  }
 
   // ---- index tables -----------------------------------------------------------------------------------
   for (int n = tid; n < NKEY; n += kThreadsF) {
@@ -242,10 +276,18 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
   if (tid < 64) {
     const int a = tid / 7, b = tid - a * 7;
     roff[tid] = tid < kTok ? (a * 13 + b) * 4 : 0;
-    pix_s[tid] = tid < kTok ? __ldg(p.tok_map + (size_t)w * kTok + tid) : -1;
   }
-  __syncthreads();
-  pdl_wait();   // everything above is static data; the frames below were written by the previous kernel of the chain
+  if (kPers) {
+    cpa_wait<0>();
+    __syncthreads();   // weights, bias table and projection weights of BOTH halves' copies are in place
+  }
+  bool first_window = true;
+  if (kPers && w >= p.n_win) return;   // (an odd window count leaves the last half without work)
+  do {   // window loop; one window per CTA: a single pass
+  if (tid < 64) pix_s[tid] = tid < kTok ? __ldg(p.tok_map + (size_t)w * kTok + tid) : -1;
+  sync_tiles();
+  if (first_window) pdl_wait();   // everything above is static data; the frames below were written by the previous kernel of the chain
+  first_window = false;
 
   // ---- gather + LayerNorm: 8 lanes per token, 4 tokens per warp pass ----------------------------------
   // The loads of NB passes are issued together (independent global reads in flight) before any of them is reduced.
@@ -328,17 +370,17 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
   if (dbg) { const long long c = clock64(); t_ln = c - t_mark; t_mark = c; }
   // ---- q, k, v projections (mma.sync): warp = (n-tile pair, m half) --------------------------------------
   const int npair = warp & 3, mh = warp >> 2;
-  const uint32_t xn_u32 = sb + Cfg::OFF_XN;
+  const uint32_t xn_u32 = sb_h + Cfg::OFF_XN;
   constexpr int MTK = (KSTEPS + 1) / 2;  // k / v m-tiles per warp
   if (NW == 3) {  // all three weight slices were loaded up front: one barrier covers them and the LayerNorm'ed tokens
-    cpa_wait<0>();
-    __syncthreads();
+    if (!kPers) cpa_wait<0>();
+    sync_tiles();
   }
   for (int which = 0; which < ((BDE_ATTN_PROBE & 16) ? 0 : 3); ++which) {
     if (NW != 3) {
       // slices were committed in order: wait until slice `which` has landed
       if (which == 2) cpa_wait<0>(); else cpa_wait<1>();
-      __syncthreads();  // slice + (first pass) the LayerNorm'ed tokens visible to every warp
+      sync_tiles();  // slice + (first pass) the LayerNorm'ed tokens visible to every warp
     }
     const uint32_t w_base = sb + Cfg::OFF_W + (uint32_t)((which % NW) * 64 * PX * 2);
     const float* bsrc = p.bqkv + which * C + hg * 64 + npair * 16 + 2 * t;
@@ -386,15 +428,15 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
       }
     }
     if (which + NW < 3) {
-      __syncthreads();  // every warp is done reading buffer which % NW
+      sync_tiles();  // every warp is done reading buffer which % NW
       load_w_slice(which + NW, which % NW);
     }
   }
-  __syncthreads();  // q, k, v complete; the token / weight region is free
+  sync_tiles();  // q, k, v complete; the token / weight region is free
   if (dbg) { const long long c = clock64(); t_qkv = c - t_mark; t_mark = c; }
 
   // ---- bias table (+ projection weights) -> smem ------------------------------------------------------------
-  {
+  if (!kPers) {
     const float* src = p.tbl + (size_t)hg * HG * tbl_ld;
     const int n16 = HG * tbl_ld / 4;  // 16-byte chunks (HG * D * 169 floats; multiple of 4 because HG is)
     for (int i = tid; i < n16; i += kThreadsF) cpa16(sb + Cfg::OFF_TBL + (uint32_t)(i * 16), src + i * 4);
@@ -406,7 +448,7 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
     }
     cpa_commit();
     cpa_wait<0>();
-    __syncthreads();
+    sync_tiles();
   }
 
   if (dbg) { const long long c = clock64(); t_tbl = c - t_mark; t_mark = c; }
@@ -414,10 +456,10 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
   // head_dim 4: the 49th query row would cost a whole tile per head, so the normal units cover rows 0..47 and one
   // "special" unit packs row 48 of all 16 heads into a single tile (tile row = head; the query fragment carries only
   // that head's 4 channels, the key fragment all 64, so each row still sees its own head's dot product).
-  const uint32_t vs_u32 = sb + Cfg::OFF_V;
+  const uint32_t vs_u32 = sb_h + Cfg::OFF_V;
   const uint32_t tbl_u32 = sb + Cfg::OFF_TBL;
-  const uint32_t coff_u32 = sb + Cfg::OFF_COFF;
-  __nv_bfloat16* os = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::OFF_OS);  // C == 64 only
+  const uint32_t coff_u32 = sb_h + Cfg::OFF_COFF;
+  __nv_bfloat16* os = reinterpret_cast<__nv_bfloat16*>(smem_h + Cfg::OFF_OS);  // C == 64 only
   constexpr int MTN = HD == 4 ? 3 : 4;                 // query tiles per head handled by normal units
   constexpr int NUNITS = HG * MTN;
   constexpr uint32_t kOnes = 0x3C003C00u;              // fp16x2 (1, 1)
@@ -727,9 +769,9 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
           sc[i][hrow][n] = pix >= 0 ? *(reinterpret_cast<const float2*>(shortcut + (size_t)pix * C + npair * 16 + n * 8 + 2 * t))
                                     : make_float2(0.f, 0.f);
       }
-    __syncthreads();
+    sync_tiles();
     float acc[2][2][4];
-    warp_gemm<C, PQ, 2>(acc, 2, sb + Cfg::OFF_OS, [&](int i, int r) { return (mh * 2 + i) * 16 + r; }, sb + Cfg::OFF_WP, npair, lane);
+    warp_gemm<C, PQ, 2>(acc, 2, sb_h + Cfg::OFF_OS, [&](int i, int r) { return (mh * 2 + i) * 16 + r; }, sb + Cfg::OFF_WP, npair, lane);
     // note: os has pitch PQ == PX for C == 64, so the same routine serves both operands
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -751,7 +793,9 @@ __global__ void __launch_bounds__(kThreadsF, C == 64 ? 2 : 1) attn_fused_kernel(
       }
     }
   }
-  if (dbg && tid == 0) {
+  if (kPers) sync_tiles();   // the next window overwrites pix_s and the token tile that the projection above reads
+  } while (kPers && (w += w_step) < p.n_win);
+  if (dbg && tid == 0 && !kPers) {
     long long* o = p.dbg + (size_t)blockIdx.x * 8;
     const long long c = clock64();
     o[0] = c - t_begin; o[1] = t_ln; o[2] = 0; o[3] = t_qkv; o[4] = t_tbl; o[5] = t_attn; o[6] = c - t_mark;
@@ -772,6 +816,24 @@ int launch_fused(const FusedAttnParams& p, cudaStream_t s) {
   const cudaError_t le = launch_pdl(kern, (unsigned)(p.n_win * (C / 64)), (unsigned)kThreadsF, (size_t)Cfg::SMEM, s, 1, q);
   BDE_REQUIRE(le == cudaSuccess, "bde_window_attention_fused: launch: %s", cudaGetErrorString(le));
   return check_launch("attn_fused_kernel");
+}
+
+// C == 64, persistent form: one 512-thread CTA per SM, two halves walking the windows (see FusedCfg<.., kPers = true>)
+template <int NT>
+int launch_fused_pers(const FusedAttnParams& p, cudaStream_t s) {
+  using Cfg = FusedCfg<64, 4, NT, true>;
+  auto kern = attn_fused_kernel<64, 4, NT, true>;
+  if (first_use_on_device((const void*)kern)) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    BDE_REQUIRE(e == cudaSuccess, "bde_window_attention_fused: smem attribute (%d bytes): %s", Cfg::SMEM, cudaGetErrorString(e));
+  }
+  FusedAttnParams q = p;
+  q.dbg = nullptr;
+  const int n_sm = device_sm_count();
+  const int ctas = (p.n_win + 1) / 2 < n_sm ? (p.n_win + 1) / 2 : n_sm;
+  const cudaError_t le = launch_pdl(kern, (unsigned)ctas, (unsigned)(2 * kThreadsF), (size_t)Cfg::SMEM, s, 1, q);
+  BDE_REQUIRE(le == cudaSuccess, "bde_window_attention_fused: launch (persistent): %s", cudaGetErrorString(le));
+  return check_launch("attn_fused_kernel (persistent)");
 }
 
 
@@ -1279,7 +1341,22 @@ extern "C" int bde_window_attention_fused(const float* const* frames_host, int D
     case 2: return launch_fused<C_, HD_, 13>(p, s);              \
     default: return launch_fused<C_, HD_, 19>(p, s);             \
   }
-  if (c == 64) { BDE_FUSED(64, 4) }
+  if (c == 64) {
+    // BDE2VID_ATTN64_PERSIST=1 selects the persistent form (weights / bias table resident per SM, two halves walking the
+    // windows).  Measured on B200 (tools/attn64_probe.py, us per launch, one CTA per window vs persistent): 494 windows
+    // 49.7 vs 48.3, 1976 windows 158.3 vs 158.3, 3952 windows 310.4 vs 327.7 -- the 65 KB of per-window weight / table
+    // reloads were already hidden by the second co-resident CTA, and the hardware's dynamic CTA scheduling balances the
+    // windows better than the static round-robin of the persistent form; hence off by default.
+    const char* e = getenv("BDE2VID_ATTN64_PERSIST");
+    if (e != nullptr && e[0] == '1' && n_win >= 2) {
+      switch (D) {
+        case 1: return launch_fused_pers<7>(p, s);
+        case 2: return launch_fused_pers<13>(p, s);
+        default: return launch_fused_pers<19>(p, s);
+      }
+    }
+    BDE_FUSED(64, 4)
+  }
   if (with_proj) {   // c == 256 with the projection fused: whole-window kernel
     // default: projections on tcgen05 (attn_tc256.cu); BDE2VID_ATTN_TC256=0 selects the mma.sync form below
     const char* e = getenv("BDE2VID_ATTN_TC256");

@@ -381,3 +381,79 @@ def test_window_attention_whole_window_kernel_c256(dilated, zero_frame):
         err2 = float((xs2 - ref).abs().max())
         print("win256 kvpre", dilated, zero_frame, err2)
         assert err2 <= 1.5e-2 * max(1.0, upd)
+
+
+@pytest.mark.parametrize("dilated,zero_frame,D,q_ind", [(False, None, 3, 1), (True, 2, 3, 1), (False, 0, 3, 1), (True, None, 2, 0),
+                                                        (False, None, 1, 0)])
+def test_window_attention_fused_c64_vs_fp32_torch(dilated, zero_frame, D, q_ind):
+    """C = 64, 16 heads of 4 channels (level 1): attn_fused_kernel<64, 4, NT> -- gather + LayerNorm + q/k/v + softmax(q k^T +
+    bias) v + projection + scatter in ONE launch -- against an fp32 torch restatement of DTransformer.py:183-207, 294-299.
+    Both launch forms: one CTA per window (default) and the persistent form (BDE2VID_ATTN64_PERSIST=1: two 256-thread halves
+    per SM walking the windows, an odd window count); the two must agree BIT FOR BIT (same arithmetic per window)."""
+    import os
+    from bde2vid_b200 import ops
+    from bde2vid_b200.engine import window_token_map
+    g = torch.Generator().manual_seed(11 + int(dilated) + D)
+    B, h, w, C, heads = 3, 33, 45, 64, 16
+    P = B * h * w
+    tm, _ = window_token_map(B, h, w, (7, 7), dilated, DEV)
+    nwin = tm.shape[0]
+    assert nwin % 2 == 1 and nwin > 100          # odd: the last half of the persistent form has one window less
+    frames = [(torch.randn(P, C, generator=g) * 1.5 + 0.2).to(DEV) for _ in range(D)]
+    if zero_frame is not None:
+        frames[zero_frame] = None
+    hd = C // heads
+    wq_f = torch.randn(3 * C, C, generator=g) / C ** 0.5
+    wq_f[:C] *= hd ** -0.5
+    wqkv = wq_f.to(torch.bfloat16).to(DEV)
+    bqkv = (torch.randn(3 * C, generator=g) * 0.1).to(DEV)
+    tbl = (torch.randn(heads, D, 169, generator=g) * 0.5).to(DEV)
+    wproj = (torch.randn(C, C, generator=g) / C ** 0.5).to(torch.bfloat16).to(DEV)
+    bproj = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    xs0 = frames[q_ind].clone()
+    idx = tm.view(nwin, 49).long()
+    keep = idx >= 0
+
+    def win_tokens(fr):
+        if fr is None:
+            return torch.zeros(nwin, 49, C, device=DEV)
+        return fr[idx.clamp(min=0)] * keep.unsqueeze(-1)
+
+    fr_list = [xs0 if d == q_ind else frames[d] for d in range(D)]
+    xhat = torch.cat([F.layer_norm(win_tokens(f), (C,), eps=1e-5) for f in fr_list], 1)
+    qkv_ref = xhat @ wqkv.float().t() + bqkv
+    q = qkv_ref[:, q_ind * 49:(q_ind + 1) * 49, :C].reshape(nwin, 49, heads, hd).permute(0, 2, 1, 3)
+    k = qkv_ref[:, :, C:2 * C].reshape(nwin, D * 49, heads, hd).permute(0, 2, 1, 3)
+    v = qkv_ref[:, :, 2 * C:].reshape(nwin, D * 49, heads, hd).permute(0, 2, 1, 3)
+    a_ = torch.arange(7, device=DEV)
+    ai, bi = a_.repeat_interleave(7), a_.repeat(7)
+    rel = (ai[:, None] - ai[None, :] + 6) * 13 + (bi[:, None] - bi[None, :] + 6)
+    bias = torch.cat([tbl[:, d][:, rel] for d in range(D)], 2)
+    attn = torch.softmax(q @ k.transpose(-2, -1) + bias.unsqueeze(0), dim=-1)
+    o = (attn @ v).permute(0, 2, 1, 3).reshape(nwin * 49, C)
+    proj = o @ wproj.float().t() + bproj
+    ref = xs0.clone()
+    flat, kflat = idx.reshape(-1), keep.reshape(-1)
+    ref[flat[kflat]] += proj[kflat]
+    upd = float((ref - xs0).abs().max())
+    assert upd > 0.1
+    got = {}
+    for pers in ("0", "1"):
+        os.environ["BDE2VID_ATTN64_PERSIST"] = pers
+        try:
+            for rep in range(2):
+                xs = xs0.clone()
+                fr = list(frames)
+                fr[q_ind] = xs
+                ops.window_attention_fused(fr, q_ind, tm.view(-1), nwin, C, heads, wqkv, bqkv, tbl, wproj, bproj, xs=xs)
+                torch.cuda.synchronize()
+                if rep == 0:
+                    got[pers] = xs
+                else:
+                    assert torch.equal(xs, got[pers]), "persist %s: not deterministic" % pers
+        finally:
+            del os.environ["BDE2VID_ATTN64_PERSIST"]
+        err = float((got[pers] - ref).abs().max())
+        print("attn64 persist", pers, dilated, zero_frame, D, err, upd)
+        assert err <= 1.5e-2 * max(1.0, upd), (pers, err, upd)
+    assert torch.equal(got["0"], got["1"])
