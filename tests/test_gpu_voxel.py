@@ -271,3 +271,54 @@ def test_hot_pixel_mask_vs_oracle():
     xs, ys, ts, ps = synth.to_loader_format(ev, 0)
     _value_gate(got, ref, O.voxel_abs_mass(xs, ys, ts, ps, 5, (H, W)))
     assert not got[:, mask.cpu().numpy() == 0].any()
+
+
+@pytest.mark.parametrize("fmt", ["f32", "raw"])
+@pytest.mark.parametrize("H,W,pad", [(180, 240, (2, 0, 184, 240)), (37, 53, (1, 2, 40, 57))])
+def test_chunk_pipeline_many_chunks(monkeypatch, fmt, H, W, pad):
+    """The default algorithm as a chain of MANY chunks (1 MB chunks: one or a few windows each): every launch zeroes the next
+    chunk's grids and the launches are linked by programmatic dependent launch.  The destination starts as NaN garbage, some
+    windows are empty / below min_events (their grids must still be zeroed by the previous launch), the batch stride leaves
+    foreign grids between the windows untouched.  Equal to the one-chunk result (bit-exact on the zero pattern, value gate
+    otherwise), with PDL on and off, with in-kernel zeroing on and off; the odd 37 x 53 sensor padded to 40 x 57 covers rows
+    that are not multiples of 16 bytes."""
+    from bde2vid_b200 import ops
+    T, N, B = 23, 4000, 2
+    ev = synth.gen_events(5, T, H, W, N)
+    off = ev["offsets"].copy()
+    off[7] = off[6]                                        # window 6 empty
+    off[12] = off[11] + 2                                  # window 11: 2 events (< min_events 3 -> zeros)
+    ev = dict(ev, offsets=off)
+    xs, ys, ts, ps, _ = synth.to_loader_format_seq(ev)
+    pt, pl, Hp, Wp = pad
+    ge = 5 * Hp * Wp
+    if fmt == "f32":
+        args = [_dev(a) for a in (xs, ys, ts, ps)]
+    else:
+        args = [_dev(ev["xs"]), _dev(ev["ys"]), _dev(ev["ts"]), _dev(ev["ps"].view(np.uint8))]
+    results = {}
+    for name, env in (("one_chunk", {"BDE2VID_VOXEL_CHUNK_MB": "4096"}), ("chunks", {"BDE2VID_VOXEL_CHUNK_MB": "1"}),
+                      ("chunks_nopdl", {"BDE2VID_VOXEL_CHUNK_MB": "1", "BDE2VID_PDL": "0"}),
+                      ("chunks_memset", {"BDE2VID_VOXEL_CHUNK_MB": "1", "BDE2VID_VOXEL_ZERO_IN_KERNEL": "0"})):
+        for k in ("BDE2VID_VOXEL_CHUNK_MB", "BDE2VID_PDL", "BDE2VID_VOXEL_ZERO_IN_KERNEL"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        buf = torch.full((T, B, 5, Hp, Wp), float("nan"), device=DEV)
+        ops.voxelize_seq_into(*args, _dev(off), 5, H, W, pt, pl, Hp, Wp, buf[0, 1], B * ge, min_events=3)
+        torch.cuda.synchronize()
+        assert torch.isnan(buf[:, 0]).all()                # the other sequence's grids between the windows are untouched
+        results[name] = buf[:, 1].cpu().numpy()
+    ref = results["one_chunk"]
+    assert np.isfinite(ref).all() and not ref[6].any() and not ref[11].any() and ref[0].any()
+    for w in (0, 5, 22):
+        a, b = int(off[w]), int(off[w + 1])
+        full = np.zeros((5, Hp, Wp), np.float32)
+        full[:, pt:pt + H, pl:pl + W] = O.loader_voxel(ev["xs"][a:b], ev["ys"][a:b], ev["ts"][a:b], ev["ps"][a:b], 5, (H, W))
+        mass = np.zeros((5, Hp, Wp), np.float32)
+        mass[:, pt:pt + H, pl:pl + W] = O.voxel_abs_mass(xs[a:b], ys[a:b], ts[a:b], ps[a:b], 5, (H, W))
+        _value_gate(ref[w], full, mass)
+    for name in ("chunks", "chunks_nopdl", "chunks_memset"):
+        got = results[name]
+        assert np.array_equal(got == 0, ref == 0), name     # same zero pattern: nothing left unzeroed, nothing lost
+        assert np.abs(got - ref).max() <= 1e-5, name        # only the accumulation order of colliding events differs
