@@ -104,6 +104,18 @@ __device__ __forceinline__ void mma16816_f16(float (&d)[4], const uint32_t (&a)[
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// 1 / x and 1 / sqrt(x) as ONE MUFU op each (<= 1-2 ulp; the results are rounded to bf16 right after).  The IEEE forms cost a
+// MUFU + Newton step + range check + slow-path branch each: 3.4 % + 1.8 % of the level-1 kernel's stall samples (ncu source view)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ uint32_t pack2_h(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -352,7 +364,7 @@ __global__ void __launch_bounds__(kPers ? 2 * kThreadsF : kThreadsF, (C == 64 &&
         sq += __shfl_xor_sync(0xffffffffu, sq, 1);
         sq += __shfl_xor_sync(0xffffffffu, sq, 2);
         sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-        const float rstd = 1.0f / sqrtf(sq / (float)C + 1e-5f);
+        const float rstd = rsqrt_approx(sq / (float)C + 1e-5f);
 #pragma unroll
         for (int kb = 0; kb < NCH; ++kb) {
           uint4 pk;
@@ -592,7 +604,7 @@ __global__ void __launch_bounds__(kPers ? 2 * kThreadsF : kThreadsF, (C == 64 &&
         for (int e = 0; e < 4; ++e) oa[u][e] += ob[u][e];
         const float l0 = __shfl_xor_sync(0xffffffffu, oa[u][0], 2), l1 = __shfl_xor_sync(0xffffffffu, oa[u][2], 2);
         if ((t >> 1) == (hp & 1)) {
-          const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+          const float inv0 = rcp_approx(l0), inv1 = rcp_approx(l1);
           const int col = ((hp + 8 * u) >> 1) * 8 + 2 * t;
           *reinterpret_cast<uint32_t*>(os + row0 * PQ + col) = pack2(oa[u][0] * inv0, oa[u][1] * inv0);
           *reinterpret_cast<uint32_t*>(os + row1 * PQ + col) = pack2(oa[u][2] * inv1, oa[u][3] * inv1);
@@ -654,7 +666,7 @@ __global__ void __launch_bounds__(kPers ? 2 * kThreadsF : kThreadsF, (C == 64 &&
       for (int e = 0; e < 4; ++e) o4[e] += __shfl_xor_sync(0xffffffffu, o4[e], o);
     }
     if (sl == 0) {
-      const float inv = 1.0f / l;
+      const float inv = rcp_approx(l);
       uint2 pk;
       pk.x = pack2(o4[0] * inv, o4[1] * inv);
       pk.y = pack2(o4[2] * inv, o4[3] * inv);

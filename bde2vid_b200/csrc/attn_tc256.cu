@@ -131,6 +131,17 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+// one MUFU op each (see attn_fused.cu: the IEEE forms add a Newton step, a range check and a slow-path branch)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ uint32_t pack2_h(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -423,7 +434,7 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
         sq += __shfl_xor_sync(0xffffffffu, sq, 1);
         sq += __shfl_xor_sync(0xffffffffu, sq, 2);
         sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-        const float rstd = 1.0f / sqrtf(sq / (float)C + 1e-5f);
+        const float rstd = rsqrt_approx(sq / (float)C + 1e-5f);
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
@@ -618,7 +629,7 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
             }
           }
         }
-        const float inv0 = 1.0f / ol[0], inv1 = 1.0f / ol[2];
+        const float inv0 = rcp_approx(ol[0]), inv1 = rcp_approx(ol[2]);
         // attention output -> slab hg of the swizzled K-major O tile (token row, 64 channels of this head group)
         const uint32_t o_slab = sb + Cfg::OFF_O + l * (64 * 128);
 #pragma unroll
