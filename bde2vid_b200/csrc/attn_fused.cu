@@ -60,6 +60,14 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// K = 8 form: head_dim 4 fills half of it (lanes t >= 2 hold zeros); the K = 16 form needed two more zero registers per
+// operand, materialised with MOV / CS2R in front of every score tile (2.9 % of the level-1 kernel's instructions)
+__device__ __forceinline__ void mma1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -186,13 +194,16 @@ struct FusedCfg {
 
 // acc[mt][nt][4] += A[rows, C] (smem, pitch PX) * Wslice[64, C]^T (smem, pitch PX) for this warp's
 // (m-tile list, n-tile pair).  a_row(mt, r) gives the smem row of tile row r.
+// The accumulators start at (init0, init1): the bias of this lane's two column pairs (n-tile 0 / 1), or zero.
 template <int C, int PX, int MT, typename RowFn>
 __device__ __forceinline__ void warp_gemm(float (&acc)[MT][2][4], int n_mt, uint32_t a_base, RowFn a_row, uint32_t w_base,
-                                          int npair, int lane) {
+                                          int npair, int lane, float2 init0 = make_float2(0.f, 0.f),
+                                          float2 init1 = make_float2(0.f, 0.f)) {
 #pragma unroll
-  for (int i = 0; i < MT; ++i)
-#pragma unroll
-    for (int n = 0; n < 2; ++n) acc[i][n][0] = acc[i][n][1] = acc[i][n][2] = acc[i][n][3] = 0.f;
+  for (int i = 0; i < MT; ++i) {
+    acc[i][0][0] = acc[i][0][2] = init0.x; acc[i][0][1] = acc[i][0][3] = init0.y;
+    acc[i][1][0] = acc[i][1][2] = init1.x; acc[i][1][1] = acc[i][1][3] = init1.y;
+  }
   // B: matrices (n 0-7, k 0-7) (n 0-7, k 8-15) (n 8-15, k 0-7) (n 8-15, k 8-15)
   const int bm = lane >> 3;
   const uint32_t b_addr0 = w_base + (uint32_t)(((npair * 16 + (bm >> 1) * 8 + (lane & 7)) * PX + (bm & 1) * 8) * 2);
@@ -403,23 +414,22 @@ __global__ void __launch_bounds__(kPers ? 2 * kThreadsF : kThreadsF, (C == 64 &&
       float acc[2][2][4];
       const int qrow0 = p.q_slot * kTok;
       warp_gemm<C, PX, 2>(acc, 2, xn_u32, [&](int i, int r) { return min(qrow0 + (mh * 2 + i) * 16 + r, XROWS - 1); }, w_base,
-                          npair, lane);
+                          npair, lane, bia0, bia1);   // accumulators start at the bias
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int r0 = (mh * 2 + i) * 16 + g;
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
-          const float2 bb = n == 0 ? bia0 : bia1;
           const int col = npair * 16 + n * 8 + 2 * t;
-          *reinterpret_cast<uint32_t*>(qs + r0 * PQ + col) = pack2(acc[i][n][0] + bb.x, acc[i][n][1] + bb.y);
-          *reinterpret_cast<uint32_t*>(qs + (r0 + 8) * PQ + col) = pack2(acc[i][n][2] + bb.x, acc[i][n][3] + bb.y);
+          *reinterpret_cast<uint32_t*>(qs + r0 * PQ + col) = pack2(acc[i][n][0], acc[i][n][1]);
+          *reinterpret_cast<uint32_t*>(qs + (r0 + 8) * PQ + col) = pack2(acc[i][n][2], acc[i][n][3]);
         }
       }
     } else {
       float acc[MTK][2][4];
       const int mt0 = mh * MTK;
       const int n_mt = min(MTK, KSTEPS - mt0);
-      warp_gemm<C, PX, MTK>(acc, n_mt, xn_u32, [&](int i, int r) { return (mt0 + i) * 16 + r; }, w_base, npair, lane);
+      warp_gemm<C, PX, MTK>(acc, n_mt, xn_u32, [&](int i, int r) { return (mt0 + i) * 16 + r; }, w_base, npair, lane, bia0, bia1);
       __nv_bfloat16* dstm = which == 1 ? ks : vs;
       const int row_lim = which == 1 ? NKEY : XROWS;
 #pragma unroll
@@ -428,10 +438,9 @@ __global__ void __launch_bounds__(kPers ? 2 * kThreadsF : kThreadsF, (C == 64 &&
           const int r0 = (mt0 + i) * 16 + g;
 #pragma unroll
           for (int n = 0; n < 2; ++n) {
-            const float2 bb = n == 0 ? bia0 : bia1;
             const int col = npair * 16 + n * 8 + 2 * t;
             // k stays bf16 (q.k^T is a bf16 product); v is stored as fp16 for the fp16 P.V product
-            const float v00 = acc[i][n][0] + bb.x, v01 = acc[i][n][1] + bb.y, v10 = acc[i][n][2] + bb.x, v11 = acc[i][n][3] + bb.y;
+            const float v00 = acc[i][n][0], v01 = acc[i][n][1], v10 = acc[i][n][2], v11 = acc[i][n][3];
             if (r0 < row_lim) *reinterpret_cast<uint32_t*>(dstm + r0 * PQ + col) = which == 1 ? pack2(v00, v01) : pack2_hs(v00, v01);
             if (r0 + 8 < row_lim)
               *reinterpret_cast<uint32_t*>(dstm + (r0 + 8) * PQ + col) = which == 1 ? pack2(v10, v11) : pack2_hs(v10, v11);
@@ -545,8 +554,7 @@ __global__ void __launch_bounds__(kPers ? 2 * kThreadsF : kThreadsF, (C == 64 &&
                 if (j * 8 + 2 * t >= n_kv) s[u][jj][0] = s[u][jj][2] = -1e30f;
                 if (j * 8 + 2 * t + 1 >= n_kv) s[u][jj][1] = s[u][jj][3] = -1e30f;
               }
-              const uint32_t qa[4] = {qa0[u], qa1[u], 0u, 0u};
-              mma16816(s[u][jj], qa, kb[u], 0u);
+              mma1688(s[u][jj], qa0[u], qa1[u], kb[u]);
             }
           }
         }
