@@ -58,9 +58,10 @@ struct TCfg {
   static constexpr int OFF_RING = OFF_XN + 4 * XN_SLAB;
   static constexpr int OFF_O = OFF_RING + kStages * kStageBytes;        // 4 slabs x [64 rows x 128 B]
   static constexpr int OFF_Q = OFF_O + 4 * 64 * 128;
+  static constexpr int PT = XROWS + 8;            // token pitch of the channel-major k / v tiles [64][PT]
   static constexpr int OFF_K = OFF_Q + 64 * PQ * 2;
-  static constexpr int OFF_V = OFF_K + NKEY * PQ * 2;
-  static constexpr int OFF_TBL = OFF_V + XROWS * PQ * 2;
+  static constexpr int OFF_V = OFF_K + 64 * PT * 2;
+  static constexpr int OFF_TBL = OFF_V + 64 * PT * 2;
   static constexpr int OFF_COFF = OFF_TBL + HG * DMAX * kRel * 4;
   static constexpr int OFF_ROFF = OFF_COFF + NKEY * 4;
   static constexpr int OFF_PIX = OFF_ROFF + 256;
@@ -147,6 +148,21 @@ __device__ __forceinline__ uint32_t pack2_h(float lo, float hi) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// v tiles: values beyond the fp16 range saturate at +-65504 instead of becoming inf
+__device__ __forceinline__ uint32_t pack2_hs(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+// k / v tiles of a head group stay CHANNEL-major, [64 channels][PT tokens] -- the layout the transposed projections leave in
+// TMEM (lane = channel, column = token): a thread packs 8 consecutive tokens of its channel into ONE 16-byte store (the
+// token-major tiles cost a convert + a 2-byte store per element: 15 % of the kernel's instructions, ncu source view), and the
+// B fragments of both products come out of ldmatrix: .trans for q k^T (rows = 16 channels of the head, 8 tokens each), plain
+// for P v (rows = 8 channels, 2 x 8 tokens).  Token pitch Cfg::PT = XROWS + 8 (336-byte rows for D = 3): 16-byte aligned and
+// conflict-free for 8-row ldmatrix phases.
 __device__ __forceinline__ uint32_t ex2_h2(float lo, float hi) {
   float a, b;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(lo));
@@ -466,7 +482,7 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
       tc_cluster_wait();
     }
 
-    const uint32_t vs_u32 = sb + Cfg::OFF_V, tbl_u32 = sb + Cfg::OFF_TBL, coff_u32 = sb + Cfg::OFF_COFF;
+    const uint32_t ks_u32 = sb + Cfg::OFF_K, vs_u32 = sb + Cfg::OFF_V, tbl_u32 = sb + Cfg::OFF_TBL, coff_u32 = sb + Cfg::OFF_COFF;
     constexpr uint32_t kOnes = 0x3C003C00u;
     constexpr float kLog2e = 1.4426950408889634f;
     const int qd = warp & 3, part = warp >> 2;                   // TMEM lane quarter of this warp, column-chunk phase
@@ -494,7 +510,6 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
         const int ch = (qd & 1) * 32 + lane;
         const float bias = bias_s[(is_k ? C : 2 * C) + hg * 64 + ch];
         __nv_bfloat16* dstm = is_k ? ks : vs;
-        const int row_lim = is_k ? NKEY : XROWS;
         constexpr int NCH = (XROWS / 8 + 3) / 4;       // 8-token column chunks per warp (chunk c8 = part + 4 i)
         uint32_t raw[NCH][8];
         const bool has_q = (qd >> 1) == (hg & 1);
@@ -510,16 +525,17 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
         for (int i = 0; i < NCH; ++i) {
           const int c8 = part + 4 * i;
           if (c8 < XROWS / 8) {
+            float val[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int tok = c8 * 8 + e;
-              const float val = __uint_as_float(raw[i][e]) + bias;
-              if (tok < row_lim) {
-                // k stays bf16 (q.k^T is a bf16 product); v is fp16 for the fp16 P.V product
-                if (is_k) dstm[tok * PQ + ch] = __float2bfloat16_rn(val);
-                else reinterpret_cast<__half*>(dstm)[tok * PQ + ch] = __float2half_rn(fminf(fmaxf(val, -65504.0f), 65504.0f));   // saturate, never inf
-              }
+            for (int e = 0; e < 8; ++e) val[e] = __uint_as_float(raw[i][e]) + bias;
+            // k stays bf16 (q.k^T is a bf16 product); v is fp16 for the fp16 P.V product
+            uint4 pk;
+            if (is_k) {
+              pk.x = pack2(val[0], val[1]); pk.y = pack2(val[2], val[3]); pk.z = pack2(val[4], val[5]); pk.w = pack2(val[6], val[7]);
+            } else {
+              pk.x = pack2_hs(val[0], val[1]); pk.y = pack2_hs(val[2], val[3]); pk.z = pack2_hs(val[4], val[5]); pk.w = pack2_hs(val[6], val[7]);
             }
+            *reinterpret_cast<uint4*>(dstm + ch * Cfg::PT + c8 * 8) = pk;   // tokens [8 c8, 8 c8 + 8) of channel ch
           }
         }
         // Q^T tile hg / 2, lanes (hg & 1) * 64 + channel, columns = the 64 staged query tokens
@@ -578,9 +594,8 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
                 if (j * 8 + 2 * t >= n_kv) s[jj][0] = s[jj][2] = -1e30f;
                 if (j * 8 + 2 * t + 1 >= n_kv) s[jj][1] = s[jj][3] = -1e30f;
               }
-              const __nv_bfloat16* kr = ks + (j * 8 + g) * PQ + hl * HD;
-              const uint32_t kb0 = *reinterpret_cast<const uint32_t*>(kr + 2 * t);
-              const uint32_t kb1 = *reinterpret_cast<const uint32_t*>(kr + 2 * t + 8);
+              uint32_t kb0, kb1;   // (channels 2t, 2t + 1 | 8 + 2t, 9 + 2t of the head; token 8 j + g)
+              ldsm_x2_trans(kb0, kb1, ks_u32 + (uint32_t)(((hl * HD + (lane & 15)) * Cfg::PT + j * 8) * 2));
               mma16816(s[jj], qa, kb0, kb1);
             }
           }
@@ -622,7 +637,7 @@ attn_win256_tc_kernel(const __grid_constant__ CUtensorMap tmap_wqkv, const __gri
 #pragma unroll
               for (int v = 0; v < 2; ++v) {
                 uint32_t vb0, vb1;
-                ldsm_x2_trans(vb0, vb1, vs_u32 + (uint32_t)(((kk * 16 + (lane & 15)) * PQ + hl * HD + 8 * v) * 2));
+                ldsm_x2(vb0, vb1, vs_u32 + (uint32_t)(((hl * HD + 8 * v + (lane & 7)) * Cfg::PT + kk * 16 + ((lane >> 3) & 1) * 8) * 2));
                 mma16816_f16(o[v], pa, vb0, vb1);
               }
               mma16816_f16(ol, pa, kOnes, kOnes);   // row sums
