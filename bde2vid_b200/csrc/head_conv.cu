@@ -57,35 +57,49 @@ __global__ void __launch_bounds__(kHcThreads, 2) head_conv_kernel(const HeadConv
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int x0 = blockIdx.x * kHcTW, y0 = blockIdx.y * kHcTH, n = blockIdx.z;
+  const int x0 = blockIdx.x * kHcTW, y0 = blockIdx.y * kHcTH;
   const int H = p.h, W = p.w_px;
 
-  // ---- weights -> smem (bf16 pairs; zero for kx >= 5 and channels >= cin) ----
-  for (int i = tid; i < kHcSteps * kHcCout * 8; i += kHcThreads) {
-    const int j = i & 7, co = (i >> 3) % kHcCout, step = i / (8 * kHcCout);
-    const int ky = step / kHcPairs, c = 2 * (step - ky * kHcPairs) + (j >> 2);
+  // ---- weights -> smem (bf16 pairs; zero for kx >= 5 and channels >= cin), ONCE per CTA: the CTA then walks the images
+  // n = blockIdx.z, blockIdx.z + gridDim.z, ... of its tile position (staging them per image was a third of the kernel) ----
+  {
+    const int j = tid & 7, co = tid >> 3;      // 32 output channels x 8 words = 256 threads
     const int kx = 2 * (j & 3);
-    float w0 = 0.f, w1 = 0.f;
-    if (c < p.cin) {
-      const float* wr = p.w + ((size_t)(co * p.cin + c) * kHcK + ky) * kHcK;
-      if (kx < kHcK) w0 = __ldg(wr + kx);
-      if (kx + 1 < kHcK) w1 = __ldg(wr + kx + 1);
+    for (int step = 0; step < kHcSteps; ++step) {
+      const int ky = step / kHcPairs, c = 2 * (step - ky * kHcPairs) + (j >> 2);
+      float w0 = 0.f, w1 = 0.f;
+      if (c < p.cin) {
+        const float* wr = p.w + ((size_t)(co * p.cin + c) * kHcK + ky) * kHcK;
+        if (kx < kHcK) w0 = __ldg(wr + kx);
+        if (kx + 1 < kHcK) w1 = __ldg(wr + kx + 1);
+      }
+      wk[step][co][j] = pack_bf16x2(w0, w1);
     }
-    wk[step][co][j] = pack_bf16x2(w0, w1);
   }
   if (tid < kHcCout) bias_s[tid] = p.bias != nullptr ? __ldg(p.bias + tid) : 0.f;
+  // 8-byte loads of (v[x], v[x + 1]): x0 - 2 is even, so rows must start 8-byte aligned
+  const bool vec_ok = (W % 2 == 0) && ((((uintptr_t)p.vox) & 7) == 0);
 
-  // ---- input tile + halo -> smem as pairs (zero outside the image / beyond cin) ----
-  for (int i = tid; i < 2 * kHcPairs * kHcRows * kHcPitch; i += kHcThreads) {
-    const int col = i % kHcPitch, row = (i / kHcPitch) % kHcRows, c = i / (kHcPitch * kHcRows);
-    const int y = y0 - kHcPad + row, x = x0 - kHcPad + col;
+  for (int n = blockIdx.z; n < p.n_img; n += gridDim.z) {
+  // ---- input tile + halo -> smem as pairs (zero outside the image / beyond cin): one warp per (channel, halo row), lane l
+  // loads v[2l], v[2l + 1], takes v[2l + 2] from its neighbour and stores the pair columns 2l and 2l + 1 ----
+  for (int r = warp; r < 2 * kHcPairs * kHcRows; r += kHcThreads / 32) {
+    const int c = r / kHcRows, row = r - c * kHcRows;
+    const int y = y0 - kHcPad + row, x = x0 - kHcPad + 2 * lane;
     float v0 = 0.f, v1 = 0.f;
-    if (c < p.cin && y >= 0 && y < H) {
+    if (c < p.cin && y >= 0 && y < H && lane < kHcPitch / 2 + 1) {
       const float* src = p.vox + ((size_t)(n * p.cin + c) * H + y) * W;
-      if (x >= 0 && x < W) v0 = __ldg(src + x);
-      if (x + 1 >= 0 && x + 1 < W) v1 = __ldg(src + x + 1);
+      if (vec_ok && x >= 0 && x + 1 < W) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(src + x));
+        v0 = v.x; v1 = v.y;
+      } else {
+        if (x >= 0 && x < W) v0 = __ldg(src + x);
+        if (x + 1 >= 0 && x + 1 < W) v1 = __ldg(src + x + 1);
+      }
     }
-    pairs[c][row][col] = pack_bf16x2(v0, v1);
+    const float vn = __shfl_down_sync(0xffffffffu, v0, 1);
+    if (lane < kHcPitch / 2)
+      *reinterpret_cast<uint2*>(&pairs[c][row][2 * lane]) = make_uint2(pack_bf16x2(v0, v1), pack_bf16x2(v1, vn));
   }
   __syncthreads();
 
@@ -137,6 +151,8 @@ __global__ void __launch_bounds__(kHcThreads, 2) head_conv_kernel(const HeadConv
       }
     }
   }
+  __syncthreads();   // every warp is done with this image's halo tile before the next one overwrites it
+  }  // image loop
 }
 
 }  // namespace
@@ -157,7 +173,11 @@ extern "C" int bde_head_conv(const float* vox, const float* w, const float* bias
   p.n_img = n_img; p.cin = cin; p.h = h; p.w_px = w_px;
   p.lo = act == BDE_ACT_NONE ? -INFINITY : 0.f;
   p.hi = act == BDE_ACT_RELU6 ? 6.f : INFINITY;
-  dim3 grid((unsigned)ceil_div(w_px, kHcTW), (unsigned)ceil_div(h, kHcTH), (unsigned)n_img);
+  // CTAs walk the images of their tile position (weights staged once per CTA): enough CTAs in z for ~8 waves of two per SM
+  const int tiles = ceil_div(w_px, kHcTW) * ceil_div(h, kHcTH);
+  int gz = ceil_div(device_sm_count() * 2 * 8, tiles);
+  gz = gz < 1 ? 1 : (gz > n_img ? n_img : gz);
+  dim3 grid((unsigned)ceil_div(w_px, kHcTW), (unsigned)ceil_div(h, kHcTH), (unsigned)gz);
   head_conv_kernel<<<grid, kHcThreads, 0, (cudaStream_t)stream>>>(p);
   return check_launch("head_conv_kernel");
 }
