@@ -85,53 +85,66 @@ __device__ __forceinline__ void load8f<__nv_bfloat16>(const __nv_bfloat16* p, fl
   }
 }
 
+// Thread = (input column, 8 channels); the block walks kUpRows input rows with a ROLLING window of three summed rows
+// (x * scale + skip, columns prev / this / next) in registers: 6 vector loads per input row instead of the 18 of the
+// one-row-per-thread form, which re-fetched and re-summed the whole 3 x 3 neighbourhood for every input pixel.
+constexpr int kUpRows = 8;
 template <typename TS, typename TX>
 __global__ void __launch_bounds__(256) upsample2x_sum_block_kernel(const TS* __restrict__ skip, const TX* __restrict__ x, float x_scale,
                                                                      int h, int w, int c8, __nv_bfloat16* __restrict__ dst) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over w * c8 of one input row
   if (idx >= w * c8) return;
   const int ix = idx / c8, cq = idx - ix * c8;
-  const int iy = blockIdx.y, img = blockIdx.z;
+  const int iy0 = blockIdx.y * kUpRows, img = blockIdx.z;
+  const int iy1 = min(iy0 + kUpRows, h);
   const int c = c8 * 8;
-  // source rows / columns: (prev, this, next) clamped
-  const int ys[3] = {max(iy - 1, 0), iy, min(iy + 1, h - 1)};
-  const int xs[3] = {max(ix - 1, 0), ix, min(ix + 1, w - 1)};
-  float v[3][3][8];
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
+  const int xs[3] = {max(ix - 1, 0), ix, min(ix + 1, w - 1)};   // source columns (prev, this, next), clamped
+  auto load_row = [&](int r, float (&row)[3][8]) {
+    r = min(max(r, 0), h - 1);
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
-      const size_t o = (((size_t)img * h + ys[a]) * w + xs[b]) * (size_t)c + cq * 8;
-      load8f<TX>(x + o, v[a][b]);
+      const size_t o = (((size_t)img * h + r) * w + xs[b]) * (size_t)c + cq * 8;
+      load8f<TX>(x + o, row[b]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[a][b][e] *= x_scale;
+      for (int e = 0; e < 8; ++e) row[b][e] *= x_scale;
       if (skip != nullptr) {
         float sk[8];
         load8f<TS>(skip + o, sk);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[a][b][e] += sk[e];
+        for (int e = 0; e < 8; ++e) row[b][e] += sk[e];
       }
     }
-  // output (2 iy + dy, 2 ix + dx): dy = 0 -> rows (prev .25, this .75); dy = 1 -> rows (this .75, next .25); same for columns
+  };
+  float v[3][3][8];   // rows (prev, this, next) x columns (prev, this, next)
+  load_row(iy0 - 1, v[0]);
+  load_row(iy0, v[1]);
+  for (int iy = iy0; iy < iy1; ++iy) {
+    load_row(iy + 1, v[2]);
+    // output (2 iy + dy, 2 ix + dx): dy = 0 -> rows (prev .25, this .75); dy = 1 -> rows (this .75, next .25); same for columns
 #pragma unroll
-  for (int dy = 0; dy < 2; ++dy)
+    for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-    for (int dx = 0; dx < 2; ++dx) {
-      const int y0 = dy, y1 = dy + 1, x0 = dx, x1 = dx + 1;   // indices into the 3 x 3 neighbourhood
-      const float wy0 = dy ? 0.75f : 0.25f, wy1 = dy ? 0.25f : 0.75f;
-      const float wx0 = dx ? 0.75f : 0.25f, wx1 = dx ? 0.25f : 0.75f;
-      float o[8];
+      for (int dx = 0; dx < 2; ++dx) {
+        const int y0 = dy, y1 = dy + 1, x0 = dx, x1 = dx + 1;   // indices into the 3 x 3 neighbourhood
+        const float wy0 = dy ? 0.75f : 0.25f, wy1 = dy ? 0.25f : 0.75f;
+        const float wx0 = dx ? 0.75f : 0.25f, wx1 = dx ? 0.25f : 0.75f;
+        float o[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        o[e] = wy0 * (wx0 * v[y0][x0][e] + wx1 * v[y0][x1][e]) + wy1 * (wx0 * v[y1][x0][e] + wx1 * v[y1][x1][e]);
-      uint4 pk;
-      __nv_bfloat162 t0 = __floats2bfloat162_rn(o[0], o[1]), t1 = __floats2bfloat162_rn(o[2], o[3]);
-      __nv_bfloat162 t2 = __floats2bfloat162_rn(o[4], o[5]), t3 = __floats2bfloat162_rn(o[6], o[7]);
-      pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
-      pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
-      const size_t op = (((size_t)img * 2 * h + (2 * iy + dy)) * (2 * w) + (2 * ix + dx)) * (size_t)c + cq * 8;
-      *reinterpret_cast<uint4*>(dst + op) = pk;
-    }
+        for (int e = 0; e < 8; ++e)
+          o[e] = wy0 * (wx0 * v[y0][x0][e] + wx1 * v[y0][x1][e]) + wy1 * (wx0 * v[y1][x0][e] + wx1 * v[y1][x1][e]);
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(o[0], o[1]), t1 = __floats2bfloat162_rn(o[2], o[3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(o[4], o[5]), t3 = __floats2bfloat162_rn(o[6], o[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        const size_t op = (((size_t)img * 2 * h + (2 * iy + dy)) * (2 * w) + (2 * ix + dx)) * (size_t)c + cq * 8;
+        *reinterpret_cast<uint4*>(dst + op) = pk;
+      }
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { v[0][b][e] = v[1][b][e]; v[1][b][e] = v[2][b][e]; }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -389,7 +402,7 @@ static int launch_upsample(const void* skip, int skip_f32, const void* x, int x_
   T* d = (T*)dst;
   if (sizeof(T) == 2 && c % 8 == 0 && h <= 65535 && n_img <= 65535) {
     // block form (bf16 output): thread = input pixel x 8 channels
-    dim3 grid((unsigned)ceil_div((size_t)w * (c / 8), 256), (unsigned)h, (unsigned)n_img);
+    dim3 grid((unsigned)ceil_div((size_t)w * (c / 8), 256), (unsigned)ceil_div(h, kUpRows), (unsigned)n_img);
     __nv_bfloat16* db = (__nv_bfloat16*)dst;
     if (skip_f32 && x_f32)
       upsample2x_sum_block_kernel<float, float><<<grid, 256, 0, s>>>((const float*)skip, (const float*)x, x_scale, h, w, c / 8, db);
