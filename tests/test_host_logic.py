@@ -141,3 +141,29 @@ def test_e2vid_state_dict_keys_match_reference(manifest):
     assert list(sd.keys()) == rec["keys"]
     assert [list(v.shape) for v in sd.values()] == rec["shapes"]
     assert m.num_encoders == 4
+
+
+def test_bench_contract_without_gpu():
+    """bench.py / bench_configs.py import cleanly, every --config has its runner, the product arm refuses to run without a
+    CUDA device (no CPU fallback), and the reference arm prints one JSON line with the contract's keys on a tiny sample."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import bench
+    import bench_configs
+    for cfg in ("e2vid16", "gen4", "shard64", "pair"):
+        assert callable(getattr(bench_configs, "run_" + cfg))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True,
+                           text=True, cwd=root)
+        assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-windows", "2"], capture_output=True, text=True, cwd=root, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["value"] > 0
+    assert getattr(bench, "VOXEL_BYTES_PER_WINDOW") == 16 * 31500 + 4 * 5 * 260 * 346
